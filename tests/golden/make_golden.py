@@ -1,0 +1,259 @@
+"""
+Generates tests/golden/*.json|*.npz by running the UNMODIFIED reference
+(/root/reference, importable only in the build container) on deterministic
+weights and inputs.  The committed fixtures are what pins oracle/nasrec_oracle.py
+and the CUDA path; nothing at test time reads /root/reference.
+
+    python tests/golden/make_golden.py            # regenerate everything
+
+Weights come from oracle.fill_state_dict(shapes, seed) (copied INTO the
+reference model), inputs from oracle.synth_batch(seed) -- both regenerate
+bit-identically on any box, so the fixtures only hold shapes, choices and the
+reference's outputs (logits, loss, per-tensor grad norms, a few small grads).
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+# shims: fvcore is imported at module scope by train_utils
+fv = types.ModuleType("fvcore"); fvnn = types.ModuleType("fvcore.nn"); fvnn.FlopCountAnalysis = object
+fv.nn = fvnn; sys.modules["fvcore"] = fv; sys.modules["fvcore.nn"] = fvnn
+np.int = int
+
+from nasrec.supernet.supernet import SuperNet, ops_config_lib          # noqa: E402  (reference)
+from nasrec.searcher.tokenizer import Tokenizer                          # noqa: E402  (reference)
+from oracle import nasrec_oracle as orc                                   # noqa: E402
+
+DATASETS = {
+    "criteo": dict(nd=13, F=26, ne=[1461, 584, 10131227, 2202609, 306, 25, 12518, 634, 4, 93146, 5684, 8351593,
+                                    3195, 28, 14993, 5461307, 11, 5653, 2174, 5, 7046548, 19, 16, 286182, 106, 142573]),
+    "avazu": dict(nd=1, F=23, ne=[10000, 241, 8, 8, 4738, 7746, 27, 8553, 560, 37, 2686409, 6729487, 8252, 6, 5,
+                                  2627, 9, 10, 436, 5, 69, 173, 61]),
+    "kdd": dict(nd=3, F=10, ne=[26274, 641708, 14848, 22122011, 1188090, 3735797, 2934102, 20004011, 4, 8]),
+}
+ROW_CAP = 40   # tiny tables: the fixtures pin arithmetic, not capacity
+
+
+def jsonable(o):
+    if isinstance(o, dict):
+        return {k: jsonable(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [jsonable(v) for v in o]
+    if isinstance(o, np.ndarray):
+        return [jsonable(v) for v in o.tolist()]
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    return o
+
+
+def build(ds, ops, ln, fixed=False, choice=None, strategy="full-path", anypath="uniform", steps=0):
+    D = DATASETS[ds]
+    ne = [min(n, ROW_CAP) for n in D["ne"]]
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib[ops], use_layernorm=ln, num_embeddings=ne,
+                 sparse_input_size=D["F"], path_sampling_strategy="fixed-path" if fixed else strategy,
+                 fixed=fixed, fixed_choice=choice, anypath_choice=anypath, supernet_training_steps=steps)
+    int_x, cat_x, _ = orc.synth_batch(2, D["nd"], ne, seed=7, all_zero_dense=(ds == "avazu"))
+    with torch.no_grad():
+        m(int_x, cat_x)                       # lazy warm-up (train_utils.py:413-433)
+    return m, ne
+
+
+def load_filled(m, seed):
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = orc.fill_state_dict(shapes, seed)
+    m.load_state_dict(sd, strict=True)
+    return shapes
+
+
+def run_case(m, ne, ds, choice, B, seed, fixed):
+    D = DATASETS[ds]
+    int_x, cat_x, y = orc.synth_batch(B, D["nd"], ne, seed=seed, all_zero_dense=(ds == "avazu"))
+    if not fixed:
+        m.configure_choice(choice)
+        m.configure_path_sampling_strategy("fixed-path")
+    m.zero_grad()
+    logits = m(int_x, cat_x)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)
+    loss.backward()
+    gn = {n: float(p.grad.double().norm()) for n, p in m.named_parameters() if p.grad is not None}
+    small = {n: p.grad.numpy().copy() for n, p in m.named_parameters()
+             if p.grad is not None and p.grad.numel() <= 4096 and not n.startswith("_embedding")}
+    emb_rows = {str(f): np.nonzero(np.abs(m._embedding[f].weight.grad.numpy()).sum(1))[0].tolist()
+                for f in range(D["F"])}
+    return dict(logits=logits.detach().numpy().copy(), loss=float(loss), grad_norms=gn, small_grads=small,
+                emb_rows=emb_rows)
+
+
+def sample_choices(ds, ops, strategy, anypath, seed, n, exhausted=True, steps=15000):
+    """Reference samplers (supernet.py:432-511, 1009-1061) -> recorded choices."""
+    m, ne = build(ds, ops, True, strategy="full-path", anypath=anypath, steps=steps)
+    m.configure_path_sampling_strategy(strategy)
+    if exhausted:
+        m._supernet_train_steps_counter = steps + 5
+        for b in m._blocks:
+            b._supernet_train_steps_counter = steps + 5
+    D = DATASETS[ds]
+    int_x, cat_x, _ = orc.synth_batch(2, D["nd"], ne, seed=3, all_zero_dense=(ds == "avazu"))
+    np.random.seed(seed)
+    out = []
+    with torch.no_grad():
+        for _ in range(n):
+            m(int_x, cat_x)
+            out.append(jsonable(m.choice))
+    return out
+
+
+def save(name, meta, arrays):
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    print("wrote", name, "arrays:", len(arrays))
+
+
+def supernet_fixture(name, ds, ops, nchoices, B=5):
+    m, ne = build(ds, ops, True)
+    shapes = load_filled(m, seed=11)
+    cfg = dict(ops=ops, use_layernorm=True, fixed=False, num_blocks=7)
+    choices = [orc.full_path_choice(cfg)]
+    choices += sample_choices(ds, ops, "default", "binomial-0.5", seed=0, n=nchoices)
+    choices += sample_choices(ds, ops, "any-path", "uniform", seed=1, n=nchoices)
+    meta = dict(dataset=ds, cfg=cfg, num_embeddings=ne, nd=DATASETS[ds]["nd"], state_seed=11, batch=B,
+                shapes={k: list(v) for k, v in shapes.items()}, cases=[])
+    arrays = {}
+    for ci, ch in enumerate(choices):
+        r = run_case(m, ne, ds, ch, B, seed=100 + ci, fixed=False)
+        meta["cases"].append(dict(choice=ch, batch_seed=100 + ci, loss=r["loss"], grad_norms=r["grad_norms"],
+                                  emb_rows=r["emb_rows"]))
+        arrays["logits_%d" % ci] = r["logits"]
+        for n_, g in r["small_grads"].items():
+            if n_.startswith("_final") or "._nodes.4._mha" in n_ or "_ln" in n_ or "layernorm" in n_:
+                arrays["grad_%d/%s" % (ci, n_)] = g
+    save(name, meta, arrays)
+
+
+def fixed_fixture():
+    cfgdir = "/root/reference/nasrec/configs"
+    files = {
+        "criteo_xlarge": ("criteo", "criteo/ea_criteo_kaggle_xlarge_best_1shot.json"),
+        "criteo_autoctr": ("criteo", "criteo/ea_criteo_kaggle_autoctr_best_1shot.json"),
+        "avazu_xlarge": ("avazu", "avazu/ea_avazu_kaggle_xlarge_best_1shot.json"),
+        "avazu_autoctr": ("avazu", "avazu/ea_avazu_kaggle_autoctr_best_1shot.json"),
+        "kdd_xlarge": ("kdd", "kdd/ea_kdd_kaggle_xlarge_best_1shot.json"),
+        "kdd_autoctr": ("kdd", "kdd/ea_kdd_kaggle_autoctr_best_1shot.json"),
+    }
+    meta = dict(models={})
+    arrays = {}
+    for key, (ds, rel) in files.items():
+        choice = json.load(open(os.path.join(cfgdir, rel)))
+        for ln in ([False, True] if key == "criteo_xlarge" else [False]):   # main_train.py:262 forces False
+            tag = key + ("_ln" if ln else "")
+            m, ne = build(ds, choice["config"], ln, fixed=True, choice=choice)
+            shapes = load_filled(m, seed=5)
+            r = run_case(m, ne, ds, choice, 6, seed=42, fixed=True)
+            meta["models"][tag] = dict(dataset=ds, choice=jsonable(choice), num_embeddings=ne, nd=DATASETS[ds]["nd"],
+                                       cfg=dict(ops=choice["config"], use_layernorm=ln, fixed=True, num_blocks=7),
+                                       state_seed=5, batch=6, batch_seed=42, loss=r["loss"],
+                                       shapes={k: list(v) for k, v in shapes.items()},
+                                       grad_norms=r["grad_norms"], emb_rows=r["emb_rows"],
+                                       dense_params=int(sum(p.numel() for n, p in m.named_parameters()
+                                                            if not n.startswith("_embedding"))))
+            arrays["logits/" + tag] = r["logits"]
+            for n_, g in r["small_grads"].items():
+                if n_.startswith("_final") or "_mha" in n_:
+                    arrays["grad/%s/%s" % (tag, n_)] = g
+    save("fixed_best", meta, arrays)
+
+
+def step_fixture():
+    """3 reference training steps (train_utils.py:262-286) on an autoctr and an
+    xlarge supernet: Adagrad(lr, eps=1e-2) + clip 5.0, dense embedding grads."""
+    meta = dict(runs={})
+    arrays = {}
+    for tag, ops, lr in (("autoctr", "autoctr", 0.12), ("xlarge", "xlarge", 0.12)):
+        m, ne = build("criteo", ops, True)
+        shapes = load_filled(m, seed=21)
+        choices = sample_choices("criteo", ops, "default", "binomial-0.5", seed=4, n=3)
+        opt = torch.optim.Adagrad(m.parameters(), lr=lr, eps=1e-2)
+        m.configure_path_sampling_strategy("fixed-path")
+        losses, norms = [], []
+        for si, ch in enumerate(choices):
+            int_x, cat_x, y = orc.synth_batch(8, 13, ne, seed=300 + si)
+            m.configure_choice(ch)
+            opt.zero_grad()
+            logits = m(int_x, cat_x)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)
+            loss.backward()
+            tn = torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+            opt.step()
+            losses.append(float(loss)); norms.append(float(tn))
+            arrays["%s/logits_%d" % (tag, si)] = logits.detach().numpy().copy()
+        sd = m.state_dict()
+        checks = {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in sd.items()}
+        arrays[tag + "/final_weight"] = sd["_final.weight"].numpy().copy()
+        arrays[tag + "/emb0"] = sd["_embedding.0.weight"].numpy().copy()
+        meta["runs"][tag] = dict(cfg=dict(ops=ops, use_layernorm=True, fixed=False, num_blocks=7), lr=lr,
+                                 num_embeddings=ne, state_seed=21, choices=choices, losses=losses,
+                                 total_norms=norms, checksums=checks,
+                                 shapes={k: list(v) for k, v in shapes.items()})
+    save("train_steps", meta, arrays)
+
+
+def sampler_fixture():
+    """RNG-order goldens: what the reference draws from numpy's
+    global legacy RNG, forward by forward."""
+    meta = dict(streams=[])
+    for ops in ("xlarge", "autoctr", "xlarge-zeros"):
+        for strategy, anypath in (("default", "binomial-0.5"), ("default", "uniform"), ("single-path", "uniform"),
+                                  ("any-path", "binomial-0.5"), ("any-path", "uniform")):
+            for exhausted in (True, False):
+                for seed in (0, 5):
+                    ch = sample_choices("criteo", ops, strategy, anypath, seed, n=4, exhausted=exhausted, steps=6)
+                    meta["streams"].append(dict(ops=ops, strategy=strategy, anypath=anypath, exhausted=exhausted,
+                                                seed=seed, steps=6, choices=ch))
+    # fixed-path sampled once, then frozen (supernet.py:476-491, 1035-1048)
+    m, ne = build("criteo", "xlarge", True)
+    m.configure_path_sampling_strategy("fixed-path")
+    int_x, cat_x, _ = orc.synth_batch(2, 13, ne, seed=3)
+    np.random.seed(9)
+    with torch.no_grad():
+        m(int_x, cat_x); c1 = jsonable(m.choice); m(int_x, cat_x); c2 = jsonable(m.choice)
+    assert c1 == c2
+    meta["fixed_path_seed9"] = c1
+    # EA candidate generator (tokenizer.py:267-336) -- defines config #3's candidates
+    meta["ea_candidates"] = {}
+    for ops in ("xlarge", "autoctr"):
+        tok = Tokenizer(7, ops_config_lib[ops])
+        np.random.seed(1234)
+        meta["ea_candidates"][ops] = [jsonable(tok.generate_random_choice()) for _ in range(6)]
+    with open(os.path.join(HERE, "samplers.json"), "w") as f:
+        json.dump(meta, f)
+    print("wrote samplers")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps"]
+    if "samplers" in which:
+        sampler_fixture()
+    if "fixed" in which:
+        fixed_fixture()
+    if "autoctr" in which:
+        supernet_fixture("supernet_autoctr_criteo", "criteo", "autoctr", nchoices=3)
+    if "xlarge" in which:
+        supernet_fixture("supernet_xlarge_criteo", "criteo", "xlarge", nchoices=3)
+    if "kdd" in which:
+        supernet_fixture("supernet_xlarge_kdd", "kdd", "xlarge", nchoices=2)
+    if "steps" in which:
+        step_fixture()
