@@ -1,0 +1,210 @@
+/*
+ * nasrec_b200 -- C ABI of the B200-native NASRec supernet hot path.
+ *
+ * Drop-in boundary: these are the entry points a binding
+ * inside the reference's nasrec/supernet/{supernet,modules}.py would call
+ * instead of its eager PyTorch ops.  Plain device pointers, sizes and a
+ * cudaStream_t (passed as void*); no torch types.  Every function
+ *   - launches asynchronously on `stream`, never synchronises, never allocates,
+ *   - returns 0 on success, a cudaError_t (> 0) for a CUDA failure, or a
+ *     negative NASREC_E* code for a rejected argument (nothing is launched),
+ *   - is CUDA-graph capturable.
+ * All floating-point data is fp32, indices are int64 (as the reference's
+ * cat_feats), row-major.  "Citations" name the reference code each entry point
+ * replaces (paths relative to the NasRec repository root).
+ *
+ * Data model.  A block output is stored *compact*: dense [B, d] holds only the
+ * d live columns of the reference's zero-masked [B, 1024]; sparse
+ * [B, s (+8), 16] holds the s live rows (+ the 8 dense->sparse merger rows).
+ * A module input (the reference's zero-padded torch.cat of earlier outputs,
+ * supernet.py:530-573) is therefore a *segment list*: for every selected
+ * source, where it lives and which columns of the weight's K axis it meets.
+ */
+#ifndef NASREC_B200_H
+#define NASREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NASREC_MAX_SEGS 16
+#define NASREC_EMB_DIM 16          /* supernet.py:224 embedding_dim */
+#define NASREC_ATTN_PARAMS 1696    /* floats in one Transformer node's 16-wide parameter pack */
+
+#define NASREC_EINVAL (-1)         /* bad argument (null pointer, size out of range) */
+#define NASREC_ETOOBIG (-2)        /* size beyond what this build supports */
+
+/* One source of a zero-padded concat.  2-D: `ptr` is [M, >=width] with row stride
+ * `ld`; 3-D: `ptr` is [B, >=width, 16] with batch stride `ld` (floats).  `width`
+ * live columns (2-D) / rows (3-D) meet weight columns [w_off, w_off+width). */
+typedef struct {
+    const float* ptr;
+    int64_t ld;
+    int64_t width;
+    int64_t w_off;
+} nasrec_seg_t;
+
+/* Library identity: returns a version number; *sm (if non-null) gets the compute
+ * capability the kernels were compiled for (100 for sm_100a). */
+int nasrec_version(int* sm);
+
+/* ------------------------------------------------------------------ embedding
+ * a1  SuperNet._input_stem_layers_bi_output, supernet.py:404-430:
+ *     out[b,f,:] = tables[f][idx[b,f],:]   (F nn.Embedding lookups + torch.stack).
+ * tables: device array of F table base pointers; num_rows: device array [F].
+ * err_flag (device int, may be null) is OR-ed with 1 on an out-of-range id
+ * (the reference relies on PyTorch's device-side assert); such ids read row 0. */
+int nasrec_emb_gather_fwd(const float* const* tables, const int64_t* num_rows, const int64_t* idx,
+                          float* out, int B, int F, int* err_flag, void* stream);
+
+/* a1 backward, replaces F embedding_dense_backward calls (nn.Embedding, supernet.py:407).
+ * Deterministic: per table, (row, sample) keys are sorted; duplicate rows are summed in
+ * ascending sample order.  Outputs per table f: uniq[f, 0..nuniq[f]) ascending row ids,
+ * row_grad[f, u, :] the summed gradient rows, sumsq[f] = sum of squares of row_grad
+ * (for the global clip norm).  seg_scratch: int32 [F, B+1].  B <= 16384. */
+int nasrec_emb_grad_sort_reduce(const int64_t* idx, const float* gout, int B, int F,
+                                int64_t* uniq, int* nuniq, float* row_grad, float* sumsq,
+                                int* seg_scratch, void* stream);
+
+/* Scatter the reduced rows into dense zero-initialised [N_f,16] gradients (what
+ * nn.Embedding.weight.grad holds in the reference). */
+int nasrec_emb_grad_to_dense(const int64_t* uniq, const int* nuniq, const float* row_grad,
+                             float* const* grad_tables, int B, int F, void* stream);
+
+/* a17 restricted to the touched rows; identical to torch.optim.Adagrad(eps) on the dense
+ * gradient because untouched rows have g == 0 (train_supernet.py:121-123):
+ *   g = row_grad * clip_coef[0];  state[row] += g*g;  W[row] -= lr * g / (sqrt(state[row]) + eps). */
+int nasrec_emb_rowwise_adagrad(const int64_t* uniq, const int* nuniq, const float* row_grad,
+                               float* const* tables, float* const* states, int B, int F,
+                               float lr, float eps, const float* clip_coef, void* stream);
+
+/* ------------------------------------------------------- segment linear (2-D)
+ * a5/a7/a8/a11/a12/a4  nn.LazyLinear applied to a zero-padded concat
+ * (modules.py:171,340,385,489,578,584,740; supernet.py:598,1140):
+ *   C[m,n] = sum_s sum_k A_s[m,k] * W[n_off+n, w_off_s+k] (+ bias[n_off+n]),  n < N.
+ * Zero padding contributes nothing, so only the live K support is read. */
+int nasrec_seg_linear_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off,
+                          int N, const float* bias, float* C, int64_t ldc, int M, void* stream);
+/* dA_s[m,k] (+)= sum_n dC[m,n] * W[n_off+n, w_off_s+k]; segment outputs must not alias. */
+int nasrec_seg_linear_dgrad(const float* dC, int64_t ldc, int N, const float* W, int64_t ldw, int n_off,
+                            const nasrec_seg_t* dsegs, int nseg, int M, int accumulate, void* stream);
+/* dW[n_off+n, w_off_s+k] (+)= sum_m dC[m,n] * A_s[m,k]; segments must not overlap in W. */
+int nasrec_seg_linear_wgrad(const float* dC, int64_t ldc, int N, const nasrec_seg_t* segs, int nseg,
+                            float* dW, int64_t ldw, int n_off, int M, int accumulate, void* stream);
+/* out[n] (+)= sum_m x[m,n]  (bias gradients); deterministic. */
+int nasrec_colsum(const float* x, int64_t ld, int M, int N, float* out, int accumulate, void* stream);
+
+/* ------------------------------------------- projection along the sparse axis
+ * a9/a10/a6  nn.LazyLinear on sparse.transpose(1,2) (modules.py:222-223,358-359,648):
+ *   Z[b,p,e] = sum_s sum_r W[p, w_off_s+r] * X_s[b,r,e] (+ bias[p]),  p < P, e < 16. */
+int nasrec_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int P,
+                     const float* bias, float* Z, int64_t z_bstride, int B, void* stream);
+int nasrec_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* W, int64_t ldw,
+                       const nasrec_seg_t* dsegs, int nseg, int B, int accumulate, void* stream);
+/* workspace: nasrec_sproj_wgrad_ws_floats(P, total_width, B) floats. */
+int64_t nasrec_sproj_wgrad_ws_floats(int P, int64_t total_width, int B);
+int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_seg_t* segs, int nseg,
+                       float* dW, int64_t ldw, int B, int accumulate, float* ws, void* stream);
+
+/* db[p] (+)= sum_{b,e} dZ[b,p,e]  (bias gradient of the projection; use_layernorm=False models). */
+int nasrec_sproj_bias_grad(const float* dZ, int64_t dz_bstride, int P, int B, float* db, int accumulate,
+                           void* stream);
+
+/* ------------------------------------------------------- LayerNorm epilogues
+ * nn.LayerNorm(N) + activation + prefix mask (modules.py:171-181, 385-400, 489-499):
+ *   y[m,j] (+)= act(LN(x[m,0:N])[j]) for j < d_out  (columns >= d_out are the masked ones
+ *   and are not stored); mean/rstd [M] are saved for the backward. relu: 0/1. */
+int nasrec_ln_fwd(const float* x, int64_t ldx, int M, int N, const float* gamma, const float* beta,
+                  float eps, int relu, int d_out, float* y, int64_t ldy, float* mean, float* rstd,
+                  int accumulate, void* stream);
+/* dx [M,N] from dy [M,d_out]; dgamma/dbeta [N] (+)= column sums (zero beyond d_out). */
+int nasrec_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* x, int64_t ldx, int M, int N,
+                  const float* gamma, const float* beta, const float* mean, const float* rstd, int relu,
+                  float* dx, int64_t lddx, float* dgamma, float* dbeta, int accumulate_params, void* stream);
+/* Same over the P axis of z [B,P,16] (nn.LayerNorm(P) on the transposed tensor,
+ * modules.py:224-230,360,649): y[b,p,e] = act(LN_p(z[b,:,e])[p]) for p < p_out;
+ * mean/rstd are [B,16]. */
+int nasrec_ln3_fwd(const float* z, int64_t z_bstride, int B, int P, const float* gamma, const float* beta,
+                   float eps, int relu, int p_out, float* y, int64_t y_bstride, float* mean, float* rstd,
+                   int accumulate, void* stream);
+int nasrec_ln3_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* z, int64_t z_bstride, int B,
+                   int P, const float* gamma, const float* beta, const float* mean, const float* rstd, int relu,
+                   float* dz, int64_t dz_bstride, float* dgamma, float* dbeta, int accumulate_params,
+                   void* stream);
+/* Plain epilogue without LayerNorm (use_layernorm=False fixed models): y = act(x) (+)=. */
+int nasrec_act_fwd(const float* x, int64_t ldx, int M, int N, int relu, float* y, int64_t ldy,
+                   int accumulate, void* stream);
+int nasrec_act_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, int M, int N, int relu,
+                   float* dx, int64_t lddx, void* stream);
+
+/* ----------------------------------------------------------------- DotProduct
+ * a6  modules.py:366-383: T = [x ; y] ([B,1+P,16]); Z = T T^T; R = strict lower triangle
+ * of Z in torch.tril_indices row-major order ((1,0),(2,0),(2,1),...): R [B, (P+1)P/2]. */
+int nasrec_dot_tril_fwd(const float* x, int64_t ldx, const float* y, int64_t y_bstride, int P,
+                        float* R, int64_t ldr, int B, void* stream);
+int nasrec_dot_tril_bwd(const float* dR, int64_t ldr, const float* x, int64_t ldx, const float* y,
+                        int64_t y_bstride, int P, float* dx, int64_t lddx, float* dy, int64_t dy_bstride,
+                        int B, void* stream);
+
+/* ------------------------------------------------------------ SigmoidGating
+ * a7  modules.py:576-582: out[m, koff_s+k] = sigmoid(pre[m, koff_s+k]) * right_s[m,k], where the
+ * right operand is a segment list and koff_s is the running sum of widths. */
+int nasrec_gate_fwd(const float* pre, int64_t ldp, const nasrec_seg_t* right, int nseg, float* out,
+                    int64_t ldo, int M, void* stream);
+/* dpre = dout * right * s(1-s);  dright_s (+)= dout * s   (dright given as segments). */
+int nasrec_gate_bwd(const float* dout, int64_t ldo, const float* pre, int64_t ldp, const nasrec_seg_t* right,
+                    const nasrec_seg_t* dright, int nseg, float* dpre, int64_t lddp, int M, int accumulate,
+                    void* stream);
+/* out[m, w_off_s+k] (+)= A_s[m,k]: materialises a padded concat (rare no-projection corner,
+ * modules.py:487-491, 582-586). */
+int nasrec_concat_segs(const nasrec_seg_t* segs, int nseg, float* out, int64_t ldo, int M, int accumulate,
+                       void* stream);
+
+/* ----------------------------------------------------- FactorizationMachine3D
+ * a11  modules.py:736-738: ix[b,e] = (sum_r x[b,r,e])^2 - sum_r x[b,r,e]^2, r < rows. */
+int nasrec_fm_fwd(const float* x, int64_t x_bstride, int rows, float* ix, int B, void* stream);
+/* dx[b,r,e] = (dx_in ? dx_in[b,r,e] : 0) + 2*dix[b,e]*(S[b,e] - x[b,r,e]). */
+int nasrec_fm_bwd(const float* dix, const float* x, int64_t x_bstride, int rows, const float* dx_in,
+                  int64_t dxin_bstride, float* dx, int64_t dx_bstride, int B, void* stream);
+
+/* ------------------------------------------------------------------ Attention
+ * a10  modules.py:664-688: nn.MultiheadAttention(16, heads=8, batch_first) self-attention over
+ * L tokens, +residual, LayerNorm(16), FC-ReLU-FC, +residual, LayerNorm(16), row mask.
+ * x is [B, s_live, 16]; tokens s_live..L-1 are the masked (all-zero) rows which still act as
+ * keys/values through the in-proj bias.  params: HOST array of 12 device pointers, in order
+ * in_proj_weight[48,16] in_proj_bias[48] out_proj.weight[16,16] out_proj.bias[16]
+ * attn_ln.w[16] attn_ln.b[16] fc1.w[16,16] fc1.b[16] fc2.w[16,16] fc2.b[16] fc_ln.w[16] fc_ln.b[16]
+ * (NASREC_ATTN_PARAMS floats in total; dparams below is one packed buffer in the same order).
+ * y [B, s_live, 16]. L <= 64. */
+int nasrec_attn_fwd(const float* x, int64_t x_bstride, int L, int s_live, const float* const* params,
+                    float* y, int64_t y_bstride, int B, void* stream);
+/* dx [B,s_live,16]; dparams [NASREC_ATTN_PARAMS] (+)=; ws: nasrec_attn_bwd_ws_floats(B) floats. */
+int64_t nasrec_attn_bwd_ws_floats(int B);
+int nasrec_attn_bwd(const float* dy, int64_t dy_bstride, const float* x, int64_t x_bstride, int L,
+                    int s_live, const float* const* params, float* dx, int64_t dx_bstride, float* dparams,
+                    int accumulate_params, float* ws, int B, void* stream);
+
+/* ------------------------------------------------------------------ loss/step
+ * a17  BCEWithLogitsLoss(mean) forward + gradient (train_supernet.py:104, train_utils.py:266):
+ * loss[0] = mean(max(z,0) - z*y + log1p(exp(-|z|))); dlogits[b] = (sigmoid(z)-y)/B * grad_scale. */
+int nasrec_bce_fwd_bwd(const float* logits, const float* y, int B, float grad_scale, float* loss,
+                       float* dlogits, void* stream);
+/* (grads/sizes/w/state below are HOST arrays of device pointers / element counts.)
+ * Global L2 norm of n tensors + extra pre-reduced sums of squares, then the
+ * clip_grad_norm_ coefficient (train_utils.py:285): out[0] = total_norm,
+ * out[1] = min(1, max_norm / (total_norm + 1e-6)).  partial: >= nasrec_sumsq_ws_floats() floats. */
+int64_t nasrec_sumsq_ws_floats(const int64_t* sizes, int n);
+int nasrec_grad_norm_clip(const float* const* grads, const int64_t* sizes, int n, const float* extra_sumsq,
+                          int n_extra, float max_norm, float* partial, float* out, void* stream);
+/* torch.optim.Adagrad(lr, eps, lr_decay=0) over n dense tensors:
+ *   g = grad*clip_coef[0]; state += g*g; w -= lr * g / (sqrt(state)+eps). */
+int nasrec_adagrad_multi(float* const* w, const float* const* grads, float* const* state,
+                         const int64_t* sizes, int n, float lr, float eps, const float* clip_coef,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NASREC_B200_H */

@@ -1,0 +1,26 @@
+"""nasrec_b200 -- B200-native (sm_100a) implementation of NASRec's supernet hot path.
+
+Drop-in for ``nasrec.supernet`` (SuperNet / SuperNetBlock / modules / config JSON);
+see INTEGRATION.md.  The arithmetic is hand-written CUDA behind the C ABI in
+``include/nasrec_b200.h`` -- there is no CPU or eager-PyTorch fallback.
+"""
+from . import _lib  # noqa: F401
+from .supernet.supernet import SuperNet, SuperNetBlock, ops_config_lib, path_sampling_strategy_lib  # noqa: F401
+
+__version__ = "0.1.0"
+
+
+def install_as_nasrec():
+    """Alias this package as ``nasrec`` so reference entry scripts import it unchanged
+    (``from nasrec.supernet.supernet import SuperNet`` ...)."""
+    import sys
+    from . import supernet as _sn, utils as _ut
+    from .supernet import modules as _m, supernet as _s, utils as _u
+    from .utils import config as _c
+    sys.modules.setdefault("nasrec", sys.modules[__name__])
+    sys.modules.setdefault("nasrec.supernet", _sn)
+    sys.modules.setdefault("nasrec.supernet.supernet", _s)
+    sys.modules.setdefault("nasrec.supernet.modules", _m)
+    sys.modules.setdefault("nasrec.supernet.utils", _u)
+    sys.modules.setdefault("nasrec.utils", _ut)
+    sys.modules.setdefault("nasrec.utils.config", _c)

@@ -1,0 +1,140 @@
+"""ctypes binding of include/nasrec_b200.h (the C-ABI drop-in boundary).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call
+fails, this module raises.  Nothing here (or anywhere in nasrec_b200) imports
+``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Sequence, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnasrec_b200.so")
+
+MAX_SEGS = 16
+ATTN_PARAMS = 1696
+
+_f = C.c_void_p      # device pointers travel as integers
+_i = C.c_int
+_l = C.c_int64
+_fl = C.c_float
+
+# name -> (argtypes, kernels launched per call) ; restype is int unless noted
+_SIGS = {
+    "nasrec_emb_gather_fwd": ([_f, _f, _f, _f, _i, _i, _f, _f], 1),
+    "nasrec_emb_grad_sort_reduce": ([_f, _f, _i, _i, _f, _f, _f, _f, _f, _f], 1),
+    "nasrec_emb_grad_to_dense": ([_f, _f, _f, _f, _i, _i, _f], 1),
+    "nasrec_emb_rowwise_adagrad": ([_f, _f, _f, _f, _f, _i, _i, _fl, _fl, _f, _f], 1),
+    "nasrec_seg_linear_fwd": ([_f, _i, _f, _l, _i, _i, _f, _f, _l, _i, _f], 1),
+    "nasrec_seg_linear_dgrad": ([_f, _l, _i, _f, _l, _i, _f, _i, _i, _i, _f], 1),
+    "nasrec_seg_linear_wgrad": ([_f, _l, _i, _f, _i, _f, _l, _i, _i, _i, _f], 1),
+    "nasrec_colsum": ([_f, _l, _i, _i, _f, _i, _f], 1),
+    "nasrec_sproj_fwd": ([_f, _i, _f, _l, _i, _f, _f, _l, _i, _f], 1),
+    "nasrec_sproj_dgrad": ([_f, _l, _i, _f, _l, _f, _i, _i, _i, _f], 1),
+    "nasrec_sproj_wgrad": ([_f, _l, _i, _f, _i, _f, _l, _i, _i, _f, _f], 2),
+    "nasrec_sproj_bias_grad": ([_f, _l, _i, _i, _f, _i, _f], 1),
+    "nasrec_ln_fwd": ([_f, _l, _i, _i, _f, _f, _fl, _i, _i, _f, _l, _f, _f, _i, _f], 1),
+    "nasrec_ln_bwd": ([_f, _l, _i, _f, _l, _i, _i, _f, _f, _f, _f, _i, _f, _l, _f, _f, _i, _f], 2),
+    "nasrec_ln3_fwd": ([_f, _l, _i, _i, _f, _f, _fl, _i, _i, _f, _l, _f, _f, _i, _f], 1),
+    "nasrec_ln3_bwd": ([_f, _l, _i, _f, _l, _i, _i, _f, _f, _f, _f, _i, _f, _l, _f, _f, _i, _f], 2),
+    "nasrec_act_fwd": ([_f, _l, _i, _i, _i, _f, _l, _i, _f], 1),
+    "nasrec_act_bwd": ([_f, _l, _f, _l, _i, _i, _i, _f, _l, _f], 1),
+    "nasrec_dot_tril_fwd": ([_f, _l, _f, _l, _i, _f, _l, _i, _f], 1),
+    "nasrec_dot_tril_bwd": ([_f, _l, _f, _l, _f, _l, _i, _f, _l, _f, _l, _i, _f], 1),
+    "nasrec_gate_fwd": ([_f, _l, _f, _i, _f, _l, _i, _f], 1),
+    "nasrec_gate_bwd": ([_f, _l, _f, _l, _f, _f, _i, _f, _l, _i, _i, _f], 1),
+    "nasrec_concat_segs": ([_f, _i, _f, _l, _i, _i, _f], 1),
+    "nasrec_fm_fwd": ([_f, _l, _i, _f, _i, _f], 1),
+    "nasrec_fm_bwd": ([_f, _f, _l, _i, _f, _l, _f, _l, _i, _f], 1),
+    "nasrec_attn_fwd": ([_f, _l, _i, _i, _f, _f, _l, _i, _f], 1),
+    "nasrec_attn_bwd": ([_f, _l, _f, _l, _i, _i, _f, _f, _l, _f, _i, _f, _i, _f], 2),
+    "nasrec_bce_fwd_bwd": ([_f, _f, _i, _fl, _f, _f, _f], 1),
+    "nasrec_grad_norm_clip": ([_f, _f, _i, _f, _i, _fl, _f, _f, _f], 2),
+    "nasrec_adagrad_multi": ([_f, _f, _f, _f, _i, _fl, _fl, _f, _f], 1),
+}
+_SIGS_I64 = {
+    "nasrec_sproj_wgrad_ws_floats": [_i, _l, _i],
+    "nasrec_attn_bwd_ws_floats": [_i],
+    "nasrec_sumsq_ws_floats": [_f, _i],
+}
+EXPORTS = ["nasrec_version"] + list(_SIGS) + list(_SIGS_I64)
+
+
+class _Lib:
+    def __init__(self):
+        self.cdll = None
+        self.launches = 0          # kernels launched through this binding (bench.py's gpu_launches)
+        self.fn = {}
+
+    def load(self):
+        if self.cdll is not None:
+            return self
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "nasrec_b200: CUDA library %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nasrec_b200/csrc/build.sh). There is no CPU fallback." % LIB_PATH)
+        self.cdll = C.CDLL(LIB_PATH)
+        for name, (argtypes, _n) in _SIGS.items():
+            fn = getattr(self.cdll, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+            self.fn[name] = fn
+        for name, argtypes in _SIGS_I64.items():
+            fn = getattr(self.cdll, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int64
+            self.fn[name] = fn
+        self.cdll.nasrec_version.argtypes = [C.POINTER(C.c_int)]
+        self.cdll.nasrec_version.restype = C.c_int
+        return self
+
+    def version(self) -> Tuple[int, int]:
+        self.load()
+        sm = C.c_int(0)
+        v = self.cdll.nasrec_version(C.byref(sm))
+        return v, sm.value
+
+
+LIB = _Lib()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke a C-ABI entry point on torch's current stream; raise on any error."""
+    lib = LIB.load()
+    rc = lib.fn[name](*args, stream_ptr())
+    if rc != 0:
+        if rc > 0:
+            raise RuntimeError("%s failed: CUDA error %d" % (name, rc))
+        raise ValueError("%s rejected its arguments (code %d)" % (name, rc))
+    lib.launches += _SIGS[name][1]
+
+
+def query(name: str, *args) -> int:
+    return int(LIB.load().fn[name](*args))
+
+
+def segs(items: Sequence[Tuple[int, int, int, int]]):
+    """Pack (device_ptr, ld, width, w_off) tuples as a nasrec_seg_t[] (4 x int64 each)."""
+    n = len(items)
+    if n == 0 or n > MAX_SEGS:
+        raise ValueError("segment list must hold 1..%d entries, got %d" % (MAX_SEGS, n))
+    flat: List[int] = []
+    for it in items:
+        flat.extend(it)
+    return (C.c_int64 * (4 * n))(*flat), n
+
+
+def i64_array(vals: Sequence[int]):
+    return (C.c_int64 * len(vals))(*vals)
+
+
+def ptr_array(vals: Sequence[int]):
+    return (C.c_void_p * len(vals))(*vals)

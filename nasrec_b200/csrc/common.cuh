@@ -1,0 +1,45 @@
+// Shared helpers for the nasrec_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/nasrec_b200.h"
+
+#define NASREC_VERSION 100
+
+#define CHECK_ARG(cond)            \
+    do {                           \
+        if (!(cond)) return NASREC_EINVAL; \
+    } while (0)
+
+static inline int nasrec_launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return (int)e;
+}
+
+static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum (fixed tree); result valid in every thread.
+// `red` must hold >= 33 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        float t = lane < nw ? red[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,212 @@
+// Embedding stem: fused bag-size-1 gather over all F tables, deterministic
+// sorted-row gradient reduction and row-wise Adagrad.
+//
+// Replaces F x nn.Embedding + torch.stack (nasrec/supernet/supernet.py:404-430),
+// F x embedding_dense_backward, and the dense torch.optim.Adagrad sweep over
+// every table row (nasrec/train_supernet.py:121-123).
+//
+// HBM-bound byte work: rows are 64 B (16 fp32); 4 lanes move one row as float4,
+// so one warp instruction moves 8 rows; indices are read coalesced along F.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) emb_gather_kernel(const float* const* __restrict__ tables,
+                                                         const int64_t* __restrict__ num_rows,
+                                                         const int64_t* __restrict__ idx,
+                                                         float* __restrict__ out, long long n_pairs, int F,
+                                                         int* err_flag) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long pair = t >> 2;          // (b,f) flattened, same order as idx and out
+    if (pair >= n_pairs) return;
+    const int q = (int)(t & 3);
+    const int f = (int)(pair % F);
+    long long row = idx[pair];
+    if ((unsigned long long)row >= (unsigned long long)num_rows[f]) {
+        if (err_flag) atomicOr(err_flag, 1);
+        row = 0;
+    }
+    const float4 v = __ldg(reinterpret_cast<const float4*>(tables[f] + row * NASREC_EMB_DIM) + q);
+    reinterpret_cast<float4*>(out + pair * NASREC_EMB_DIM)[q] = v;
+}
+
+// One CTA per table: bitonic sort of (row << 32 | sample) keys in shared memory,
+// head flags + block scan -> unique rows, then 16 lanes per unique row sum the
+// duplicates in ascending sample order.
+__global__ void __launch_bounds__(1024) emb_sort_reduce_kernel(const int64_t* __restrict__ idx,
+                                                               const float* __restrict__ gout, int B, int Bpad,
+                                                               int F, int64_t* __restrict__ uniq,
+                                                               int* __restrict__ nuniq,
+                                                               float* __restrict__ row_grad,
+                                                               float* __restrict__ sumsq,
+                                                               int* __restrict__ seg_scratch) {
+    extern __shared__ unsigned long long keys[];
+    __shared__ int wsum[32];
+    __shared__ float red[34];
+    __shared__ int s_total;
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < Bpad; i += nt)
+        keys[i] = i < B ? (((unsigned long long)idx[(long long)i * F + f] << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= Bpad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < Bpad; i += nt) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // contiguous chunk per thread; count heads, scan, then emit segment starts
+    const int chunk = (Bpad + nt - 1) / nt;
+    const int beg = tid * chunk, end = min(B, beg + chunk);
+    int cnt = 0;
+    for (int i = beg; i < end; ++i)
+        cnt += (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) ? 1 : 0;
+    // block exclusive scan of cnt
+    const int lane = tid & 31, wid = tid >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < (nt >> 5) ? wsum[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        wsum[lane] = winc - w;                 // exclusive
+        if (lane == 31) s_total = winc;
+    }
+    __syncthreads();
+    int pos = wsum[wid] + inc - cnt;
+    int* seg = seg_scratch + (long long)f * (B + 1);
+    for (int i = beg; i < end; ++i)
+        if (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) seg[pos++] = i;
+    const int U = s_total;
+    if (tid == 0) {
+        seg[U] = B;
+        nuniq[f] = U;
+    }
+    __syncthreads();
+    // 16 lanes per unique row
+    const int e = tid & 15;
+    float sq = 0.f;
+    for (int u = tid >> 4; u < U; u += nt >> 4) {
+        const int s0 = seg[u], s1 = seg[u + 1];
+        float acc = 0.f;
+        for (int i = s0; i < s1; ++i) {
+            const unsigned b = (unsigned)(keys[i] & 0xffffffffu);
+            acc += gout[((long long)b * F + f) * NASREC_EMB_DIM + e];
+        }
+        row_grad[((long long)f * B + u) * NASREC_EMB_DIM + e] = acc;
+        if (e == 0) uniq[(long long)f * B + u] = (int64_t)(keys[s0] >> 32);
+        sq += acc * acc;
+    }
+    const float tot = block_sum(sq, red);
+    if (tid == 0) sumsq[f] = tot;
+}
+
+__global__ void __launch_bounds__(256) emb_to_dense_kernel(const int64_t* __restrict__ uniq,
+                                                           const int* __restrict__ nuniq,
+                                                           const float* __restrict__ row_grad,
+                                                           float* const* __restrict__ grad_tables, int B) {
+    const int f = blockIdx.y;
+    const int U = nuniq[f];
+    const int e = threadIdx.x & 15;
+    for (int u = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); u < U; u += gridDim.x * (blockDim.x >> 4)) {
+        const long long row = uniq[(long long)f * B + u];
+        grad_tables[f][row * NASREC_EMB_DIM + e] = row_grad[((long long)f * B + u) * NASREC_EMB_DIM + e];
+    }
+}
+
+__global__ void __launch_bounds__(256) emb_adagrad_kernel(const int64_t* __restrict__ uniq,
+                                                          const int* __restrict__ nuniq,
+                                                          const float* __restrict__ row_grad,
+                                                          float* const* __restrict__ tables,
+                                                          float* const* __restrict__ states, int B, float lr,
+                                                          float eps, const float* __restrict__ clip_coef) {
+    const int f = blockIdx.y;
+    const int U = nuniq[f];
+    const int e = threadIdx.x & 15;
+    const float coef = clip_coef ? clip_coef[0] : 1.f;
+    for (int u = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); u < U; u += gridDim.x * (blockDim.x >> 4)) {
+        const long long o = uniq[(long long)f * B + u] * NASREC_EMB_DIM + e;
+        const float g = row_grad[((long long)f * B + u) * NASREC_EMB_DIM + e] * coef;
+        const float s = states[f][o] + g * g;
+        states[f][o] = s;
+        tables[f][o] = tables[f][o] - lr * (g / (sqrtf(s) + eps));
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int nasrec_version(int* sm) {
+    if (sm) *sm = 100;
+    return NASREC_VERSION;
+}
+
+int nasrec_emb_gather_fwd(const float* const* tables, const int64_t* num_rows, const int64_t* idx, float* out,
+                          int B, int F, int* err_flag, void* stream) {
+    CHECK_ARG(tables && num_rows && idx && out && B > 0 && F > 0);
+    const long long n_pairs = (long long)B * F;
+    emb_gather_kernel<<<cdiv(n_pairs * 4, 256), 256, 0, as_stream(stream)>>>(tables, num_rows, idx, out, n_pairs, F,
+                                                                            err_flag);
+    return nasrec_launch_status();
+}
+
+int nasrec_emb_grad_sort_reduce(const int64_t* idx, const float* gout, int B, int F, int64_t* uniq, int* nuniq,
+                                float* row_grad, float* sumsq, int* seg_scratch, void* stream) {
+    CHECK_ARG(idx && gout && uniq && nuniq && row_grad && sumsq && seg_scratch && B > 0 && F > 0);
+    if (B > 16384) return NASREC_ETOOBIG;
+    int Bpad = 32;
+    while (Bpad < B) Bpad <<= 1;
+    const size_t smem = (size_t)Bpad * sizeof(unsigned long long);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(emb_sort_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             16384 * 8);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int threads = Bpad >= 1024 ? 1024 : (Bpad < 64 ? 64 : Bpad);
+    emb_sort_reduce_kernel<<<F, threads, smem, as_stream(stream)>>>(idx, gout, B, Bpad, F, uniq, nuniq, row_grad,
+                                                                    sumsq, seg_scratch);
+    return nasrec_launch_status();
+}
+
+int nasrec_emb_grad_to_dense(const int64_t* uniq, const int* nuniq, const float* row_grad,
+                             float* const* grad_tables, int B, int F, void* stream) {
+    CHECK_ARG(uniq && nuniq && row_grad && grad_tables && B > 0 && F > 0);
+    dim3 grid(cdiv(B, 16), F);
+    emb_to_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(uniq, nuniq, row_grad, grad_tables, B);
+    return nasrec_launch_status();
+}
+
+int nasrec_emb_rowwise_adagrad(const int64_t* uniq, const int* nuniq, const float* row_grad, float* const* tables,
+                               float* const* states, int B, int F, float lr, float eps, const float* clip_coef,
+                               void* stream) {
+    CHECK_ARG(uniq && nuniq && row_grad && tables && states && B > 0 && F > 0);
+    dim3 grid(cdiv(B, 16), F);
+    emb_adagrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(uniq, nuniq, row_grad, tables, states, B, lr, eps,
+                                                            clip_coef);
+    return nasrec_launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,444 @@
+// Segment-list SGEMM family (fp32 FFMA path).
+//
+// One tiled kernel computes, for a small batch of independent problems,
+//     C(m,n) = sum_terms sum_k A_t(m,k) * B_t(n,k)  (+ bias[n]) (+ addend(m,n))
+// where every operand is a strided "view" with an optional two-level index
+// (i -> (i >> sh) * hi + (i & mask) * lo), which is what lets the same kernel
+// serve the 2-D linears over zero-padded concats (a K axis made of segments
+// living in different tensors) and the projections along the sparse axis of
+// [B, rows, 16] tensors without ever materialising a concat or a transpose.
+//
+// Replaces: F.linear on torch.cat([...zeros...]) in nasrec/supernet/modules.py
+// (:171,:223,:340,:359,:385,:489,:578,:584,:648,:740) and supernet.py:598,1140.
+#include "common.cuh"
+
+namespace {
+
+struct View {
+    const float* p;
+    long long hi_i, hi_j;
+    int lo_i, lo_j, sh_i, sh_j;
+    int contig_j;   // 1: consecutive j are adjacent in memory, 0: consecutive i are
+    int pad_;
+};
+
+__device__ __forceinline__ long long voff(const View& v, int i, int j) {
+    return (long long)(i >> v.sh_i) * v.hi_i + (long long)(i & ((1 << v.sh_i) - 1)) * v.lo_i +
+           (long long)(j >> v.sh_j) * v.hi_j + (long long)(j & ((1 << v.sh_j) - 1)) * v.lo_j;
+}
+
+struct Term {
+    View a;   // A(m, k): i = m, j = k
+    View b;   // B(n, k): i = n, j = k
+    int K;
+    int pad_;
+};
+
+struct Prob {
+    int M, N, term0, nterm;
+    float* c;
+    const float* addend;          // same layout as c, or null
+    long long c_hi_i, c_hi_j;
+    int c_lo_i, c_sh_i;
+    const float* bias;            // indexed by n, or null
+    int nsplit;
+    int pad_;
+    long long split_stride;
+};
+
+constexpr int MAXP = 16, MAXT = 20;
+struct Batch {
+    int nprob;
+    int pad_;
+    Prob prob[MAXP];
+    Term term[MAXT];
+};
+
+constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
+
+__device__ __forceinline__ void load_tile(float (*S)[BM + PADM], const View& v, int i0, int I, int k0, int K,
+                                          int tid) {
+    if (v.contig_j) {
+        const int j = tid & 15;
+        int i = tid >> 4;
+        const bool jok = (k0 + j) < K;
+#pragma unroll
+        for (int q = 0; q < 4; ++q, i += 16) {
+            float val = 0.f;
+            if (jok && (i0 + i) < I) val = __ldg(v.p + voff(v, i0 + i, k0 + j));
+            S[j][i] = val;
+        }
+    } else {
+        const int i = tid & 63;
+        int j = tid >> 6;
+        const bool iok = (i0 + i) < I;
+#pragma unroll
+        for (int q = 0; q < 4; ++q, j += 4) {
+            float val = 0.f;
+            if (iok && (k0 + j) < K) val = __ldg(v.p + voff(v, i0 + i, k0 + j));
+            S[j][i] = val;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gemm64_kernel(const __grid_constant__ Batch bt) {
+    __shared__ __align__(16) float As[BK][BM + PADM];
+    __shared__ __align__(16) float Bs[BK][BN + PADM];
+    int z = blockIdx.z, pi = 0;
+    for (; pi < bt.nprob; ++pi) {
+        const int ns = bt.prob[pi].nsplit;
+        if (z < ns) break;
+        z -= ns;
+    }
+    if (pi >= bt.nprob) return;
+    const Prob& pr = bt.prob[pi];
+    const int split = z;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (m0 >= pr.M || n0 >= pr.N) return;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+    int tot = 0;
+    for (int t = 0; t < pr.nterm; ++t) tot += (bt.term[pr.term0 + t].K + BK - 1) / BK;
+    const int per = (tot + pr.nsplit - 1) / pr.nsplit;
+    const int kt_begin = split * per;
+    const int kt_end = min(tot, kt_begin + per);
+    int kt = 0;
+    for (int t = 0; t < pr.nterm; ++t) {
+        const Term& tm = bt.term[pr.term0 + t];
+        const int nk = (tm.K + BK - 1) / BK;
+        if (kt + nk <= kt_begin) {
+            kt += nk;
+            continue;
+        }
+        if (kt >= kt_end) break;
+        const int kb = max(0, kt_begin - kt), ke = min(nk, kt_end - kt);
+        for (int kk = kb; kk < ke; ++kk) {
+            const int k0 = kk * BK;
+            load_tile(As, tm.a, m0, pr.M, k0, tm.K, tid);
+            load_tile(Bs, tm.b, n0, pr.N, k0, tm.K, tid);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < BK; ++j) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&As[j][ty * 4]);
+                const float4 b4 = *reinterpret_cast<const float4*>(&Bs[j][tx * 4]);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+            }
+            __syncthreads();
+        }
+        kt += nk;
+    }
+
+    const int cmask = (1 << pr.c_sh_i) - 1;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int m = m0 + ty * 4 + r;
+        if (m >= pr.M) continue;
+        const long long ro = (long long)(m >> pr.c_sh_i) * pr.c_hi_i + (long long)(m & cmask) * pr.c_lo_i;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int n = n0 + tx * 4 + c;
+            if (n >= pr.N) continue;
+            const long long o = ro + (long long)n * pr.c_hi_j;
+            float v = acc[r][c];
+            if (pr.bias) v += __ldg(pr.bias + n);
+            if (pr.addend) v += pr.addend[o];
+            pr.c[o + (long long)split * pr.split_stride] = v;
+        }
+    }
+}
+
+struct RedSeg {
+    const float* ws;      // [nsplit][M][N]
+    float* c;             // destination, row stride ldc
+    int N;
+    int pad_;
+};
+struct RedBatch {
+    int nseg, nsplit, M, accumulate;
+    long long ldc;
+    RedSeg seg[NASREC_MAX_SEGS];
+};
+
+__global__ void splitk_reduce_kernel(const __grid_constant__ RedBatch rb) {
+    const RedSeg& s = rb.seg[blockIdx.y];
+    const long long total = (long long)rb.M * s.N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / s.N), n = (int)(i % s.N);
+        float v = 0.f;
+        for (int sp = 0; sp < rb.nsplit; ++sp) v += s.ws[(long long)sp * total + i];
+        float* dst = s.c + (long long)m * rb.ldc + n;
+        *dst = rb.accumulate ? (*dst + v) : v;
+    }
+}
+
+View plain_view(const float* p, long long si, long long sj, int contig_j) {
+    View v{};
+    v.p = p;
+    v.hi_i = si;
+    v.hi_j = sj;
+    v.contig_j = contig_j;
+    return v;
+}
+
+int launch(const Batch& bt, cudaStream_t st) {
+    int maxM = 0, maxN = 0, totz = 0;
+    for (int i = 0; i < bt.nprob; ++i) {
+        maxM = bt.prob[i].M > maxM ? bt.prob[i].M : maxM;
+        maxN = bt.prob[i].N > maxN ? bt.prob[i].N : maxN;
+        totz += bt.prob[i].nsplit;
+    }
+    if (maxM <= 0 || maxN <= 0 || totz <= 0) return 0;
+    dim3 grid(cdiv(maxN, BN), cdiv(maxM, BM), totz);
+    if (grid.y > 65535 || grid.z > 65535) return NASREC_ETOOBIG;
+    gemm64_kernel<<<grid, 256, 0, st>>>(bt);
+    return nasrec_launch_status();
+}
+
+bool segs_ok(const nasrec_seg_t* segs, int nseg) {
+    if (!segs || nseg <= 0 || nseg > NASREC_MAX_SEGS) return false;
+    for (int s = 0; s < nseg; ++s)
+        if (!segs[s].ptr || segs[s].width < 0 || segs[s].w_off < 0) return false;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nasrec_seg_linear_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off, int N,
+                          const float* bias, float* C, int64_t ldc, int M, void* stream) {
+    CHECK_ARG(segs_ok(segs, nseg) && W && C && M > 0 && N > 0 && n_off >= 0);
+    Batch bt{};
+    bt.nprob = 1;
+    Prob& p = bt.prob[0];
+    p.M = M;
+    p.N = N;
+    p.term0 = 0;
+    p.c = C;
+    p.c_hi_i = ldc;
+    p.c_hi_j = 1;
+    p.bias = bias ? bias + n_off : nullptr;
+    p.nsplit = 1;
+    int nt = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        Term& t = bt.term[nt++];
+        t.K = (int)segs[s].width;
+        t.a = plain_view(segs[s].ptr, segs[s].ld, 1, 1);
+        t.b = plain_view(W + (long long)n_off * ldw + segs[s].w_off, ldw, 1, 1);
+    }
+    p.nterm = nt;
+    return launch(bt, as_stream(stream));
+}
+
+int nasrec_seg_linear_dgrad(const float* dC, int64_t ldc, int N, const float* W, int64_t ldw, int n_off,
+                            const nasrec_seg_t* dsegs, int nseg, int M, int accumulate, void* stream) {
+    CHECK_ARG(segs_ok(dsegs, nseg) && dC && W && M > 0 && N > 0);
+    Batch bt{};
+    int np = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (dsegs[s].width == 0) continue;
+        Prob& p = bt.prob[np];
+        Term& t = bt.term[np];
+        p.M = M;
+        p.N = (int)dsegs[s].width;
+        p.term0 = np;
+        p.nterm = 1;
+        p.c = const_cast<float*>(dsegs[s].ptr);
+        p.c_hi_i = dsegs[s].ld;
+        p.c_hi_j = 1;
+        p.addend = accumulate ? dsegs[s].ptr : nullptr;
+        p.nsplit = 1;
+        t.K = N;
+        t.a = plain_view(dC, ldc, 1, 1);
+        // B(n = k-column of the segment, k = output row of W): W[(n_off+k)*ldw + w_off + n]
+        t.b = plain_view(W + (long long)n_off * ldw + dsegs[s].w_off, 1, ldw, 0);
+        ++np;
+    }
+    bt.nprob = np;
+    return launch(bt, as_stream(stream));
+}
+
+int nasrec_seg_linear_wgrad(const float* dC, int64_t ldc, int N, const nasrec_seg_t* segs, int nseg, float* dW,
+                            int64_t ldw, int n_off, int M, int accumulate, void* stream) {
+    CHECK_ARG(segs_ok(segs, nseg) && dC && dW && M > 0 && N > 0);
+    Batch bt{};
+    int np = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        Prob& p = bt.prob[np];
+        Term& t = bt.term[np];
+        p.M = N;                       // rows of dW
+        p.N = (int)segs[s].width;      // columns of dW in this segment
+        p.term0 = np;
+        p.nterm = 1;
+        p.c = dW + (long long)n_off * ldw + segs[s].w_off;
+        p.c_hi_i = ldw;
+        p.c_hi_j = 1;
+        p.addend = accumulate ? p.c : nullptr;
+        p.nsplit = 1;
+        t.K = M;                       // contraction over the batch
+        t.a = plain_view(dC, 1, ldc, 0);                    // A(i = n_out, j = m) = dC[m*ldc + n_out]
+        t.b = plain_view(segs[s].ptr, 1, segs[s].ld, 0);    // B(i = k, j = m)     = A_s[m*ld + k]
+        ++np;
+    }
+    bt.nprob = np;
+    return launch(bt, as_stream(stream));
+}
+
+// ---------------------------------------------------------------- 3-D (sparse axis)
+int nasrec_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int P, const float* bias,
+                     float* Z, int64_t z_bstride, int B, void* stream) {
+    CHECK_ARG(segs_ok(segs, nseg) && W && Z && B > 0 && P > 0);
+    Batch bt{};
+    bt.nprob = 1;
+    Prob& p = bt.prob[0];
+    p.M = B * NASREC_EMB_DIM;          // m = b*16 + e
+    p.N = P;
+    p.term0 = 0;
+    p.c = Z;                           // Z[b*zbs + p*16 + e]
+    p.c_hi_i = z_bstride;
+    p.c_lo_i = 1;
+    p.c_sh_i = 4;
+    p.c_hi_j = NASREC_EMB_DIM;
+    p.bias = bias;
+    p.nsplit = 1;
+    int nt = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        Term& t = bt.term[nt++];
+        t.K = (int)segs[s].width;
+        View a{};                      // A(m=(b,e), k=r) = X[b*ld + r*16 + e]
+        a.p = segs[s].ptr;
+        a.hi_i = segs[s].ld;
+        a.lo_i = 1;
+        a.sh_i = 4;
+        a.hi_j = NASREC_EMB_DIM;
+        a.contig_j = 0;
+        t.a = a;
+        t.b = plain_view(W + segs[s].w_off, ldw, 1, 1);   // B(n=p, k=r) = W[p*ldw + w_off + r]
+    }
+    p.nterm = nt;
+    return launch(bt, as_stream(stream));
+}
+
+int nasrec_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* W, int64_t ldw,
+                       const nasrec_seg_t* dsegs, int nseg, int B, int accumulate, void* stream) {
+    CHECK_ARG(segs_ok(dsegs, nseg) && dZ && W && B > 0 && P > 0);
+    Batch bt{};
+    int np = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (dsegs[s].width == 0) continue;
+        Prob& p = bt.prob[np];
+        Term& t = bt.term[np];
+        p.M = B * NASREC_EMB_DIM;
+        p.N = (int)dsegs[s].width;     // n = r
+        p.term0 = np;
+        p.nterm = 1;
+        p.c = const_cast<float*>(dsegs[s].ptr);   // dX[b*ld + r*16 + e]
+        p.c_hi_i = dsegs[s].ld;
+        p.c_lo_i = 1;
+        p.c_sh_i = 4;
+        p.c_hi_j = NASREC_EMB_DIM;
+        p.addend = accumulate ? dsegs[s].ptr : nullptr;
+        p.nsplit = 1;
+        t.K = P;
+        View a{};                      // A(m=(b,e), k=p) = dZ[b*zbs + p*16 + e]
+        a.p = dZ;
+        a.hi_i = dz_bstride;
+        a.lo_i = 1;
+        a.sh_i = 4;
+        a.hi_j = NASREC_EMB_DIM;
+        a.contig_j = 0;
+        t.a = a;
+        t.b = plain_view(W + dsegs[s].w_off, 1, ldw, 0);   // B(n=r, k=p) = W[p*ldw + w_off + r]
+        ++np;
+    }
+    bt.nprob = np;
+    return launch(bt, as_stream(stream));
+}
+
+static int sproj_nsplit(int B) {
+    int ns = B / 32;
+    if (ns < 1) ns = 1;
+    if (ns > 32) ns = 32;
+    return ns;
+}
+
+int64_t nasrec_sproj_wgrad_ws_floats(int P, int64_t total_width, int B) {
+    return (int64_t)sproj_nsplit(B) * P * total_width;
+}
+
+int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_seg_t* segs, int nseg, float* dW,
+                       int64_t ldw, int B, int accumulate, float* ws, void* stream) {
+    CHECK_ARG(segs_ok(segs, nseg) && dZ && dW && ws && B > 0 && P > 0);
+    const int ns = sproj_nsplit(B);
+    Batch bt{};
+    RedBatch rb{};
+    rb.nsplit = ns;
+    rb.M = P;
+    rb.accumulate = accumulate;
+    rb.ldc = ldw;
+    int np = 0;
+    long long wsoff = 0;
+    long long maxtot = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        const int w = (int)segs[s].width;
+        Prob& p = bt.prob[np];
+        Term& t = bt.term[np];
+        p.M = P;
+        p.N = w;
+        p.term0 = np;
+        p.nterm = 1;
+        p.c = ws + wsoff;              // partial [split][P][w]
+        p.c_hi_i = w;
+        p.c_hi_j = 1;
+        p.nsplit = ns;
+        p.split_stride = (long long)P * w;
+        t.K = B * NASREC_EMB_DIM;      // k = b*16 + e
+        View a{};                      // A(i=p, k=(b,e)) = dZ[b*zbs + p*16 + e]
+        a.p = dZ;
+        a.hi_i = NASREC_EMB_DIM;
+        a.hi_j = dz_bstride;
+        a.lo_j = 1;
+        a.sh_j = 4;
+        a.contig_j = 1;
+        t.a = a;
+        View b{};                      // B(i=r, k=(b,e)) = X[b*ld + r*16 + e]
+        b.p = segs[s].ptr;
+        b.hi_i = NASREC_EMB_DIM;
+        b.hi_j = segs[s].ld;
+        b.lo_j = 1;
+        b.sh_j = 4;
+        b.contig_j = 1;
+        t.b = b;
+        rb.seg[np].ws = ws + wsoff;
+        rb.seg[np].c = dW + segs[s].w_off;
+        rb.seg[np].N = w;
+        if ((long long)P * w > maxtot) maxtot = (long long)P * w;
+        wsoff += (long long)ns * P * w;
+        ++np;
+    }
+    bt.nprob = np;
+    rb.nseg = np;
+    if (np == 0) return 0;
+    int rc = launch(bt, as_stream(stream));
+    if (rc) return rc;
+    dim3 grid(cdiv(maxtot, 256), np);
+    splitk_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(rb);
+    return nasrec_launch_status();
+}
+
+}  // extern "C"

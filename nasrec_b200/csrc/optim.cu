@@ -1,0 +1,173 @@
+// Step-body kernels: BCE-with-logits (+gradient), global-norm clip coefficient,
+// multi-tensor Adagrad.
+//
+// Replaces BCEWithLogitsLoss + backward seed (nasrec/utils/train_utils.py:266,283),
+// torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0) (:285) and
+// torch.optim.Adagrad(eps=1e-2).step() (:286, nasrec/train_supernet.py:121-123),
+// which in eager PyTorch are ~10 elementwise launches per parameter tensor.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(1024) bce_kernel(const float* __restrict__ z, const float* __restrict__ y, int B,
+                                                   float grad_scale, float* __restrict__ loss,
+                                                   float* __restrict__ dz) {
+    __shared__ float red[34];
+    float acc = 0.f;
+    const float invB = 1.f / (float)B;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const float v = z[i], t = y[i];
+        acc += fmaxf(v, 0.f) - v * t + log1pf(expf(-fabsf(v)));
+        if (dz) dz[i] = (1.f / (1.f + expf(-v)) - t) * invB * grad_scale;
+    }
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0 && loss) loss[0] = tot * invB;
+}
+
+constexpr int MT_MAX = 96;            // tensors per launch
+constexpr int MT_CHUNK = 16384;       // elements per CTA
+
+struct SumsqPack {
+    int n;
+    int pad_;
+    const float* g[MT_MAX];
+    long long size[MT_MAX];
+    int chunk0[MT_MAX + 1];           // first chunk index of tensor i (prefix sum)
+};
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const __grid_constant__ SumsqPack pk, float* __restrict__ partial,
+                                                    int partial_off) {
+    __shared__ float red[34];
+    const int c = blockIdx.x;
+    int t = 0;
+    while (t + 1 < pk.n && pk.chunk0[t + 1] <= c) ++t;
+    const long long beg = (long long)(c - pk.chunk0[t]) * MT_CHUNK;
+    const long long end = min(pk.size[t], beg + MT_CHUNK);
+    const float* g = pk.g[t];
+    float acc = 0.f;
+    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        const float v = g[i];
+        acc = fmaf(v, v, acc);
+    }
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[partial_off + c] = tot;
+}
+
+__global__ void __launch_bounds__(1024) clip_finalize_kernel(const float* __restrict__ partial, int n_partial,
+                                                             const float* __restrict__ extra, int n_extra,
+                                                             float max_norm, float* __restrict__ out) {
+    __shared__ float red[34];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n_partial; i += blockDim.x) acc += partial[i];
+    for (int i = threadIdx.x; i < n_extra; i += blockDim.x) acc += extra[i];
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        const float norm = sqrtf(tot);
+        out[0] = norm;
+        out[1] = fminf(1.f, max_norm / (norm + 1e-6f));
+    }
+}
+
+struct AdagradPack {
+    int n;
+    int pad_;
+    float* w[MT_MAX];
+    const float* g[MT_MAX];
+    float* s[MT_MAX];
+    long long size[MT_MAX];
+    int chunk0[MT_MAX + 1];
+};
+
+__global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ AdagradPack pk, float lr, float eps,
+                                                      const float* __restrict__ clip_coef) {
+    const int c = blockIdx.x;
+    int t = 0;
+    while (t + 1 < pk.n && pk.chunk0[t + 1] <= c) ++t;
+    const long long beg = (long long)(c - pk.chunk0[t]) * MT_CHUNK;
+    const long long end = min(pk.size[t], beg + MT_CHUNK);
+    const float coef = clip_coef ? clip_coef[0] : 1.f;
+    float* w = pk.w[t];
+    const float* g = pk.g[t];
+    float* s = pk.s[t];
+    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        const float gv = g[i] * coef;
+        const float sv = fmaf(gv, gv, s[i]);
+        s[i] = sv;
+        w[i] = w[i] - lr * (gv / (sqrtf(sv) + eps));
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int nasrec_bce_fwd_bwd(const float* logits, const float* y, int B, float grad_scale, float* loss, float* dlogits,
+                       void* stream) {
+    CHECK_ARG(logits && y && B > 0);
+    bce_kernel<<<1, 1024, 0, as_stream(stream)>>>(logits, y, B, grad_scale, loss, dlogits);
+    return nasrec_launch_status();
+}
+
+int64_t nasrec_sumsq_ws_floats(const int64_t* sizes, int n) {
+    int64_t c = 0;
+    for (int i = 0; i < n; ++i) c += (sizes[i] + MT_CHUNK - 1) / MT_CHUNK;
+    return c > 0 ? c : 1;
+}
+
+int nasrec_grad_norm_clip(const float* const* grads, const int64_t* sizes, int n, const float* extra_sumsq,
+                          int n_extra, float max_norm, float* partial, float* out, void* stream) {
+    CHECK_ARG(partial && out && n >= 0 && n_extra >= 0 && (n == 0 || (grads && sizes)));
+    cudaStream_t st = as_stream(stream);
+    int done = 0, poff = 0;
+    while (done < n) {
+        SumsqPack pk{};
+        int m = 0, chunks = 0;
+        for (; done + m < n && m < MT_MAX; ++m) {
+            pk.g[m] = grads[done + m];
+            pk.size[m] = sizes[done + m];
+            pk.chunk0[m] = chunks;
+            chunks += (int)((sizes[done + m] + MT_CHUNK - 1) / MT_CHUNK);
+        }
+        pk.chunk0[m] = chunks;
+        pk.n = m;
+        if (chunks > 0) {
+            sumsq_kernel<<<chunks, 256, 0, st>>>(pk, partial, poff);
+            int rc = nasrec_launch_status();
+            if (rc) return rc;
+        }
+        poff += chunks;
+        done += m;
+    }
+    clip_finalize_kernel<<<1, 1024, 0, st>>>(partial, poff, extra_sumsq, n_extra, max_norm, out);
+    return nasrec_launch_status();
+}
+
+int nasrec_adagrad_multi(float* const* w, const float* const* grads, float* const* state, const int64_t* sizes,
+                         int n, float lr, float eps, const float* clip_coef, void* stream) {
+    CHECK_ARG(n >= 0 && (n == 0 || (w && grads && state && sizes)));
+    cudaStream_t st = as_stream(stream);
+    int done = 0;
+    while (done < n) {
+        AdagradPack pk{};
+        int m = 0, chunks = 0;
+        for (; done + m < n && m < MT_MAX; ++m) {
+            pk.w[m] = w[done + m];
+            pk.g[m] = grads[done + m];
+            pk.s[m] = state[done + m];
+            pk.size[m] = sizes[done + m];
+            pk.chunk0[m] = chunks;
+            chunks += (int)((sizes[done + m] + MT_CHUNK - 1) / MT_CHUNK);
+        }
+        pk.chunk0[m] = chunks;
+        pk.n = m;
+        if (chunks > 0) {
+            adagrad_kernel<<<chunks, 256, 0, st>>>(pk, lr, eps, clip_coef);
+            int rc = nasrec_launch_status();
+            if (rc) return rc;
+        }
+        done += m;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""Mirror of the step body in ``nasrec/utils/train_utils.py`` plus the fused trainer.
+
+* ``init_weights`` / ``warmup_supernet_model`` / ``warmup_model`` / ``accuracy`` /
+  ``get_l2_loss`` keep the reference's names and semantics (train_utils.py:70-127,
+  393-433).
+* ``reference_style_step`` is the reference's own step body (train_utils.py:262-286)
+  run on the CUDA model with stock ``torch.optim.Adagrad`` / ``clip_grad_norm_`` --
+  the drop-in path.
+* ``FusedTrainer`` is the B200 fast path for the same step: forward tape -> fused
+  BCE -> backward tape -> one global-norm reduction -> multi-tensor Adagrad on the
+  dense parameters that took part + row-wise Adagrad on the touched embedding rows.
+  It is mathematically the reference step when wd == 0: untouched rows
+  and unused parameters have zero gradient, for which Adagrad is the identity.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .. import engine as eng
+from ..engine import Tape, Var
+from ..supernet.modules import Run
+from ..supernet.supernet import SuperNet
+
+
+def init_weights(m):
+    """train_utils.py:70-89 (exact type matches, so LayerNorm and MHA.out_proj keep their init)."""
+    if type(m) == nn.Embedding:
+        torch.nn.init.xavier_normal_(m.weight)
+    elif type(m) == nn.Linear:
+        torch.nn.init.xavier_uniform_(m.weight)
+        if m.bias is not None:
+            torch.nn.init.zeros_(m.bias)
+    elif type(m) == nn.MultiheadAttention:
+        for p in m.parameters():
+            if len(p.size()) > 1:
+                torch.nn.init.xavier_uniform_(p)
+            else:
+                torch.nn.init.zeros_(p)
+
+
+def get_l2_loss(model: nn.Module, reg: float, no_reg_param_name=None, gpu=None):
+    """train_utils.py:91-115."""
+    if reg == 0:
+        return torch.tensor(0.0).to(gpu)
+    reg_loss = None
+    for n, m in model.named_parameters():
+        if len(m.shape) == 1 or ((no_reg_param_name is not None) and n.startswith(no_reg_param_name)):
+            continue
+        r = torch.square(torch.norm(m, p=2)) * reg
+        reg_loss = r if reg_loss is None else reg_loss + r
+    return reg_loss
+
+
+def accuracy(gt, pred):
+    """train_utils.py:118-126."""
+    pred_binary = torch.gt(pred, 0.5).float()
+    return (pred_binary == gt).sum() / pred_binary.size(0)
+
+
+def warmup_model(model: nn.Module, train_loader, gpu):
+    """train_utils.py:393-410."""
+    model = model.to(gpu)
+    int_x, cat_x, _ = next(iter(train_loader))
+    with torch.no_grad():
+        model(int_x.to(gpu), cat_x.to(gpu))
+    return model
+
+
+def warmup_supernet_model(model: nn.Module, train_loader, gpu):
+    """train_utils.py:413-433: one full-path forward materialises every lazy layer."""
+    assert isinstance(model, SuperNet), NotImplementedError(
+        "For 'warmup_supernet_model', the passed in model must be a 'SuperNet' object.")
+    model = model.to(gpu)
+    int_x, cat_x, _ = next(iter(train_loader))
+    model.configure_path_sampling_strategy("full-path")
+    with torch.no_grad():
+        model(int_x.to(gpu), cat_x.to(gpu))
+    return model
+
+
+def reference_style_step(model, optimizer, loss_fn, int_x, cat_x, y, grad_clip_value: Optional[float] = 5.0):
+    """train_utils.py:262-286 verbatim in structure, on the CUDA model."""
+    optimizer.zero_grad()
+    res = model(int_x, cat_x)
+    loss = loss_fn(res, y)
+    loss.backward()
+    if grad_clip_value is not None:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), grad_clip_value)
+    optimizer.step()
+    return res, loss
+
+
+class FusedTrainer:
+    """Fused step for SuperNet training (weight sharing or fixed), wd == 0."""
+
+    def __init__(self, model: SuperNet, lr: float, eps: float = 1e-2, clip: Optional[float] = 5.0):
+        self.model = model
+        self.lr = lr
+        self.eps = eps
+        self.clip = clip
+        self.state: Dict[int, torch.Tensor] = {}
+        self._emb_state: Optional[List[torch.Tensor]] = None
+        self._emb_ptrs = None
+        self.last_total_norm: Optional[torch.Tensor] = None
+
+    def _state_of(self, p: torch.Tensor) -> torch.Tensor:
+        s = self.state.get(id(p))
+        if s is None:
+            s = torch.zeros_like(p)
+            self.state[id(p)] = s
+        return s
+
+    def _emb_tables(self):
+        ws = [m.weight for m in self.model._embedding]
+        key = tuple(w.data_ptr() for w in ws)
+        if self._emb_ptrs is None or self._emb_ptrs[0] != key:
+            dev = ws[0].device
+            states = [self._state_of(w) for w in ws]
+            self._emb_ptrs = (key, torch.tensor(list(key), dtype=torch.int64, device=dev),
+                              torch.tensor([s.data_ptr() for s in states], dtype=torch.int64, device=dev))
+        return self._emb_ptrs[1], self._emb_ptrs[2]
+
+    def forward_backward(self, int_x, cat_x, y, grad_scale: float = 1.0):
+        """One forward + backward; returns (logits, loss[1], run, sparse grads)."""
+        model = self.model
+        macro, micro = model._sample()
+        if model._needs_materialize():
+            model.materialize(int_x.shape[1])
+        tape = Tape(True)
+        sink: list = []
+        run = Run(tape, sparse_sink=sink)
+        cat = cat_x if cat_x.dtype == torch.int64 else cat_x.long()
+        logits = model._run_network(run, Var(int_x.contiguous()), cat.contiguous(), macro, micro)
+        loss, dl = eng.bce_with_logits(logits.t, y, grad_scale=grad_scale)
+        logits.g = dl
+        tape.backward()
+        return logits.t, loss, run, (sink[0] if sink else None)
+
+    def apply(self, run: Run, sparse, lr: Optional[float] = None):
+        """Global-norm clip + Adagrad on everything that received a gradient."""
+        lr = self.lr if lr is None else lr
+        emb_ids = {id(m.weight) for m in self.model._embedding}
+        dense = [h for h in run.touched() if h.g is not None and id(h.p) not in emb_ids]
+        dev = self.model._final.weight.device
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        sizes = [h.g.numel() for h in dense]
+        if self.clip is not None:
+            gp = _lib.ptr_array([h.g.data_ptr() for h in dense])
+            sz = _lib.i64_array(sizes)
+            nws = _lib.query("nasrec_sumsq_ws_floats", sz, len(dense))
+            partial = torch.empty(nws, dtype=torch.float32, device=dev)
+            _lib.call("nasrec_grad_norm_clip", gp, sz, len(dense),
+                      sparse.sumsq.data_ptr() if sparse is not None else None,
+                      sparse.F if sparse is not None else 0, float(self.clip), partial.data_ptr(), out.data_ptr())
+            coef = out.data_ptr() + 4
+            self.last_total_norm = out[0:1]
+        else:
+            coef = None
+        if dense:
+            _lib.call("nasrec_adagrad_multi", _lib.ptr_array([h.t.data_ptr() for h in dense]),
+                      _lib.ptr_array([h.g.data_ptr() for h in dense]),
+                      _lib.ptr_array([self._state_of(h.p).data_ptr() for h in dense]), _lib.i64_array(sizes),
+                      len(dense), float(lr), float(self.eps), coef)
+        if sparse is not None:
+            tp, sp = self._emb_tables()
+            _lib.call("nasrec_emb_rowwise_adagrad", sparse.uniq.data_ptr(), sparse.nuniq.data_ptr(),
+                      sparse.row_grad.data_ptr(), tp.data_ptr(), sp.data_ptr(), sparse.B, sparse.F, float(lr),
+                      float(self.eps), coef)
+
+    def step(self, int_x, cat_x, y, lr: Optional[float] = None):
+        logits, loss, run, sparse = self.forward_backward(int_x, cat_x, y)
+        self.apply(run, sparse, lr)
+        return logits, loss

