@@ -1,0 +1,477 @@
+#!/usr/bin/env python
+"""bench.py -- NASRec supernet hot path on B200 (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload at every N (weak scaling, BASELINE.json configs[1]): NASRec-Small ("autoctr")
+weight-sharing supernet TRAINING step on synthetic Criteo-shape data (13 dense + 26 sparse),
+embedding tables capped at 0.5 M rows, use_layernorm=1, strategy "default",
+anypath_choice "binomial-0.5", warm-up exhausted (a freshly sampled subnet every step),
+B = 512 per GPU, step = forward + BCE + backward + global-norm clip 5.0 + Adagrad(0.12, eps 1e-2).
+
+One JSON line on stdout (rank 0).  `value` = samples/s with inputs resident in HBM, each step
+timed with CUDA events on the launching stream, L2 flushed between steps, max over ranks.
+`e2e` = the same step driven from pinned HOST batches (H2D copies inside the timed region) with
+the loss read back every step.  `roofline` = the dominant kernel (the segment-list SGEMM),
+timed launch by launch with CUDA events in a separate instrumented pass.  `cpu_baseline` = the
+reference algorithm (oracle port: zero-padded dense math + dense Adagrad over every table row)
+timed on this box's host cores on a bounded sample.  `extra` carries BASELINE configs[0]
+(Criteo NASRec-Full best fixed model, B=256: the ">=100x CPU" target) and configs[2]
+(one-shot scoring of sampled NASRec-Full subnets, subnets/s).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "supernet_train_samples_per_sec"
+UNIT = "samples/s"
+B_TRAIN = 512
+CAP = 500000
+LR = 0.12
+WORKLOAD = ("NASRec-Small (autoctr) supernet training, synthetic Criteo shape 13 dense + 26 sparse, tables capped "
+            "0.5M rows, B=512/GPU, LN on, default/binomial-0.5 sampling, Adagrad+clip5")
+_CRITEO = [1461, 584, 10131227, 2202609, 306, 25, 12518, 634, 4, 93146, 5684, 8351593, 3195, 28, 14993, 5461307, 11,
+           5653, 2174, 5, 7046548, 19, 16, 286182, 106, 142573]
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def synth_pool(n_batches, batch, nd, num_embeddings, seed, zipf=True):
+    """log1p(Poisson(3)) dense, Zipf(1.05)-ranked ids through a fixed permutation with id 0 =
+    'missing' (p=0.02), Bernoulli(0.25) labels; a pool of distinct batches that is cycled."""
+    rs = np.random.RandomState(seed)
+    pool = []
+    for _ in range(n_batches):
+        int_x = np.log1p(rs.poisson(3.0, (batch, nd))).astype(np.float32)
+        cols = []
+        for n in num_embeddings:
+            if n <= 1:
+                c = np.zeros(batch, np.int64)
+            elif zipf:
+                r = np.minimum(rs.zipf(1.05, batch), n - 1).astype(np.int64)
+                c = (r * 2654435761 % (n - 1)) + 1
+            else:
+                c = rs.randint(1, n, batch).astype(np.int64)
+            c[rs.rand(batch) < 0.02] = 0
+            cols.append(c)
+        y = (rs.rand(batch, 1) < 0.25).astype(np.float32)
+        pool.append((int_x, np.stack(cols, 1), y))
+    return pool
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th is not None:
+            self._th.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_baseline_supernet(steps, warmup, seed=1234):
+    """Reference algorithm on the host cores: zero-padded masked modules, dense embedding grads,
+    dense Adagrad over all rows (oracle/nasrec_oracle.py, pinned to the reference by tests/golden)."""
+    import torch
+    from oracle import nasrec_oracle as orc
+    from nasrec_b200 import SuperNet, ops_config_lib
+    from nasrec_b200.utils.train_utils import init_weights
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ne = [min(x, CAP) for x in _CRITEO]
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    host = SuperNet(num_blocks=7, ops_config=ops_config_lib["autoctr"], use_layernorm=True, num_embeddings=ne,
+                    path_sampling_strategy="default", anypath_choice="binomial-0.5", supernet_training_steps=0)
+    host.materialize(13)            # host-only: no kernels involved
+    host.apply(init_weights)
+    sd = {k: v.detach().clone() for k, v in host.state_dict().items()}
+    cfg = dict(ops="autoctr", use_layernorm=True, fixed=False, num_blocks=7)
+    tr = orc.OracleTrainer(sd, cfg, lr=LR)
+    pool = synth_pool(max(2, min(8, steps + warmup)), B_TRAIN, 13, ne, seed)
+    times = []
+    for i in range(warmup + steps):
+        host._sample()
+        b = pool[i % len(pool)]
+        t0 = time.perf_counter()
+        tr.step(host.choice, torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2]))
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    med = float(np.median(times))
+    return {"value": B_TRAIN / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d timed steps of B=%d (median) after %d warm-up, torch %d threads" % (
+                steps, B_TRAIN, warmup, cores)}, med
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, med = cpu_baseline_supernet(max(1, min(args.steps, 6)), max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B_TRAIN}, "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- per-kernel timer (roofline)
+class GemmTimer:
+    """Wraps nasrec_b200._lib.call to time every segment-GEMM launch with CUDA events on the
+    launching stream and to count its ALGORITHMIC flops (2*M*N*K over the live support only)."""
+    NAMES = ("nasrec_seg_linear_fwd", "nasrec_seg_linear_dgrad", "nasrec_seg_linear_wgrad", "nasrec_sproj_fwd",
+             "nasrec_sproj_dgrad", "nasrec_sproj_wgrad")
+
+    def __init__(self, torch, lib):
+        self.torch, self.lib, self.events, self.flops, self.orig = torch, lib, [], 0.0, lib.call
+        self.per = {}
+
+    @staticmethod
+    def _ksum(seg_arr, n):
+        return sum(int(seg_arr[4 * i + 2]) for i in range(n))
+
+    def _flops(self, name, a):
+        if name == "nasrec_seg_linear_fwd":
+            return 2.0 * a[9] * a[5] * self._ksum(a[0], a[1])
+        if name == "nasrec_seg_linear_dgrad":
+            return 2.0 * a[8] * a[2] * self._ksum(a[6], a[7])
+        if name == "nasrec_seg_linear_wgrad":
+            return 2.0 * a[8] * a[2] * self._ksum(a[3], a[4])
+        if name == "nasrec_sproj_fwd":
+            return 2.0 * a[8] * 16 * a[4] * self._ksum(a[0], a[1])
+        if name == "nasrec_sproj_dgrad":
+            return 2.0 * a[7] * 16 * a[2] * self._ksum(a[5], a[6])
+        return 2.0 * a[7] * 16 * a[2] * self._ksum(a[3], a[4])      # sproj_wgrad
+
+    def __enter__(self):
+        def timed(name, *a):
+            if name not in self.NAMES:
+                return self.orig(name, *a)
+            e0 = self.torch.cuda.Event(enable_timing=True)
+            e1 = self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.orig(name, *a)
+            e1.record()
+            f = self._flops(name, a)
+            self.events.append((name, e0, e1, f))
+        self.lib.call = timed
+        return self
+
+    def __exit__(self, *exc):
+        self.lib.call = self.orig
+        self.torch.cuda.synchronize()
+        for name, e0, e1, f in self.events:
+            ms = e0.elapsed_time(e1)
+            p = self.per.setdefault(name, [0, 0.0, 0.0])
+            p[0] += 1
+            p[1] += ms
+            p[2] += f
+
+    def summary(self):
+        n = sum(p[0] for p in self.per.values())
+        ms = sum(p[1] for p in self.per.values())
+        fl = sum(p[2] for p in self.per.values())
+        return n, ms, fl
+
+
+# ----------------------------------------------------------------------------- main (ours)
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nasrec_b200 import SuperNet, ops_config_lib, _lib
+    from nasrec_b200.parallel import DataParallelTrainer, shard_range, gather_results
+    from nasrec_b200.utils.train_utils import FusedTrainer, init_weights
+    from nasrec_b200.search import SubnetEvaluator, generate_random_choice
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, args.warmup
+    assert W >= 3, "timing rules: at least 3 warm-up steps"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- model (identical on every rank: same seeds) ----
+    ne = [min(x, CAP) for x in _CRITEO]
+    torch.manual_seed(1234)
+    np.random.seed(1234)
+    model = SuperNet(num_blocks=7, ops_config=ops_config_lib["autoctr"], use_layernorm=True, num_embeddings=ne,
+                     path_sampling_strategy="default", anypath_choice="binomial-0.5",
+                     supernet_training_steps=0).to(dev)
+    model.materialize(13)
+    model.apply(init_weights)
+    trainer = DataParallelTrainer(model, lr=LR) if world > 1 else FusedTrainer(model, lr=LR)
+
+    pool_h = synth_pool(64, B_TRAIN, 13, ne, seed=1234 + rank)      # different data per rank, same choices
+    pool_d = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in pool_h]
+    pool_p = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in pool_h]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    # ---- warm-up ----
+    for i in range(W):
+        trainer.step(*pool_d[i % 64])
+    barrier()
+
+    # ---- value: inputs resident in HBM, per-step CUDA events, L2 flushed between steps ----
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    l0 = _lib.LIB.launches
+    barrier()
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record()
+        trainer.step(*pool_d[(W + i) % 64])
+        ev[i][1].record()
+    barrier()
+    launches = _lib.LIB.launches - l0
+    total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    clk = clocks.stop()
+    ms_per_step = total_ms / K
+    value = world * B_TRAIN * K / (total_ms * 1e-3)
+
+    # ---- pipelined (back-to-back, one event pair; informational) ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        trainer.step(*pool_d[(W + K + i) % 64])
+    e1.record()
+    barrier()
+    pipelined = world * B_TRAIN * K / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+
+    # ---- e2e: pinned host batches, H2D inside the timed region, loss read back each step ----
+    h2d = sum(a.numel() * a.element_size() for a in pool_p[0])
+    barrier()
+    e0.record()
+    last = 0.0
+    for i in range(K):
+        b = pool_p[(W + 2 * K + i) % 64]
+        xb = tuple(t.to(dev, non_blocking=True) for t in b)
+        _, loss = trainer.step(*xb)
+        last = float(loss.item())                       # D2H read of the step's result
+    e1.record()
+    barrier()
+    e2e = world * B_TRAIN * K / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "per_gpu_batch": B_TRAIN, "global_batch": B_TRAIN * world,
+                           "parallelism": "dp%d" % world, "l2": "256 MB flush write between timed steps",
+                           "ids": "zipf(1.05)"},
+                "clocks": clk, "gpu_launches": launches,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "last_loss": last},
+                "pipelined_value": pipelined}
+
+    # ---- N == 1 only: roofline pass, CPU baseline, the other BASELINE configs ----
+    if world == 1:
+        with GemmTimer(torch, _lib) as gt:
+            for i in range(min(K, 10)):
+                flush.zero_()
+                trainer.step(*pool_d[i % 64])
+        n, ms, fl = gt.summary()
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, which = float(peaks["bf16_tflops_sustained"]), "measured bf16_tflops_sustained"
+        except Exception:
+            peak, which = 1590.0, "fallback"
+        achieved = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm64_kernel (segment-list SGEMM, fp32 FFMA)",
+                            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                            "peak_source": which, "traffic": None, "launches_timed": n,
+                            "avg_launch_us": ms * 1e3 / max(n, 1), "gflop_per_launch": fl / max(n, 1) / 1e9,
+                            "share_of_step": ms / (min(K, 10) * ms_per_step) if ms_per_step > 0 else None,
+                            "by_entry_point": {k: {"launches": v[0], "ms": v[1], "gflop": v[2] / 1e9}
+                                               for k, v in gt.per.items()}}
+        line["extra"] = {}
+        if not args.no_extras:
+            line["extra"].update(extra_fixed_best(torch, _lib, dev, flush))
+            line["extra"].update(extra_ea_eval(torch, _lib, dev))
+        if not args.no_cpu:
+            base, _ = cpu_baseline_supernet(3, 1)
+            line["cpu_baseline"] = base
+            if not args.no_extras:
+                line["extra"]["criteo_full_best_cpu_port_samples_per_sec"] = cpu_baseline_fixed(3, 1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _best_choice():
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "fixed_best.json")))
+    return meta["models"]["criteo_xlarge"]["choice"]
+
+
+def extra_fixed_best(torch, _lib, dev, flush, steps=30, warm=5):
+    """BASELINE configs[0]: Criteo NASRec-Full best model (fixed, use_layernorm=False as
+    main_train.py:262 forces), B=256, lr 0.16, capped AND full-size tables."""
+    from nasrec_b200 import SuperNet, ops_config_lib
+    from nasrec_b200.utils.train_utils import FusedTrainer, init_weights
+    out = {}
+    for tag, ne in (("capped", [min(x, CAP) for x in _CRITEO]), ("full", list(_CRITEO))):
+        torch.manual_seed(1)
+        m = SuperNet(num_blocks=7, ops_config=ops_config_lib["xlarge"], use_layernorm=False, num_embeddings=ne,
+                     path_sampling_strategy="fixed-path", fixed=True, fixed_choice=_best_choice()).to(dev)
+        m.materialize(13)
+        m.apply(init_weights)
+        tr = FusedTrainer(m, lr=0.16)
+        pool = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in synth_pool(16, 256, 13, ne, 7)]
+        for i in range(warm):
+            tr.step(*pool[i % 16])
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            flush.zero_()
+            ev[i][0].record()
+            tr.step(*pool[i % 16])
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        out["criteo_full_best_train_samples_per_sec_%s_tables" % tag] = 256 / (ms * 1e-3)
+        del m, tr, pool
+        torch.cuda.empty_cache()
+    return out
+
+
+def cpu_baseline_fixed(steps, warmup):
+    import torch
+    from oracle import nasrec_oracle as orc
+    from nasrec_b200 import SuperNet, ops_config_lib
+    from nasrec_b200.utils.train_utils import init_weights
+    ne = [min(x, CAP) for x in _CRITEO]
+    choice = _best_choice()
+    host = SuperNet(num_blocks=7, ops_config=ops_config_lib["xlarge"], use_layernorm=False, num_embeddings=ne,
+                    path_sampling_strategy="fixed-path", fixed=True, fixed_choice=choice)
+    host.materialize(13)
+    host.apply(init_weights)
+    sd = {k: v.detach().clone() for k, v in host.state_dict().items()}
+    tr = orc.OracleTrainer(sd, dict(ops="xlarge", use_layernorm=False, fixed=True, num_blocks=7), lr=0.16)
+    pool = synth_pool(4, 256, 13, ne, 7)
+    times = []
+    for i in range(warmup + steps):
+        b = pool[i % 4]
+        t0 = time.perf_counter()
+        tr.step(choice, torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2]))
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return 256 / float(np.median(times))
+
+
+def extra_ea_eval(torch, _lib, dev, n_cand=16, n_batches=4, B=8192):
+    """BASELINE configs[2] (sample): one-shot scoring of random NASRec-Full candidates against a
+    shared Criteo xlarge supernet; each candidate = n_batches x 8192 eval samples -> loss/AUC.
+    Reported as subnets/s at this reduced batch count and extrapolated to the recipe's 150."""
+    from nasrec_b200 import SuperNet, ops_config_lib
+    from nasrec_b200.search import SubnetEvaluator, generate_random_choice
+    from nasrec_b200.utils.train_utils import init_weights
+    ne = [min(x, CAP) for x in _CRITEO]
+    torch.manual_seed(2)
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib["xlarge"], use_layernorm=True, num_embeddings=ne,
+                 path_sampling_strategy="full-path").to(dev)
+    m.materialize(13)
+    m.apply(init_weights)
+    m.requires_grad_(False)
+    np.random.seed(1234)
+    cands = [generate_random_choice(7, ops_config_lib["xlarge"]) for _ in range(n_cand + 2)]
+    batches = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in synth_pool(n_batches, B, 13, ne, 11)]
+    ev = SubnetEvaluator(m)
+    ev.score(cands[:2], batches)                     # warm-up (also fills the shared gather cache)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = ev.score(cands[2:], batches)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    out = {"ea_subnets_per_sec_%dx%d" % (n_batches, B): n_cand / sec,
+           "ea_eval_samples_per_sec": n_cand * n_batches * B / sec,
+           "ea_subnets_per_sec_150x8192_extrapolated": n_cand / sec * n_batches / 150.0,
+           "ea_mean_auc": float(np.mean([r["test_auroc"] for r in res]))}
+    del m, ev, batches
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip BASELINE configs[0]/[2] side measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,13 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import call, query
+from ._lib import query
+
+
+def call(name: str, *args):
+    # late-bound so that bench.py's per-kernel timer can wrap _lib.call
+    _lib.call(name, *args)
+
 
 E = 16                 # embedding dim (supernet.py:224)
 LN_EPS = 1e-5
@@ -539,17 +545,47 @@ class SparseEmbGrad:
     __slots__ = ("uniq", "nuniq", "row_grad", "sumsq", "B", "F")
 
 
+class SparseSink(list):
+    """Receives the embedding gradient of a step instead of dense [N_f,16] tensors.
+    defer=True stores the raw (cat_x, d_out) pair (data-parallel training gathers
+    them across ranks before the sorted-row reduction)."""
+    defer = False
+
+
+def reduce_sparse(cat_x: torch.Tensor, gout: torch.Tensor) -> SparseEmbGrad:
+    """Deterministic sorted-row reduction of d(sparse)[B,F,16] (nasrec_emb_grad_sort_reduce)."""
+    B, F = cat_x.shape
+    dev = cat_x.device
+    sg = SparseEmbGrad()
+    sg.B, sg.F = B, F
+    sg.uniq = torch.empty(F, B, dtype=torch.int64, device=dev)
+    sg.nuniq = torch.empty(F, dtype=torch.int32, device=dev)
+    sg.row_grad = torch.empty(F, B, E, dtype=torch.float32, device=dev)
+    sg.sumsq = torch.empty(F, dtype=torch.float32, device=dev)
+    scratch = torch.empty(F, B + 1, dtype=torch.int32, device=dev)
+    call("nasrec_emb_grad_sort_reduce", cat_x.data_ptr(), _p(gout), B, F, sg.uniq.data_ptr(), sg.nuniq.data_ptr(),
+         _p(sg.row_grad), _p(sg.sumsq), scratch.data_ptr())
+    return sg
+
+
 def embedding(tape: Tape, tables: EmbeddingTables, weights: Sequence[PVar], cat_x: torch.Tensor,
-              sparse_sink: Optional[list] = None) -> Var:
+              sparse_sink: Optional[list] = None, cache: Optional[dict] = None) -> Var:
     """sparse[b,f,:] = W_f[cat[b,f],:]  (supernet.py:412-430).  Backward: sorted-row
     reduction; dense [N_f,16] grads (reference layout) unless `sparse_sink` is given,
     in which case the reduced rows are handed to the fused optimizer instead."""
     B, F = cat_x.shape
+    req = any(w.req for w in weights)
+    if cache is not None and not req:
+        # frozen tables (one-shot candidate scoring): one gather per batch, shared by every candidate
+        hit = cache.get(cat_x.data_ptr())
+        if hit is not None:
+            return Var(hit)
     tables.refresh([w.t for w in weights])
     out = Var(torch.empty(B, F, E, dtype=torch.float32, device=cat_x.device))
     call("nasrec_emb_gather_fwd", _p_i(tables.ptrs), _p_i(tables.rows), _p_i(cat_x), _p(out.t), B, F,
          _p_i(tables.err))
-    req = any(w.req for w in weights)
+    if cache is not None and not req:
+        cache[cat_x.data_ptr()] = out.t
     out.req = req
     if not (tape.enabled and req):
         return out
@@ -558,15 +594,10 @@ def embedding(tape: Tape, tables: EmbeddingTables, weights: Sequence[PVar], cat_
         if out.g is None:
             return
         dev = cat_x.device
-        sg = SparseEmbGrad()
-        sg.B, sg.F = B, F
-        sg.uniq = torch.empty(F, B, dtype=torch.int64, device=dev)
-        sg.nuniq = torch.empty(F, dtype=torch.int32, device=dev)
-        sg.row_grad = torch.empty(F, B, E, dtype=torch.float32, device=dev)
-        sg.sumsq = torch.empty(F, dtype=torch.float32, device=dev)
-        scratch = torch.empty(F, B + 1, dtype=torch.int32, device=dev)
-        call("nasrec_emb_grad_sort_reduce", _p_i(cat_x), _p(out.g), B, F, _p_i(sg.uniq), _p_i(sg.nuniq),
-             _p(sg.row_grad), _p(sg.sumsq), _p_i(scratch))
+        if sparse_sink is not None and getattr(sparse_sink, "defer", False):
+            sparse_sink.append((cat_x, out.g))
+            return
+        sg = reduce_sparse(cat_x, out.g)
         if sparse_sink is not None:
             sparse_sink.append(sg)
             return

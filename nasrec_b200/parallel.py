@@ -1,0 +1,107 @@
+"""Single-node multi-GPU: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch).
+
+The reference has no collectives at all (its only multi-GPU mechanism is one OS
+process per EA candidate, searcher/searcher.py:126-156).  The hot path shards in
+exactly two ways:
+
+* data-parallel supernet training: same-seed choice on every rank, one all-reduce
+  of the *active subnet's* dense gradients, an all-gather of the (ids, d_embedding)
+  pairs followed by the same deterministic sorted-row Adagrad on every replica
+  (replicas stay bit-identical), the clip norm computed on the already-global grads;
+* EA candidate scoring: candidates partitioned across ranks, no data-path
+  collective, one final gather of (loss, AUC, accuracy) per candidate.
+
+The helpers are device-agnostic so the host logic is testable with gloo on CPU.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import engine as eng
+from .utils.train_utils import FusedTrainer
+
+
+def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous partition of candidates (sizes differ by at most one)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_flat(tensors: Sequence[torch.Tensor], group=None) -> List[torch.Tensor]:
+    """Sum-all-reduce a list of tensors as ONE bucket; returns views into the bucket
+    (replacing the inputs), so no copy-back pass is needed."""
+    if not tensors:
+        return []
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    out, o = [], 0
+    for t in tensors:
+        n = t.numel()
+        out.append(flat[o:o + n].view(t.shape))
+        o += n
+    return out
+
+
+def allgather_cat(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate equally-shaped per-rank tensors along dim 0, in rank order."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+def gather_results(local: Sequence[Sequence[float]], n_total: int, group=None) -> Optional[torch.Tensor]:
+    """Final EA gather: every rank contributes [n_local, k] floats; rank 0 gets [n_total, k]
+    in candidate order (shards are contiguous, so rank order == candidate order)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    k = len(local[0]) if len(local) else 0
+    kk = torch.tensor([k], dtype=torch.int64)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    kk = kk.to(dev)
+    dist.all_reduce(kk, op=dist.ReduceOp.MAX, group=group)
+    k = int(kk.item())
+    pad = max(shard_range(n_total, world, r)[1] - shard_range(n_total, world, r)[0] for r in range(world))
+    buf = torch.zeros(pad, k, dtype=torch.float64, device=dev)
+    if len(local):
+        buf[:len(local)] = torch.tensor(local, dtype=torch.float64, device=dev)
+    allb = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(allb, buf, group=group)
+    if rank != 0:
+        return None
+    rows = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, world, r)
+        rows.append(allb[r][:hi - lo])
+    return torch.cat(rows).cpu()
+
+
+class DataParallelTrainer(FusedTrainer):
+    """Data-parallel fused step.  Every rank must seed numpy identically so that the
+    sampled subnet (and therefore the gradient support) coincides on all ranks."""
+
+    def __init__(self, model, lr, eps: float = 1e-2, clip: Optional[float] = 5.0, group=None):
+        super().__init__(model, lr, eps, clip)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.defer_sparse = self.world > 1
+
+    def step(self, int_x, cat_x, y, lr: Optional[float] = None):
+        if self.world == 1:
+            return super().step(int_x, cat_x, y, lr)
+        # local loss is a mean over the local batch; scale so the summed gradient is the
+        # gradient of the mean over the GLOBAL batch (BCEWithLogitsLoss 'mean', train_utils.py:266)
+        logits, loss, run, raw = self.forward_backward(int_x, cat_x, y, grad_scale=1.0 / self.world)
+        emb_ids = {id(m.weight) for m in self.model._embedding}
+        dense = [h for h in run.touched() if h.g is not None and id(h.p) not in emb_ids]
+        for h, g in zip(dense, allreduce_flat([h.g for h in dense], self.group)):
+            h.g = g
+        sparse = None
+        if raw is not None:
+            cat_l, gout_l = raw
+            sparse = eng.reduce_sparse(allgather_cat(cat_l, self.group), allgather_cat(gout_l, self.group))
+        self.apply(run, sparse, lr)
+        return logits, loss

@@ -94,11 +94,13 @@ _zeros_generator = CleverZeroTensorGenerator()
 class Run:
     """Per-forward context: the tape plus the parameter handles."""
 
-    def __init__(self, tape: Tape, grad_ok=None, sparse_sink: Optional[list] = None):
+    def __init__(self, tape: Tape, grad_ok=None, sparse_sink: Optional[list] = None,
+                 emb_cache: Optional[dict] = None):
         self.tape = tape
         self._pv = {}
         self._grad_ok = grad_ok          # None: honour requires_grad; else set of id(param) allowed
         self.sparse_sink = sparse_sink
+        self.emb_cache = emb_cache
 
     def pv(self, p: Optional[torch.Tensor]) -> Optional[PVar]:
         if p is None:

@@ -447,7 +447,7 @@ class SuperNet(nn.Module):
         if cat_x.shape != (B, F):
             raise ValueError("cat_feats must be [%d, %d], got %s" % (B, F, tuple(cat_x.shape)))
         sp0 = eng.embedding(run.tape, self._tables, [run.pv(m.weight) for m in self._embedding], cat_x,
-                            sparse_sink=run.sparse_sink)
+                            sparse_sink=run.sparse_sink, cache=run.emb_cache)
         dsrc: List[Optional[_DSrc]] = [_DSrc(int_x, nd_)]
         ssrc: List[Optional[_SSrc]] = [_SSrc(sp0, F, 0)]
         live = self._liveness(macro, micro)

@@ -106,6 +106,7 @@ class FusedTrainer:
         self._emb_state: Optional[List[torch.Tensor]] = None
         self._emb_ptrs = None
         self.last_total_norm: Optional[torch.Tensor] = None
+        self.defer_sparse = False
 
     def _state_of(self, p: torch.Tensor) -> torch.Tensor:
         s = self.state.get(id(p))
@@ -131,7 +132,8 @@ class FusedTrainer:
         if model._needs_materialize():
             model.materialize(int_x.shape[1])
         tape = Tape(True)
-        sink: list = []
+        sink = eng.SparseSink()
+        sink.defer = self.defer_sparse
         run = Run(tape, sparse_sink=sink)
         cat = cat_x if cat_x.dtype == torch.int64 else cat_x.long()
         logits = model._run_network(run, Var(int_x.contiguous()), cat.contiguous(), macro, micro)
