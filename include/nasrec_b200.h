@@ -50,6 +50,15 @@ typedef struct {
  * capability the kernels were compiled for (100 for sm_100a). */
 int nasrec_version(int* sm);
 
+/* GEMM arithmetic mode of every nasrec_seg_linear_* / nasrec_sproj_* entry point:
+ *   0  fp32 FFMA on CUDA cores (reference-exact fp32 products);
+ *   3  tcgen05 kind::tf32 tensor cores, each fp32 operand split into tf32 hi+lo, products
+ *      hi*hi + hi*lo + lo*hi accumulated in fp32 Tensor Memory ("3xTF32");
+ *   4  as 3 plus lo*lo;   1  plain single-pass tf32 (not fp32 parity; diagnostics only).
+ * Process-wide; returns 0 or NASREC_EINVAL. */
+int nasrec_set_gemm_mode(int mode);
+int nasrec_get_gemm_mode(void);
+
 /* ------------------------------------------------------------------ embedding
  * a1  SuperNet._input_stem_layers_bi_output, supernet.py:404-430:
  *     out[b,f,:] = tables[f][idx[b,f],:]   (F nn.Embedding lookups + torch.stack).

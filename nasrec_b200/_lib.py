@@ -61,7 +61,7 @@ _SIGS_I64 = {
     "nasrec_attn_bwd_ws_floats": [_i],
     "nasrec_sumsq_ws_floats": [_f, _i],
 }
-EXPORTS = ["nasrec_version"] + list(_SIGS) + list(_SIGS_I64)
+EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode"] + list(_SIGS) + list(_SIGS_I64)
 
 
 class _Lib:
@@ -88,9 +88,27 @@ class _Lib:
             fn.argtypes = argtypes
             fn.restype = C.c_int64
             self.fn[name] = fn
+        self.cdll.nasrec_set_gemm_mode.argtypes = [C.c_int]
+        self.cdll.nasrec_set_gemm_mode.restype = C.c_int
+        self.cdll.nasrec_get_gemm_mode.argtypes = []
+        self.cdll.nasrec_get_gemm_mode.restype = C.c_int
+        mode = os.environ.get("NASREC_GEMM_MODE")
+        if mode is not None:
+            if self.cdll.nasrec_set_gemm_mode(int(mode)) != 0:
+                raise ValueError("NASREC_GEMM_MODE=%s is not one of 0,1,3,4" % mode)
         self.cdll.nasrec_version.argtypes = [C.POINTER(C.c_int)]
         self.cdll.nasrec_version.restype = C.c_int
         return self
+
+    def set_gemm_mode(self, mode: int):
+        """0 = fp32 FFMA, 3/4 = tcgen05 3xTF32 / 4xTF32, 1 = single-pass tf32 (diagnostics)."""
+        self.load()
+        if self.cdll.nasrec_set_gemm_mode(int(mode)) != 0:
+            raise ValueError("unsupported GEMM mode %r" % (mode,))
+
+    def gemm_mode(self) -> int:
+        self.load()
+        return int(self.cdll.nasrec_get_gemm_mode())
 
     def version(self) -> Tuple[int, int]:
         self.load()

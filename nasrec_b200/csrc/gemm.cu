@@ -10,49 +10,11 @@
 //
 // Replaces: F.linear on torch.cat([...zeros...]) in nasrec/supernet/modules.py
 // (:171,:223,:340,:359,:385,:489,:578,:584,:648,:740) and supernet.py:598,1140.
-#include "common.cuh"
+#include "gemm_common.cuh"
+#include "gemm_tc.cuh"
 
 namespace {
-
-struct View {
-    const float* p;
-    long long hi_i, hi_j;
-    int lo_i, lo_j, sh_i, sh_j;
-    int contig_j;   // 1: consecutive j are adjacent in memory, 0: consecutive i are
-    int pad_;
-};
-
-__device__ __forceinline__ long long voff(const View& v, int i, int j) {
-    return (long long)(i >> v.sh_i) * v.hi_i + (long long)(i & ((1 << v.sh_i) - 1)) * v.lo_i +
-           (long long)(j >> v.sh_j) * v.hi_j + (long long)(j & ((1 << v.sh_j) - 1)) * v.lo_j;
-}
-
-struct Term {
-    View a;   // A(m, k): i = m, j = k
-    View b;   // B(n, k): i = n, j = k
-    int K;
-    int pad_;
-};
-
-struct Prob {
-    int M, N, term0, nterm;
-    float* c;
-    const float* addend;          // same layout as c, or null
-    long long c_hi_i, c_hi_j;
-    int c_lo_i, c_sh_i;
-    const float* bias;            // indexed by n, or null
-    int nsplit;
-    int pad_;
-    long long split_stride;
-};
-
-constexpr int MAXP = 16, MAXT = 20;
-struct Batch {
-    int nprob;
-    int pad_;
-    Prob prob[MAXP];
-    Term term[MAXT];
-};
+using namespace nasrec_gemm;
 
 constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
 
@@ -182,6 +144,8 @@ __global__ void splitk_reduce_kernel(const __grid_constant__ RedBatch rb) {
     }
 }
 
+int g_gemm_mode = 0;   // 0: fp32 FFMA; 1/3/4: tcgen05 kind::tf32 with 1/3/4 split products
+
 View plain_view(const float* p, long long si, long long sj, int contig_j) {
     View v{};
     v.p = p;
@@ -199,6 +163,7 @@ int launch(const Batch& bt, cudaStream_t st) {
         totz += bt.prob[i].nsplit;
     }
     if (maxM <= 0 || maxN <= 0 || totz <= 0) return 0;
+    if (g_gemm_mode != 0) return nasrec_gemm::launch_tc(bt, maxM, maxN, totz, g_gemm_mode, st);
     dim3 grid(cdiv(maxN, BN), cdiv(maxM, BM), totz);
     if (grid.y > 65535 || grid.z > 65535) return NASREC_ETOOBIG;
     gemm64_kernel<<<grid, 256, 0, st>>>(bt);
@@ -215,6 +180,14 @@ bool segs_ok(const nasrec_seg_t* segs, int nseg) {
 }  // namespace
 
 extern "C" {
+
+int nasrec_set_gemm_mode(int mode) {
+    if (mode != 0 && mode != 1 && mode != 3 && mode != 4) return NASREC_EINVAL;
+    g_gemm_mode = mode;
+    return 0;
+}
+
+int nasrec_get_gemm_mode(void) { return g_gemm_mode; }
 
 int nasrec_seg_linear_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off, int N,
                           const float* bias, float* C, int64_t ldc, int M, void* stream) {
