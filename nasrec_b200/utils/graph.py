@@ -17,7 +17,7 @@ from .train_utils import FusedTrainer
 class GraphedFusedTrainer:
     """Wraps a FusedTrainer whose model always draws the same choice."""
 
-    def __init__(self, trainer: FusedTrainer, warmup_steps: int = 3):
+    def __init__(self, trainer: FusedTrainer, warmup_steps: int = 0):
         self.trainer = trainer
         self.warmup_steps = warmup_steps
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -48,7 +48,8 @@ class GraphedFusedTrainer:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(self.warmup_steps):      # allocator / lazy-state warm-up off the capture
+            self.trainer.prime(*self._static)       # lazy host state; leaves the model untouched
+            for _ in range(self.warmup_steps):      # optional real steps off the capture
                 self.trainer.step(*self._static, lr=lr)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()

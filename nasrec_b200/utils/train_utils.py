@@ -173,6 +173,16 @@ class FusedTrainer:
                       sparse.row_grad.data_ptr(), tp.data_ptr(), sp.data_ptr(), sparse.B, sparse.F, float(lr),
                       float(self.eps), coef)
 
+    def prime(self, int_x, cat_x, y):
+        """Trigger every lazy host-side initialisation (pointer tables, optimizer state,
+        kernel attributes) WITHOUT changing the model: one forward/backward whose gradients
+        are dropped.  Needed before CUDA-graph capture of step()."""
+        _, _, run, _ = self.forward_backward(int_x, cat_x, y)
+        for h in run.touched():
+            if h.g is not None or h.req:
+                self._state_of(h.p)
+        self._emb_tables()
+
     def step(self, int_x, cat_x, y, lr: Optional[float] = None):
         logits, loss, run, sparse = self.forward_backward(int_x, cat_x, y)
         self.apply(run, sparse, lr)

@@ -92,11 +92,58 @@ def case_3d(B, P, rows, bias=True):
         print("3d B=%d P=%d rows=%s mode=%d  fwd %.2e dgrad %.2e wgrad %.2e  fwd %.1f us wgrad %.1f us"
               % (B, P, rows, mode, e_f, e_d, e_w, us, usw), flush=True)
 
+def case_model(M, N, nd, nsrc, accumulate=False):
+    """Operands laid out exactly as in the supernet: contiguous sources, reference weight layout."""
+    widths = [nd] + [1024] * (nsrc - 1)
+    offs = [0] + [nd + 1024 * j for j in range(nsrc - 1)]
+    Ktot = nd + 1024 * (nsrc - 1)
+    xs = [torch.randn(M, w, generator=g).to(dev) for w in widths]
+    W = (torch.randn(N, Ktot, generator=g) / np.sqrt(Ktot)).to(dev)
+    ref = sum(x.double() @ W[:, o:o + w].double().t() for x, w, o in zip(xs, widths, offs))
+    dC = torch.randn(M, N, generator=g).to(dev)
+    dref = [dC.double() @ W[:, o:o + w].double() for w, o in zip(widths, offs)]
+    wref = [dC.double().t() @ x.double() for x in xs]
+    sp, ns = _lib.segs([(x.data_ptr(), w, w, o) for x, w, o in zip(xs, widths, offs)])
+    for mode in (0, 3):
+        _lib.LIB.set_gemm_mode(mode)
+        C = torch.zeros(M, N, device=dev)
+        _lib.call("nasrec_seg_linear_fwd", sp, ns, W.data_ptr(), Ktot, 0, N, None, C.data_ptr(), N, M)
+        base = [torch.randn_like(x) if accumulate else torch.zeros_like(x) for x in xs]
+        dxs = [b.clone() for b in base]
+        dsp, _ = _lib.segs([(x.data_ptr(), w, w, o) for x, w, o in zip(dxs, widths, offs)])
+        _lib.call("nasrec_seg_linear_dgrad", dC.data_ptr(), N, N, W.data_ptr(), Ktot, 0, dsp, ns, M, int(accumulate))
+        dW = torch.zeros_like(W)
+        _lib.call("nasrec_seg_linear_wgrad", dC.data_ptr(), N, N, sp, ns, dW.data_ptr(), Ktot, 0, M, 0)
+        torch.cuda.synchronize()
+        e_f = err(C, ref)
+        e_d = max(err(dx - (b if accumulate else 0), r) for dx, b, r in zip(dxs, base, dref))
+        e_w = max(err(dW[:, o:o + w], r) for w, o, r in zip(widths, offs, wref))
+        print("model-layout M=%d N=%d nsrc=%d acc=%d mode=%d  fwd %.2e dgrad %.2e wgrad %.2e" % (M, N, nsrc, accumulate, mode, e_f, e_d, e_w), flush=True)
+
+
 if __name__ == "__main__":
     a = torch.randn(4096, 4096, device=dev)
     t0 = time.time()
     while time.time() - t0 < 1.5:          # ramp the clocks before timing anything
         (a @ a).sum().item()
+    if len(sys.argv) > 1 and sys.argv[1] == "model":
+        for M in (5, 512):
+            for N in (1024, 16, 128):
+                for nsrc in (1, 2, 7):
+                    case_model(M, N, 13, nsrc)
+        case_model(5, 1024, 13, 7, accumulate=True)
+        _lib.LIB.set_gemm_mode(3)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "small":
+        case_2d(5, 1024, [13])
+        case_2d(5, 16, [13, 1024, 1024])
+        case_2d(5, 1024, [13, 1024])
+        case_2d(6, 16, [13])
+        case_2d(64, 13, [16])
+        case_3d(5, 64, [26])
+        case_3d(5, 45, [26, 64, 8])
+        _lib.LIB.set_gemm_mode(3)
+        sys.exit(0)
     case_2d(128, 64, [32])
     case_2d(512, 1024, [13, 1000])
     case_2d(37, 16, [300], n_off=5)
