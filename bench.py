@@ -431,7 +431,7 @@ def cpu_baseline_fixed(steps, warmup):
     return 256 / float(np.median(times))
 
 
-def extra_ea_eval(torch, _lib, dev, n_cand=16, n_batches=4, B=8192):
+def extra_ea_eval(torch, _lib, dev, n_cand=16, n_batches=8, B=8192):
     """BASELINE configs[2] (sample): one-shot scoring of random NASRec-Full candidates against a
     shared Criteo xlarge supernet; each candidate = n_batches x 8192 eval samples -> loss/AUC.
     Reported as subnets/s at this reduced batch count and extrapolated to the recipe's 150."""
@@ -449,18 +449,19 @@ def extra_ea_eval(torch, _lib, dev, n_cand=16, n_batches=4, B=8192):
     cands = [generate_random_choice(7, ops_config_lib["xlarge"]) for _ in range(n_cand + 2)]
     batches = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in synth_pool(n_batches, B, 13, ne, 11)]
     ev = SubnetEvaluator(m)
-    ev.score(cands[:2], batches)                     # warm-up (also fills the shared gather cache)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    res = ev.score(cands[2:], batches)
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3
-    out = {"ea_subnets_per_sec_%dx%d" % (n_batches, B): n_cand / sec,
-           "ea_eval_samples_per_sec": n_cand * n_batches * B / sec,
-           "ea_subnets_per_sec_150x8192_extrapolated": n_cand / sec * n_batches / 150.0,
-           "ea_mean_auc": float(np.mean([r["test_auroc"] for r in res]))}
+    out = {}
+    for tag, graph in (("eager", False), ("cuda_graph", True)):
+        ev.score(cands[:2], batches, use_cuda_graph=graph)     # warm-up (also fills the shared gather cache)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = ev.score(cands[2:], batches, use_cuda_graph=graph)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3
+        out["ea_subnets_per_sec_%dx%d_%s" % (n_batches, B, tag)] = n_cand / sec
+        out["ea_eval_samples_per_sec_%s" % tag] = n_cand * n_batches * B / sec
+    out["ea_mean_auc"] = float(np.mean([r["test_auroc"] for r in res]))
     del m, ev, batches
     torch.cuda.empty_cache()
     return out

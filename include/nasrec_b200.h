@@ -58,6 +58,10 @@ int nasrec_version(int* sm);
  * Process-wide; returns 0 or NASREC_EINVAL. */
 int nasrec_set_gemm_mode(int mode);
 int nasrec_get_gemm_mode(void);
+/* Optional caller-owned device scratch (the library never allocates).  With it, tensor-core GEMM
+ * launches that would occupy fewer than 64 SMs split their K range over several CTAs and finish
+ * with a fixed-order reduction (deterministic).  Pass (NULL, 0) to detach. */
+int nasrec_set_workspace(float* ws, int64_t nfloats);
 
 /* ------------------------------------------------------------------ embedding
  * a1  SuperNet._input_stem_layers_bi_output, supernet.py:404-430:

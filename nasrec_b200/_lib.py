@@ -61,13 +61,14 @@ _SIGS_I64 = {
     "nasrec_attn_bwd_ws_floats": [_i],
     "nasrec_sumsq_ws_floats": [_f, _i],
 }
-EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode"] + list(_SIGS) + list(_SIGS_I64)
+EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace"] + list(_SIGS) + list(_SIGS_I64)
 
 
 class _Lib:
     def __init__(self):
         self.cdll = None
         self.launches = 0          # kernels launched through this binding (bench.py's gpu_launches)
+        self.workspace = None
         self.fn = {}
 
     def load(self):
@@ -90,6 +91,8 @@ class _Lib:
             self.fn[name] = fn
         self.cdll.nasrec_set_gemm_mode.argtypes = [C.c_int]
         self.cdll.nasrec_set_gemm_mode.restype = C.c_int
+        self.cdll.nasrec_set_workspace.argtypes = [C.c_void_p, C.c_int64]
+        self.cdll.nasrec_set_workspace.restype = C.c_int
         self.cdll.nasrec_get_gemm_mode.argtypes = []
         self.cdll.nasrec_get_gemm_mode.restype = C.c_int
         mode = os.environ.get("NASREC_GEMM_MODE")
@@ -106,6 +109,14 @@ class _Lib:
         if self.cdll.nasrec_set_gemm_mode(int(mode)) != 0:
             raise ValueError("unsupported GEMM mode %r" % (mode,))
 
+    def ensure_workspace(self, nfloats: int = 16 * 1024 * 1024):
+        """Attach a split-K scratch buffer on the current CUDA device (kept alive here)."""
+        if self.workspace is None:
+            self.load()
+            self.workspace = torch.empty(nfloats, dtype=torch.float32, device="cuda")
+            if self.cdll.nasrec_set_workspace(self.workspace.data_ptr(), nfloats) != 0:
+                raise RuntimeError("nasrec_set_workspace failed")
+
     def gemm_mode(self) -> int:
         self.load()
         return int(self.cdll.nasrec_get_gemm_mode())
@@ -120,13 +131,31 @@ class _Lib:
 LIB = _Lib()
 
 
+_STREAM = [None]      # set by pin_stream() for the duration of a step; None -> ask torch on every call
+
+
 def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    s = _STREAM[0]
+    return torch.cuda.current_stream().cuda_stream if s is None else s
+
+
+class pin_stream:
+    """Context manager: resolve torch's current stream once for a whole launch sequence."""
+
+    def __enter__(self):
+        self.prev = _STREAM[0]
+        _STREAM[0] = torch.cuda.current_stream().cuda_stream
+        return self
+
+    def __exit__(self, *exc):
+        _STREAM[0] = self.prev
 
 
 def call(name: str, *args):
     """Invoke a C-ABI entry point on torch's current stream; raise on any error."""
     lib = LIB.load()
+    if lib.workspace is None:
+        lib.ensure_workspace()
     rc = lib.fn[name](*args, stream_ptr())
     if rc != 0:
         if rc > 0:

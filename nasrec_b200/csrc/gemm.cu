@@ -120,29 +120,49 @@ __global__ void __launch_bounds__(256) gemm64_kernel(const __grid_constant__ Bat
 }
 
 struct RedSeg {
-    const float* ws;      // [nsplit][M][N]
+    const float* ws;      // [nsplit][M][N] partial sums
     float* c;             // destination, row stride ldc
-    int N;
-    int pad_;
+    const float* bias;    // indexed by n, or null
+    long long ldc;
+    int M, N, nsplit, accumulate;
 };
 struct RedBatch {
-    int nseg, nsplit, M, accumulate;
-    long long ldc;
+    int nseg;
+    int pad_;
     RedSeg seg[NASREC_MAX_SEGS];
 };
 
+// Deterministic second stage of split-K: fixed-order sum of the partials (+bias, +in-place accumulate).
 __global__ void splitk_reduce_kernel(const __grid_constant__ RedBatch rb) {
     const RedSeg& s = rb.seg[blockIdx.y];
-    const long long total = (long long)rb.M * s.N;
+    const long long total = (long long)s.M * s.N;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int m = (int)(i / s.N), n = (int)(i % s.N);
         float v = 0.f;
-        for (int sp = 0; sp < rb.nsplit; ++sp) v += s.ws[(long long)sp * total + i];
-        float* dst = s.c + (long long)m * rb.ldc + n;
-        *dst = rb.accumulate ? (*dst + v) : v;
+        for (int sp = 0; sp < s.nsplit; ++sp) v += s.ws[(long long)sp * total + i];
+        if (s.bias) v += __ldg(s.bias + n);
+        float* dst = s.c + (long long)m * s.ldc + n;
+        *dst = s.accumulate ? (*dst + v) : v;
     }
 }
+
+int launch_reduce(const RedBatch& rb, cudaStream_t st) {
+    long long maxtot = 0;
+    for (int i = 0; i < rb.nseg; ++i) {
+        const long long t = (long long)rb.seg[i].M * rb.seg[i].N;
+        if (t > maxtot) maxtot = t;
+    }
+    if (rb.nseg == 0 || maxtot == 0) return 0;
+    long long gx = (maxtot + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    dim3 grid((unsigned)gx, rb.nseg);
+    splitk_reduce_kernel<<<grid, 256, 0, st>>>(rb);
+    return nasrec_launch_status();
+}
+
+float* g_ws = nullptr;          // library workspace for automatic split-K (nasrec_set_workspace)
+long long g_ws_floats = 0;
 
 int g_gemm_mode = 3;   // 0: fp32 FFMA; 1/3/4: tcgen05 kind::tf32 with 1/3/4 split products (default 3xTF32)
 
@@ -174,7 +194,47 @@ int launch(Batch& bt, cudaStream_t st) {
         totz += bt.prob[i].nsplit;
     }
     if (maxM <= 0 || maxN <= 0 || totz <= 0) return 0;
-    if (g_gemm_mode != 0) return nasrec_gemm::launch_tc(bt, maxM, maxN, totz, g_gemm_mode, st);
+    if (g_gemm_mode != 0) {
+        // Skinny launches (few output tiles, long K) leave most SMs idle: split K over several CTAs,
+        // partials into the library workspace, fixed-order reduction (deterministic).
+        RedBatch rb{};
+        const long long ctas = nasrec_gemm::tc_cta_count(bt, nasrec_gemm::tc_pick_bn(bt, maxN));
+        if (g_ws && ctas < 64) {
+            long long off = 0;
+            const int want = (int)(128 / (ctas > 0 ? ctas : 1));
+            for (int p = 0; p < bt.nprob; ++p) {
+                Prob& pr = bt.prob[p];
+                if (pr.nsplit != 1 || pr.c_sh_i != 0 || pr.c_hi_j != 1) continue;
+                if (pr.addend && pr.addend != pr.c) continue;
+                int ktiles = 0;
+                for (int t = 0; t < pr.nterm; ++t) ktiles += (bt.term[pr.term0 + t].K + 31) / 32;
+                int ns = want < ktiles / 4 ? want : ktiles / 4;
+                if (ns > 16) ns = 16;
+                const long long need = (long long)ns * pr.M * pr.N;
+                if (ns < 2 || off + need > g_ws_floats) continue;
+                RedSeg& rs = rb.seg[rb.nseg++];
+                rs.ws = g_ws + off;
+                rs.c = pr.c;
+                rs.bias = pr.bias;
+                rs.ldc = pr.c_hi_i;
+                rs.M = pr.M;
+                rs.N = pr.N;
+                rs.nsplit = ns;
+                rs.accumulate = pr.addend != nullptr;
+                pr.c = g_ws + off;
+                pr.c_hi_i = pr.N;
+                pr.bias = nullptr;
+                pr.addend = nullptr;
+                pr.nsplit = ns;
+                pr.split_stride = (long long)pr.M * pr.N;
+                off += need;
+                totz += ns - 1;
+            }
+        }
+        int rc = nasrec_gemm::launch_tc(bt, maxM, maxN, totz, g_gemm_mode, st);
+        if (rc || rb.nseg == 0) return rc;
+        return launch_reduce(rb, st);
+    }
     dim3 grid(cdiv(maxN, BN), cdiv(maxM, BM), totz);
     if (grid.y > 65535 || grid.z > 65535) return NASREC_ETOOBIG;
     gemm64_kernel<<<grid, 256, 0, st>>>(bt);
@@ -199,6 +259,13 @@ int nasrec_set_gemm_mode(int mode) {
 }
 
 int nasrec_get_gemm_mode(void) { return g_gemm_mode; }
+
+int nasrec_set_workspace(float* ws, int64_t nfloats) {
+    if (nfloats < 0 || (nfloats > 0 && !ws)) return NASREC_EINVAL;
+    g_ws = nfloats > 0 ? ws : nullptr;
+    g_ws_floats = nfloats;
+    return 0;
+}
 
 int nasrec_seg_linear_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off, int N,
                           const float* bias, float* C, int64_t ldc, int M, void* stream) {
@@ -370,13 +437,8 @@ int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_
     const int ns = sproj_nsplit(B);
     Batch bt{};
     RedBatch rb{};
-    rb.nsplit = ns;
-    rb.M = P;
-    rb.accumulate = accumulate;
-    rb.ldc = ldw;
     int np = 0;
     long long wsoff = 0;
-    long long maxtot = 0;
     for (int s = 0; s < nseg; ++s) {
         if (segs[s].width == 0) continue;
         const int w = (int)segs[s].width;
@@ -410,8 +472,12 @@ int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_
         t.b = b;
         rb.seg[np].ws = ws + wsoff;
         rb.seg[np].c = dW + segs[s].w_off;
+        rb.seg[np].bias = nullptr;
+        rb.seg[np].ldc = ldw;
+        rb.seg[np].M = P;
         rb.seg[np].N = w;
-        if ((long long)P * w > maxtot) maxtot = (long long)P * w;
+        rb.seg[np].nsplit = ns;
+        rb.seg[np].accumulate = accumulate;
         wsoff += (long long)ns * P * w;
         ++np;
     }
@@ -420,9 +486,7 @@ int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_
     if (np == 0) return 0;
     int rc = launch(bt, as_stream(stream));
     if (rc) return rc;
-    dim3 grid(cdiv(maxtot, 256), np);
-    splitk_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(rb);
-    return nasrec_launch_status();
+    return launch_reduce(rb, as_stream(stream));
 }
 
 }  // extern "C"

@@ -248,7 +248,7 @@ __device__ __forceinline__ void tile_sts(const TileRegs<ROWS>& R, uint8_t* s_hi,
 
 template <int BN>
 struct TcCfg {
-    static constexpr int STAGES = BN == 128 ? 3 : 4;
+    static constexpr int STAGES = BN == 128 ? 3 : 4;     // 192 KB / 192 KB / 160 KB / 144 KB of shared memory
     static constexpr int A_BYTES = TC_BM * TC_BK * 4;      // 16 KB
     static constexpr int B_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -498,12 +498,29 @@ inline int launch_tc_bn(const Batch& bt, int maxM, int maxN, int totz, int nprod
     return (int)cudaGetLastError();
 }
 
+// CTAs a launch would use with N-tile width bn
+inline long long tc_cta_count(const Batch& bt, int bn) {
+    long long c = 0;
+    for (int i = 0; i < bt.nprob; ++i)
+        c += (long long)((bt.prob[i].M + TC_BM - 1) / TC_BM) * ((bt.prob[i].N + bn - 1) / bn) * bt.prob[i].nsplit;
+    return c;
+}
+
+// widest N tile that still spreads the launch over most of the 148 SMs (one CTA per SM)
+inline int tc_pick_bn(const Batch& bt, int maxN) {
+    if (maxN <= 16) return 16;
+    if (maxN > 64 && tc_cta_count(bt, 128) >= 120) return 128;
+    if (maxN > 32 && tc_cta_count(bt, 64) >= 120) return 64;
+    return maxN <= 32 ? 32 : (tc_cta_count(bt, 32) > 296 ? 64 : 32);
+}
+
 inline int launch_tc(const Batch& bt, int maxM, int maxN, int totz, int nprod, cudaStream_t st) {
-    // narrow tiles when N is small or when 128-wide tiles would leave most SMs idle
-    const long long tiles128 = (long long)((maxN + 127) / 128) * ((maxM + TC_BM - 1) / TC_BM) * totz;
-    if (maxN <= 16) return launch_tc_bn<16>(bt, maxM, maxN, totz, nprod, st);
-    if (maxN <= 64 || tiles128 < 148) return launch_tc_bn<64>(bt, maxM, maxN, totz, nprod, st);
-    return launch_tc_bn<128>(bt, maxM, maxN, totz, nprod, st);
+    switch (tc_pick_bn(bt, maxN)) {
+        case 16: return launch_tc_bn<16>(bt, maxM, maxN, totz, nprod, st);
+        case 32: return launch_tc_bn<32>(bt, maxM, maxN, totz, nprod, st);
+        case 64: return launch_tc_bn<64>(bt, maxM, maxN, totz, nprod, st);
+        default: return launch_tc_bn<128>(bt, maxM, maxN, totz, nprod, st);
+    }
 }
 
 }  // namespace nasrec_gemm

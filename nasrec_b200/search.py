@@ -93,16 +93,56 @@ class SubnetEvaluator:
         return out.t
 
     @torch.no_grad()
-    def score(self, choices: Sequence[Dict[str, Any]], batches: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]
-              ) -> List[Dict[str, float]]:
+    def _gathered(self, cat_x: torch.Tensor) -> torch.Tensor:
+        """Embedding rows of one evaluation batch, gathered once and shared by every candidate."""
+        hit = self._emb_cache.get(cat_x.data_ptr())
+        if hit is None:
+            run = Run(Tape(False), emb_cache=self._emb_cache)
+            m = self.model
+            eng.embedding(run.tape, m._tables, [run.pv(e.weight) for e in m._embedding], cat_x, cache=self._emb_cache)
+            hit = self._emb_cache[cat_x.data_ptr()]
+        return hit
+
+    @torch.no_grad()
+    def score(self, choices: Sequence[Dict[str, Any]], batches: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
+              use_cuda_graph: bool = True) -> List[Dict[str, float]]:
         """Each candidate: logits on every batch -> log-loss, AUC, accuracy.  The embedding
-        gather of a batch is done once and shared by all candidates (tables are frozen)."""
+        gather of a batch is done once and shared by all candidates (tables are frozen).  With
+        use_cuda_graph the candidate's forward is captured on the first batch and replayed on
+        the others (all batches must then share one shape), removing the per-launch host cost."""
         ys = torch.cat([b[2].reshape(-1) for b in batches])
+        same_shape = all(b[0].shape == batches[0][0].shape for b in batches)
         res = []
+        if not (use_cuda_graph and same_shape and len(batches) > 2):
+            for ch in choices:
+                outs = [self.logits(ch, b[0], b[1]).reshape(-1) for b in batches]
+                acc, auc, loss = binary_metrics_device(torch.cat(outs), ys)
+                res.append({"test_acc": acc, "test_auroc": auc, "test_loss": loss})
+            return res
+        m = self.model
+        if m._needs_materialize():
+            m.materialize(batches[0][0].shape[1])
+        rows = [self._gathered(b[1]) for b in batches]          # shared across candidates
+        B = batches[0][0].shape[0]
+        s_int = batches[0][0].clone()
+        s_cat = batches[0][1].clone()
+        s_rows = rows[0].clone()
+        out_all = torch.empty(len(batches), B, dtype=torch.float32, device=s_int.device)
+        self.logits(choices[0], batches[0][0], batches[0][1])    # lazy kernel attributes outside capture
         for ch in choices:
-            outs = [self.logits(ch, b[0], b[1]).reshape(-1) for b in batches]
-            acc, auc, loss = binary_metrics_device(torch.cat(outs), ys)
+            cache = {s_cat.data_ptr(): s_rows}
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run = Run(Tape(False), emb_cache=cache)
+                out = m._run_network(run, Var(s_int), s_cat, ch["macro"], ch["micro"]).t
+            for bi, b in enumerate(batches):
+                s_int.copy_(b[0], non_blocking=True)
+                s_rows.copy_(rows[bi], non_blocking=True)
+                g.replay()
+                out_all[bi].copy_(out.reshape(-1), non_blocking=True)
+            acc, auc, loss = binary_metrics_device(out_all.reshape(-1), ys)
             res.append({"test_acc": acc, "test_auroc": auc, "test_loss": loss})
+            del g
         return res
 
     def release(self):

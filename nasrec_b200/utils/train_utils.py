@@ -184,6 +184,7 @@ class FusedTrainer:
         self._emb_tables()
 
     def step(self, int_x, cat_x, y, lr: Optional[float] = None):
-        logits, loss, run, sparse = self.forward_backward(int_x, cat_x, y)
-        self.apply(run, sparse, lr)
+        with _lib.pin_stream():
+            logits, loss, run, sparse = self.forward_backward(int_x, cat_x, y)
+            self.apply(run, sparse, lr)
         return logits, loss

@@ -244,3 +244,27 @@ def test_cuda_graph_step_matches_eager_step():
     assert finals[0][0] == finals[1][0]
     for k in finals[0][1]:
         assert torch.equal(finals[0][1][k], finals[1][1][k]), k
+
+
+def test_subnet_evaluator_matches_oracle_and_graph_replay():
+    """One-shot scoring: shared gather + per-candidate CUDA-graph replay == eager == oracle."""
+    from nasrec_b200.search import SubnetEvaluator
+    meta, _ = load_golden("supernet_xlarge_criteo")
+    smeta, _ = load_golden("samplers")
+    cfg, ne, nd = meta["cfg"], meta["num_embeddings"], meta["nd"]
+    m, sd = _build(cfg, ne, nd, meta["shapes"], 31)
+    m.requires_grad_(False)
+    cands = smeta["ea_candidates"]["xlarge"][:3]
+    host = [orc.synth_batch(96, nd, ne, seed=700 + i) for i in range(4)]
+    batches = [tuple(t.cuda() for t in b) for b in host]
+    ev = SubnetEvaluator(m)
+    eager = ev.score(cands, batches, use_cuda_graph=False)
+    graph = ev.score(cands, batches, use_cuda_graph=True)
+    for ch, e, g in zip(cands, eager, graph):
+        assert e == g
+        logits = torch.cat([orc.supernet_forward(sd, cfg, ch, b[0], b[1]).reshape(-1) for b in host])
+        ys = torch.cat([b[2].reshape(-1) for b in host])
+        acc, auc, loss = orc.binary_metrics(logits.detach().numpy(), ys.numpy())
+        assert abs(e["test_loss"] - loss) < 1e-5
+        assert abs(e["test_auroc"] - auc) < 1e-4
+        assert abs(e["test_acc"] - acc) < 1e-6
