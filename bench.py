@@ -171,6 +171,7 @@ class GemmTimer:
     def __init__(self, torch, lib):
         self.torch, self.lib, self.events, self.flops, self.orig = torch, lib, [], 0.0, lib.call
         self.per = {}
+        self.other_events, self.other = [], {}
 
     @staticmethod
     def _ksum(seg_arr, n):
@@ -191,15 +192,15 @@ class GemmTimer:
 
     def __enter__(self):
         def timed(name, *a):
-            if name not in self.NAMES:
-                return self.orig(name, *a)
             e0 = self.torch.cuda.Event(enable_timing=True)
             e1 = self.torch.cuda.Event(enable_timing=True)
             e0.record()
             self.orig(name, *a)
             e1.record()
-            f = self._flops(name, a)
-            self.events.append((name, e0, e1, f))
+            if name in self.NAMES:
+                self.events.append((name, e0, e1, self._flops(name, a)))
+            else:
+                self.other_events.append((name, e0, e1))
         self.lib.call = timed
         return self
 
@@ -212,6 +213,10 @@ class GemmTimer:
             p[0] += 1
             p[1] += ms
             p[2] += f
+        for name, e0, e1 in self.other_events:
+            p = self.other.setdefault(name, [0, 0.0])
+            p[0] += 1
+            p[1] += e0.elapsed_time(e1)
 
     def summary(self):
         n = sum(p[0] for p in self.per.values())
@@ -352,7 +357,9 @@ def run_ours(args):
                             "avg_launch_us": ms * 1e3 / max(n, 1), "gflop_per_launch": fl / max(n, 1) / 1e9,
                             "share_of_step": ms / (min(K, 10) * ms_per_step) if ms_per_step > 0 else None,
                             "by_entry_point": {k: {"launches": v[0], "ms": v[1], "gflop": v[2] / 1e9}
-                                               for k, v in gt.per.items()}}
+                                               for k, v in gt.per.items()},
+                            "other_entry_points_ms": {k: round(v[1], 3) for k, v in sorted(
+                                gt.other.items(), key=lambda kv: -kv[1][1])}}
         line["extra"] = {}
         if not args.no_extras:
             line["extra"].update(extra_fixed_best(torch, _lib, dev, flush))

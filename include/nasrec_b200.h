@@ -125,6 +125,29 @@ int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_
 int nasrec_sproj_bias_grad(const float* dZ, int64_t dz_bstride, int P, int B, float* db, int accumulate,
                            void* stream);
 
+/* ------------------------------------------------------- op-level sequences
+ * One call per operator direction (same kernels as the fine-grained entry points above and
+ * below, sequenced on `stream`); they exist to cut host-side call overhead.  z/dz/mean/rstd are
+ * caller-provided scratch ([M,N] / [B,P,16]); a null gamma means "no LayerNorm" (plain activation);
+ * null dW/dbias/dgamma/dbeta/dsegs[i].ptr mean "gradient not wanted"; dseg_accumulate[i] = 1 adds
+ * into the target instead of overwriting it.  Targets must be distinct and segments must meet
+ * distinct weight columns (callers fall back to the fine-grained calls otherwise). */
+int nasrec_linear_ln_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off, int N,
+                         const float* bias, const float* gamma, const float* beta, float eps, int relu, int d_out,
+                         float* z, float* y, int64_t ldy, float* mean, float* rstd, int accumulate, int M,
+                         void* stream);
+int nasrec_linear_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* z, int M, int N, const float* gamma,
+                         const float* beta, const float* mean, const float* rstd, int relu, const nasrec_seg_t* segs,
+                         const nasrec_seg_t* dsegs, const int* dseg_accumulate, int nseg, const float* W, int64_t ldw,
+                         int n_off, float* dW, float* dbias, float* dgamma, float* dbeta, float* dz, void* stream);
+int nasrec_sproj_ln_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int P, const float* bias,
+                        const float* gamma, const float* beta, float eps, int relu, int p_out, float* z, float* y,
+                        int64_t y_bstride, float* mean, float* rstd, int accumulate, int B, void* stream);
+int nasrec_sproj_ln_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* z, int B, int P, const float* gamma,
+                        const float* beta, const float* mean, const float* rstd, int relu, const nasrec_seg_t* segs,
+                        const nasrec_seg_t* dsegs, const int* dseg_accumulate, int nseg, const float* W, int64_t ldw,
+                        float* dW, float* dbias, float* dgamma, float* dbeta, float* dz, float* ws, void* stream);
+
 /* ------------------------------------------------------- LayerNorm epilogues
  * nn.LayerNorm(N) + activation + prefix mask (modules.py:171-181, 385-400, 489-499):
  *   y[m,j] (+)= act(LN(x[m,0:N])[j]) for j < d_out  (columns >= d_out are the masked ones

@@ -37,6 +37,12 @@ _SIGS = {
     "nasrec_sproj_dgrad": ([_f, _l, _i, _f, _l, _f, _i, _i, _i, _f], 1),
     "nasrec_sproj_wgrad": ([_f, _l, _i, _f, _i, _f, _l, _i, _i, _f, _f], 2),
     "nasrec_sproj_bias_grad": ([_f, _l, _i, _i, _f, _i, _f], 1),
+    "nasrec_linear_ln_fwd": ([_f, _i, _f, _l, _i, _i, _f, _f, _f, _fl, _i, _i, _f, _f, _l, _f, _f, _i, _i, _f], 2),
+    "nasrec_linear_ln_bwd": ([_f, _l, _i, _f, _i, _i, _f, _f, _f, _f, _i, _f, _f, _f, _i, _f, _l, _i, _f, _f, _f, _f,
+                              _f, _f], 5),
+    "nasrec_sproj_ln_fwd": ([_f, _i, _f, _l, _i, _f, _f, _f, _fl, _i, _i, _f, _f, _l, _f, _f, _i, _i, _f], 2),
+    "nasrec_sproj_ln_bwd": ([_f, _l, _i, _f, _i, _i, _f, _f, _f, _f, _i, _f, _f, _f, _i, _f, _l, _f, _f, _f, _f, _f,
+                             _f, _f], 6),
     "nasrec_ln_fwd": ([_f, _l, _i, _i, _f, _f, _fl, _i, _i, _f, _l, _f, _f, _i, _f], 1),
     "nasrec_ln_bwd": ([_f, _l, _i, _f, _l, _i, _i, _f, _f, _f, _f, _i, _f, _l, _f, _f, _i, _f], 2),
     "nasrec_ln3_fwd": ([_f, _l, _i, _i, _f, _f, _fl, _i, _i, _f, _l, _f, _f, _i, _f], 1),
@@ -177,6 +183,10 @@ def segs(items: Sequence[Tuple[int, int, int, int]]):
     for it in items:
         flat.extend(it)
     return (C.c_int64 * (4 * n))(*flat), n
+
+
+def i32_array(vals: Sequence[int]):
+    return (C.c_int * len(vals))(*vals)
 
 
 def i64_array(vals: Sequence[int]):

@@ -1,0 +1,108 @@
+// Op-level entry points: one C call per operator direction instead of one per kernel.
+// They only sequence the kernel launchers of gemm.cu / ln.cu on the caller's stream; the point is
+// host-side cost: at B=512 a supernet step is ~150 launches and the Python->C boundary dominated it.
+#include "common.cuh"
+
+namespace {
+struct SegSplit {
+    nasrec_seg_t fresh[NASREC_MAX_SEGS];
+    nasrec_seg_t acc[NASREC_MAX_SEGS];
+    int nf = 0, na = 0;
+};
+// grad targets: ptr == null -> no gradient wanted; flag 0 -> overwrite, 1 -> accumulate
+void split_targets(const nasrec_seg_t* dsegs, const int* acc_flags, int nseg, SegSplit& s) {
+    for (int i = 0; i < nseg; ++i) {
+        if (!dsegs[i].ptr || dsegs[i].width == 0) continue;
+        if (acc_flags && acc_flags[i]) s.acc[s.na++] = dsegs[i];
+        else s.fresh[s.nf++] = dsegs[i];
+    }
+}
+}  // namespace
+
+extern "C" {
+
+// y[:, :d_out] (+)= act(LN(concat(segs) @ W[n_off:n_off+N].T + bias))   (LN skipped when gamma == null)
+int nasrec_linear_ln_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off, int N,
+                         const float* bias, const float* gamma, const float* beta, float eps, int relu, int d_out,
+                         float* z, float* y, int64_t ldy, float* mean, float* rstd, int accumulate, int M,
+                         void* stream) {
+    int rc = nasrec_seg_linear_fwd(segs, nseg, W, ldw, n_off, N, bias, z, N, M, stream);
+    if (rc) return rc;
+    if (gamma) return nasrec_ln_fwd(z, N, M, N, gamma, beta, eps, relu, d_out, y, ldy, mean, rstd, accumulate, stream);
+    return nasrec_act_fwd(z, N, M, N, relu, y, ldy, accumulate, stream);
+}
+
+// Backward of the above.  dz: [M,N] scratch.  dW/dbias/dgamma/dbeta/dsegs[i].ptr may be null (not wanted).
+// dsegs must not contain the same target twice, segs must not meet the same W columns twice.
+int nasrec_linear_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* z, int M, int N, const float* gamma,
+                         const float* beta, const float* mean, const float* rstd, int relu, const nasrec_seg_t* segs,
+                         const nasrec_seg_t* dsegs, const int* dseg_accumulate, int nseg, const float* W, int64_t ldw,
+                         int n_off, float* dW, float* dbias, float* dgamma, float* dbeta, float* dz, void* stream) {
+    int rc;
+    if (gamma) rc = nasrec_ln_bwd(dy, lddy, d_out, z, N, M, N, gamma, beta, mean, rstd, relu, dz, N, dgamma, dbeta, 0, stream);
+    else rc = nasrec_act_bwd(dy, lddy, z, N, M, N, relu, dz, N, stream);
+    if (rc) return rc;
+    if (dW) {
+        rc = nasrec_seg_linear_wgrad(dz, N, N, segs, nseg, dW, ldw, n_off, M, 0, stream);
+        if (rc) return rc;
+    }
+    if (dbias) {
+        rc = nasrec_colsum(dz, N, M, N, dbias + n_off, 0, stream);
+        if (rc) return rc;
+    }
+    SegSplit s;
+    split_targets(dsegs, dseg_accumulate, nseg, s);
+    if (s.nf) {
+        rc = nasrec_seg_linear_dgrad(dz, N, N, W, ldw, n_off, s.fresh, s.nf, M, 0, stream);
+        if (rc) return rc;
+    }
+    if (s.na) {
+        rc = nasrec_seg_linear_dgrad(dz, N, N, W, ldw, n_off, s.acc, s.na, M, 1, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// y[b, p<p_out, :] (+)= act(LN_P(W @ concat_rows(segs)[b] + bias))
+int nasrec_sproj_ln_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int P, const float* bias,
+                        const float* gamma, const float* beta, float eps, int relu, int p_out, float* z, float* y,
+                        int64_t y_bstride, float* mean, float* rstd, int accumulate, int B, void* stream) {
+    int rc = nasrec_sproj_fwd(segs, nseg, W, ldw, P, bias, z, (int64_t)P * NASREC_EMB_DIM, B, stream);
+    if (rc) return rc;
+    if (gamma)
+        return nasrec_ln3_fwd(z, (int64_t)P * NASREC_EMB_DIM, B, P, gamma, beta, eps, relu, p_out, y, y_bstride, mean,
+                              rstd, accumulate, stream);
+    return nasrec_act_fwd(z, (int64_t)P * NASREC_EMB_DIM, B, p_out * NASREC_EMB_DIM, relu, y, y_bstride, accumulate, stream);
+}
+
+int nasrec_sproj_ln_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* z, int B, int P, const float* gamma,
+                        const float* beta, const float* mean, const float* rstd, int relu, const nasrec_seg_t* segs,
+                        const nasrec_seg_t* dsegs, const int* dseg_accumulate, int nseg, const float* W, int64_t ldw,
+                        float* dW, float* dbias, float* dgamma, float* dbeta, float* dz, float* ws, void* stream) {
+    const int64_t zbs = (int64_t)P * NASREC_EMB_DIM;
+    int rc;
+    if (gamma) rc = nasrec_ln3_bwd(dy, dy_bstride, p_out, z, zbs, B, P, gamma, beta, mean, rstd, relu, dz, zbs, dgamma, dbeta, 0, stream);
+    else rc = nasrec_act_bwd(dy, dy_bstride, z, zbs, B, P * NASREC_EMB_DIM, relu, dz, zbs, stream);
+    if (rc) return rc;
+    if (dW) {
+        rc = nasrec_sproj_wgrad(dz, zbs, P, segs, nseg, dW, ldw, B, 0, ws, stream);
+        if (rc) return rc;
+    }
+    if (dbias) {
+        rc = nasrec_sproj_bias_grad(dz, zbs, P, B, dbias, 0, stream);
+        if (rc) return rc;
+    }
+    SegSplit s;
+    split_targets(dsegs, dseg_accumulate, nseg, s);
+    if (s.nf) {
+        rc = nasrec_sproj_dgrad(dz, zbs, P, W, ldw, s.fresh, s.nf, B, 0, stream);
+        if (rc) return rc;
+    }
+    if (s.na) {
+        rc = nasrec_sproj_dgrad(dz, zbs, P, W, ldw, s.acc, s.na, B, 1, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // extern "C"

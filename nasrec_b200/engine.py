@@ -118,6 +118,33 @@ def _unique_woff_groups(seg_list: Sequence[Seg]) -> List[List[Seg]]:
     return groups
 
 
+def _distinct_woffs(seg_list: Sequence[Seg]) -> bool:
+    offs = [s.w_off for s in seg_list if s.width > 0]
+    return len(offs) == len(set(offs))
+
+
+def _grad_targets(seg_list: Sequence[Seg]):
+    """(nasrec_seg_t[] of gradient targets, accumulate flags) for the fused backward entry points,
+    or None when two segments share a target (then the grouped general path is used).  Targets are
+    allocated on first touch; a segment whose source needs no gradient gets a null pointer."""
+    keys = [(id(s.v), s.off) for s in seg_list if s.v.req and s.width > 0]
+    if len(keys) != len(set(keys)):
+        return None
+    fresh = set()
+    items, flags = [], []
+    for s in seg_list:
+        if s.v.req and s.width > 0:
+            if s.v.g is None:
+                s.v.g = torch.empty_like(s.v.t)
+                fresh.add(id(s.v))
+            flags.append(0 if id(s.v) in fresh else 1)
+            items.append((_p(s.v.g, s.off), s.ld, s.width, s.w_off))
+        else:
+            flags.append(0)
+            items.append((0, s.ld, s.width, s.w_off))
+    return _lib.segs(items)[0], _lib.i32_array(flags)
+
+
 def _dgrad_groups(seg_list: Sequence[Seg]):
     """Segments needing a gradient, grouped into launches: (segments, accumulate).
     Within a launch all targets are distinct tensors or disjoint slices."""
@@ -164,17 +191,17 @@ def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[
     N = n_full if ln is not None else d_out
     z = _new(M, N, like=ref)
     sp, ns = _pack(seg_list)
-    call("nasrec_seg_linear_fwd", sp, ns, _p(W.t), ldw, n_off, N, _p(b.t) if b is not None else None, _p(z), N, M)
     if out is None:
         out = Var(_new(M, d_out, like=ref))
         ldy = d_out
     if ln is not None:
         mean, rstd = _new(M, like=ref), _new(M, like=ref)
-        call("nasrec_ln_fwd", _p(z), N, M, N, _p(ln[0].t), _p(ln[1].t), LN_EPS, int(relu), d_out,
-             _p(out.t, out_off), ldy, _p(mean), _p(rstd), accumulate)
+        gam, bet, pm, pr = _p(ln[0].t), _p(ln[1].t), _p(mean), _p(rstd)
     else:
         mean = rstd = None
-        call("nasrec_act_fwd", _p(z), N, M, N, int(relu), _p(out.t, out_off), ldy, accumulate)
+        gam = bet = pm = pr = None
+    call("nasrec_linear_ln_fwd", sp, ns, _p(W.t), ldw, n_off, N, _p(b.t) if b is not None else None, gam, bet,
+         LN_EPS, int(relu), d_out, _p(z), _p(out.t, out_off), ldy, pm, pr, accumulate, M)
     req = _any_req(seg_list) or W.req or (b is not None and b.req) or (ln is not None and (ln[0].req or ln[1].req))
     out.req = out.req or req
     if not (tape.enabled and req):
@@ -184,21 +211,28 @@ def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[
         if out.g is None:
             return
         dz = _new(M, N, like=ref)
+        want_ln = ln is not None and (ln[0].req or ln[1].req)
+        gw = W.grad(w_full_support and N == W.t.shape[0]) if W.req else None
+        gb = b.grad(N == b.t.shape[0]) if (b is not None and b.req) else None
+        targets = _grad_targets(seg_list)
+        if targets is not None and _distinct_woffs(seg_list):
+            dsp, flags = targets
+            call("nasrec_linear_ln_bwd", _p(out.g, out_off), ldy, d_out, _p(z), M, N, gam, bet, pm, pr, int(relu), sp,
+                 dsp, flags, ns, _p(W.t), ldw, n_off, _p(gw) if gw is not None else None,
+                 _p(gb) if gb is not None else None, _p(ln[0].grad(True)) if want_ln else None,
+                 _p(ln[1].grad(True)) if want_ln else None, _p(dz))
+            return
+        # general path: the same source feeds two segments (Sum with left == right, modules.py:470-487)
         if ln is not None:
-            want = ln[0].req or ln[1].req
-            call("nasrec_ln_bwd", _p(out.g, out_off), ldy, d_out, _p(z), N, M, N, _p(ln[0].t), _p(ln[1].t),
-                 _p(mean), _p(rstd), int(relu), _p(dz), N,
-                 _p(ln[0].grad(True)) if want else None, _p(ln[1].grad(True)) if want else None, 0)
+            call("nasrec_ln_bwd", _p(out.g, out_off), ldy, d_out, _p(z), N, M, N, gam, bet, pm, pr, int(relu), _p(dz), N,
+                 _p(ln[0].grad(True)) if want_ln else None, _p(ln[1].grad(True)) if want_ln else None, 0)
         else:
             call("nasrec_act_bwd", _p(out.g, out_off), ldy, _p(z), N, M, N, int(relu), _p(dz), N)
-        if W.req:
-            full = w_full_support and N == W.t.shape[0]
-            gw = W.grad(full)
+        if gw is not None:
             for gi, grp in enumerate(_unique_woff_groups(seg_list)):
                 spk, nsk = _pack(grp)
                 call("nasrec_seg_linear_wgrad", _p(dz), N, N, spk, nsk, _p(gw), ldw, n_off, M, 1 if gi else 0)
-        if b is not None and b.req:
-            gb = b.grad(N == b.t.shape[0])
+        if gb is not None:
             call("nasrec_colsum", _p(dz), N, M, N, _p(gb, n_off), 0)
         for grp, acc in _dgrad_groups(seg_list):
             spk, nsk = _pack(grp, grad=True)
@@ -221,17 +255,17 @@ def sproj_ln(tape: Tape, seg_list: Sequence[Seg], B: int, W: PVar, b: Optional[P
     P = P_full if ln is not None else p_out
     z = _new(B, P, E, like=ref)
     sp, ns = _pack(seg_list)
-    call("nasrec_sproj_fwd", sp, ns, _p(W.t), ldw, P, _p(b.t) if b is not None else None, _p(z), P * E, B)
     if out is None:
         out = Var(_new(B, p_out, E, like=ref))
         out_bstride = p_out * E
     if ln is not None:
         mean, rstd = _new(B, E, like=ref), _new(B, E, like=ref)
-        call("nasrec_ln3_fwd", _p(z), P * E, B, P, _p(ln[0].t), _p(ln[1].t), LN_EPS, int(relu), p_out,
-             _p(out.t, out_off), out_bstride, _p(mean), _p(rstd), accumulate)
+        gam, bet, pm, pr = _p(ln[0].t), _p(ln[1].t), _p(mean), _p(rstd)
     else:
         mean = rstd = None
-        call("nasrec_act_fwd", _p(z), P * E, B, p_out * E, int(relu), _p(out.t, out_off), out_bstride, accumulate)
+        gam = bet = pm = pr = None
+    call("nasrec_sproj_ln_fwd", sp, ns, _p(W.t), ldw, P, _p(b.t) if b is not None else None, gam, bet, LN_EPS,
+         int(relu), p_out, _p(z), _p(out.t, out_off), out_bstride, pm, pr, accumulate, B)
     req = _any_req(seg_list) or W.req or (b is not None and b.req) or (ln is not None and (ln[0].req or ln[1].req))
     out.req = out.req or req
     if not (tape.enabled and req):
@@ -241,22 +275,34 @@ def sproj_ln(tape: Tape, seg_list: Sequence[Seg], B: int, W: PVar, b: Optional[P
         if out.g is None:
             return
         dz = _new(B, P, E, like=ref)
+        want_ln = ln is not None and (ln[0].req or ln[1].req)
+        gw = W.grad(w_full_support and P == P_full) if W.req else None
+        gb = b.grad(P == P_full) if (b is not None and b.req) else None
+        targets = _grad_targets(seg_list)
+        if targets is not None and _distinct_woffs(seg_list):
+            dsp, flags = targets
+            ws = None
+            if gw is not None:
+                ws = _new(query("nasrec_sproj_wgrad_ws_floats", P, sum(s.width for s in seg_list), B), like=ref)
+            call("nasrec_sproj_ln_bwd", _p(out.g, out_off), out_bstride, p_out, _p(z), B, P, gam, bet, pm, pr, int(relu),
+                 sp, dsp, flags, ns, _p(W.t), ldw, _p(gw) if gw is not None else None,
+                 _p(gb) if gb is not None else None, _p(ln[0].grad(True)) if want_ln else None,
+                 _p(ln[1].grad(True)) if want_ln else None, _p(dz), _p(ws) if ws is not None else None)
+            return
         if ln is not None:
-            want = ln[0].req or ln[1].req
-            call("nasrec_ln3_bwd", _p(out.g, out_off), out_bstride, p_out, _p(z), P * E, B, P, _p(ln[0].t),
-                 _p(ln[1].t), _p(mean), _p(rstd), int(relu), _p(dz), P * E,
-                 _p(ln[0].grad(True)) if want else None, _p(ln[1].grad(True)) if want else None, 0)
+            call("nasrec_ln3_bwd", _p(out.g, out_off), out_bstride, p_out, _p(z), P * E, B, P, gam, bet, pm, pr,
+                 int(relu), _p(dz), P * E, _p(ln[0].grad(True)) if want_ln else None,
+                 _p(ln[1].grad(True)) if want_ln else None, 0)
         else:
             call("nasrec_act_bwd", _p(out.g, out_off), out_bstride, _p(z), P * E, B, P * E, int(relu), _p(dz), P * E)
-        if W.req:
-            gw = W.grad(w_full_support and P == P_full)
+        if gw is not None:
             for gi, grp in enumerate(_unique_woff_groups(seg_list)):
                 tw = sum(s.width for s in grp)
                 ws = _new(query("nasrec_sproj_wgrad_ws_floats", P, tw, B), like=ref)
                 spk, nsk = _pack(grp)
                 call("nasrec_sproj_wgrad", _p(dz), P * E, P, spk, nsk, _p(gw), ldw, B, 1 if gi else 0, _p(ws))
-        if b is not None and b.req:
-            call("nasrec_sproj_bias_grad", _p(dz), P * E, P, B, _p(b.grad(P == P_full)), 0)
+        if gb is not None:
+            call("nasrec_sproj_bias_grad", _p(dz), P * E, P, B, _p(gb), 0)
         for grp, acc in _dgrad_groups(seg_list):
             spk, nsk = _pack(grp, grad=True)
             call("nasrec_sproj_dgrad", _p(dz), P * E, P, _p(W.t), ldw, spk, nsk, B, acc)

@@ -105,11 +105,13 @@ class SubnetEvaluator:
 
     @torch.no_grad()
     def score(self, choices: Sequence[Dict[str, Any]], batches: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
-              use_cuda_graph: bool = True) -> List[Dict[str, float]]:
+              use_cuda_graph: bool = False) -> List[Dict[str, float]]:
         """Each candidate: logits on every batch -> log-loss, AUC, accuracy.  The embedding
         gather of a batch is done once and shared by all candidates (tables are frozen).  With
         use_cuda_graph the candidate's forward is captured on the first batch and replayed on
-        the others (all batches must then share one shape), removing the per-launch host cost."""
+        the others (all batches must then share one shape), removing the per-launch host cost;
+        capture + instantiation cost ~70 ms per candidate, so it only pays for many small batches
+        (at 8192-sample batches scoring is device-bound and eager is faster)."""
         ys = torch.cat([b[2].reshape(-1) for b in batches])
         same_shape = all(b[0].shape == batches[0][0].shape for b in batches)
         res = []
