@@ -28,6 +28,7 @@ def call(name: str, *args):
 
 E = 16                 # embedding dim (supernet.py:224)
 LN_EPS = 1e-5
+FUSED_CALLS = True     # one C call per operator direction (nasrec_linear_ln_* / nasrec_sproj_ln_*)
 
 
 class Var:
@@ -200,8 +201,16 @@ def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[
     else:
         mean = rstd = None
         gam = bet = pm = pr = None
-    call("nasrec_linear_ln_fwd", sp, ns, _p(W.t), ldw, n_off, N, _p(b.t) if b is not None else None, gam, bet,
-         LN_EPS, int(relu), d_out, _p(z), _p(out.t, out_off), ldy, pm, pr, accumulate, M)
+    if FUSED_CALLS:
+        call("nasrec_linear_ln_fwd", sp, ns, _p(W.t), ldw, n_off, N, _p(b.t) if b is not None else None, gam, bet,
+             LN_EPS, int(relu), d_out, _p(z), _p(out.t, out_off), ldy, pm, pr, accumulate, M)
+    else:
+        call("nasrec_seg_linear_fwd", sp, ns, _p(W.t), ldw, n_off, N, _p(b.t) if b is not None else None, _p(z), N, M)
+        if ln is not None:
+            call("nasrec_ln_fwd", _p(z), N, M, N, gam, bet, LN_EPS, int(relu), d_out, _p(out.t, out_off), ldy, pm, pr,
+                 accumulate)
+        else:
+            call("nasrec_act_fwd", _p(z), N, M, N, int(relu), _p(out.t, out_off), ldy, accumulate)
     req = _any_req(seg_list) or W.req or (b is not None and b.req) or (ln is not None and (ln[0].req or ln[1].req))
     out.req = out.req or req
     if not (tape.enabled and req):
@@ -210,11 +219,12 @@ def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[
     def bwd():
         if out.g is None:
             return
+        pm, pr = (_p(mean), _p(rstd)) if mean is not None else (None, None)   # (keeps the saved stats alive)
         dz = _new(M, N, like=ref)
         want_ln = ln is not None and (ln[0].req or ln[1].req)
         gw = W.grad(w_full_support and N == W.t.shape[0]) if W.req else None
         gb = b.grad(N == b.t.shape[0]) if (b is not None and b.req) else None
-        targets = _grad_targets(seg_list)
+        targets = _grad_targets(seg_list) if FUSED_CALLS else None
         if targets is not None and _distinct_woffs(seg_list):
             dsp, flags = targets
             call("nasrec_linear_ln_bwd", _p(out.g, out_off), ldy, d_out, _p(z), M, N, gam, bet, pm, pr, int(relu), sp,
@@ -264,8 +274,16 @@ def sproj_ln(tape: Tape, seg_list: Sequence[Seg], B: int, W: PVar, b: Optional[P
     else:
         mean = rstd = None
         gam = bet = pm = pr = None
-    call("nasrec_sproj_ln_fwd", sp, ns, _p(W.t), ldw, P, _p(b.t) if b is not None else None, gam, bet, LN_EPS,
-         int(relu), p_out, _p(z), _p(out.t, out_off), out_bstride, pm, pr, accumulate, B)
+    if FUSED_CALLS:
+        call("nasrec_sproj_ln_fwd", sp, ns, _p(W.t), ldw, P, _p(b.t) if b is not None else None, gam, bet, LN_EPS,
+             int(relu), p_out, _p(z), _p(out.t, out_off), out_bstride, pm, pr, accumulate, B)
+    else:
+        call("nasrec_sproj_fwd", sp, ns, _p(W.t), ldw, P, _p(b.t) if b is not None else None, _p(z), P * E, B)
+        if ln is not None:
+            call("nasrec_ln3_fwd", _p(z), P * E, B, P, gam, bet, LN_EPS, int(relu), p_out, _p(out.t, out_off),
+                 out_bstride, pm, pr, accumulate)
+        else:
+            call("nasrec_act_fwd", _p(z), P * E, B, p_out * E, int(relu), _p(out.t, out_off), out_bstride, accumulate)
     req = _any_req(seg_list) or W.req or (b is not None and b.req) or (ln is not None and (ln[0].req or ln[1].req))
     out.req = out.req or req
     if not (tape.enabled and req):
@@ -274,11 +292,12 @@ def sproj_ln(tape: Tape, seg_list: Sequence[Seg], B: int, W: PVar, b: Optional[P
     def bwd():
         if out.g is None:
             return
+        pm, pr = (_p(mean), _p(rstd)) if mean is not None else (None, None)   # (keeps the saved stats alive)
         dz = _new(B, P, E, like=ref)
         want_ln = ln is not None and (ln[0].req or ln[1].req)
         gw = W.grad(w_full_support and P == P_full) if W.req else None
         gb = b.grad(P == P_full) if (b is not None and b.req) else None
-        targets = _grad_targets(seg_list)
+        targets = _grad_targets(seg_list) if FUSED_CALLS else None
         if targets is not None and _distinct_woffs(seg_list):
             dsp, flags = targets
             ws = None
