@@ -130,7 +130,7 @@ def _grad_targets(seg_list: Sequence[Seg]):
     allocated on first touch; a segment whose source needs no gradient gets a null pointer."""
     keys = [(id(s.v), s.off) for s in seg_list if s.v.req and s.width > 0]
     if len(keys) != len(set(keys)):
-        return None
+        return None               # (checked before anything is allocated)
     fresh = set()
     items, flags = [], []
     for s in seg_list:
@@ -224,8 +224,9 @@ def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[
         want_ln = ln is not None and (ln[0].req or ln[1].req)
         gw = W.grad(w_full_support and N == W.t.shape[0]) if W.req else None
         gb = b.grad(N == b.t.shape[0]) if (b is not None and b.req) else None
-        targets = _grad_targets(seg_list) if FUSED_CALLS else None
-        if targets is not None and _distinct_woffs(seg_list):
+        # (_grad_targets allocates the gradient buffers it hands out: only call it when its result is used)
+        targets = _grad_targets(seg_list) if (FUSED_CALLS and _distinct_woffs(seg_list)) else None
+        if targets is not None:
             dsp, flags = targets
             call("nasrec_linear_ln_bwd", _p(out.g, out_off), ldy, d_out, _p(z), M, N, gam, bet, pm, pr, int(relu), sp,
                  dsp, flags, ns, _p(W.t), ldw, n_off, _p(gw) if gw is not None else None,
@@ -297,8 +298,9 @@ def sproj_ln(tape: Tape, seg_list: Sequence[Seg], B: int, W: PVar, b: Optional[P
         want_ln = ln is not None and (ln[0].req or ln[1].req)
         gw = W.grad(w_full_support and P == P_full) if W.req else None
         gb = b.grad(P == P_full) if (b is not None and b.req) else None
-        targets = _grad_targets(seg_list) if FUSED_CALLS else None
-        if targets is not None and _distinct_woffs(seg_list):
+        # (_grad_targets allocates the gradient buffers it hands out: only call it when its result is used)
+        targets = _grad_targets(seg_list) if (FUSED_CALLS and _distinct_woffs(seg_list)) else None
+        if targets is not None:
             dsp, flags = targets
             ws = None
             if gw is not None:
