@@ -42,4 +42,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return red[32];
 }
 
+// library scratch attached with nasrec_set_workspace (gemm.cu); stream-ordered reuse by every kernel family
+void nasrec_internal_workspace(float** ws, long long* nfloats);
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -250,6 +250,11 @@ bool segs_ok(const nasrec_seg_t* segs, int nseg) {
 
 }  // namespace
 
+void nasrec_internal_workspace(float** ws, long long* nfloats) {
+    *ws = g_ws;
+    *nfloats = g_ws_floats;
+}
+
 extern "C" {
 
 int nasrec_set_gemm_mode(int mode) {

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
     if (tid == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, TC_PRODUCERS);
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS / 32);   // one arrival per producer warp
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_done, 1);
@@ -363,8 +363,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                     uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
                     tile_sts<TC_BM>(ra[h], st, st + Cfg::A_BYTES, tid, nprod > 1);
                     tile_sts<BN>(rb[h], st + 2 * Cfg::A_BYTES, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, tid, nprod > 1);
-                    fence_proxy_async_smem();
-                    mbar_arrive(bar_full + 8 * s);
+                    fence_proxy_async_smem();          // every writer orders its generic-proxy stores
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full + 8 * s);
                     t_cur = t_nxt;
                     kk_cur = kk_nxt;
                 }

@@ -58,46 +58,90 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
     }
 }
 
+// dx for every row (persistent warps, fixed row -> warp assignment); when `part` is given, also this
+// CTA's partial column sums of dgamma/dbeta (part[cta][0][j], part[cta][1][j]) for the second stage.
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ dy, long long lddy, int d_out,
                                                      const float* __restrict__ x, long long ldx, int M, int N,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta,
                                                      const float* __restrict__ mean_in,
                                                      const float* __restrict__ rstd_in, int relu,
-                                                     float* __restrict__ dx, long long lddx) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const float* xr = x + (long long)row * ldx;
-    const float* dyr = dy + (long long)row * lddy;
-    float xh[LN_VPT], a[LN_VPT];
-    float s1 = 0.f, s2 = 0.f;
+                                                     float* __restrict__ dx, long long lddx,
+                                                     float* __restrict__ part) {
+    extern __shared__ float sred[];          // [2][4][N] when part != null
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float accg[LN_VPT], accb[LN_VPT];
 #pragma unroll
     for (int k = 0; k < LN_VPT; ++k) {
-        const int j = lane + 32 * k;
-        xh[k] = 0.f;
-        a[k] = 0.f;
-        if (j < N) {
-            xh[k] = (xr[j] - mean) * rstd;
-            if (j < d_out) {
-                const float g = gamma[j];
-                float d = dyr[j];
-                if (relu && (xh[k] * g + beta[j]) <= 0.f) d = 0.f;
-                a[k] = d * g;
+        accg[k] = 0.f;
+        accb[k] = 0.f;
+    }
+    for (int row = blockIdx.x * 4 + w; row < M; row += gridDim.x * 4) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        const float* xr = x + (long long)row * ldx;
+        const float* dyr = dy + (long long)row * lddy;
+        float xh[LN_VPT], a[LN_VPT];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN_VPT; ++k) {
+            const int j = lane + 32 * k;
+            xh[k] = 0.f;
+            a[k] = 0.f;
+            if (j < N) {
+                xh[k] = (xr[j] - mean) * rstd;
+                if (j < d_out) {
+                    const float g = gamma[j];
+                    float d = dyr[j];
+                    if (relu && (xh[k] * g + beta[j]) <= 0.f) d = 0.f;
+                    a[k] = d * g;
+                    accg[k] = fmaf(d, xh[k], accg[k]);
+                    accb[k] += d;
+                }
+            }
+            s1 += a[k];
+            s2 += a[k] * xh[k];
+        }
+        const float c1 = warp_sum(s1) / (float)N;
+        const float c2 = warp_sum(s2) / (float)N;
+        if (dx) {
+            float* dxr = dx + (long long)row * lddx;
+#pragma unroll
+            for (int k = 0; k < LN_VPT; ++k) {
+                const int j = lane + 32 * k;
+                if (j < N) dxr[j] = rstd * (a[k] - c1 - xh[k] * c2);
             }
         }
-        s1 += a[k];
-        s2 += a[k] * xh[k];
     }
-    const float c1 = warp_sum(s1) / (float)N;
-    const float c2 = warp_sum(s2) / (float)N;
-    float* dxr = dx + (long long)row * lddx;
+    if (!part) return;
+    float* sg = sred;
+    float* sb = sred + 4 * N;
 #pragma unroll
     for (int k = 0; k < LN_VPT; ++k) {
         const int j = lane + 32 * k;
-        if (j < N) dxr[j] = rstd * (a[k] - c1 - xh[k] * c2);
+        if (j < N) {
+            sg[w * N + j] = accg[k];
+            sb[w * N + j] = accb[k];
+        }
     }
+    __syncthreads();
+    float* o = part + (long long)blockIdx.x * 2 * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        o[j] = (sg[j] + sg[N + j]) + (sg[2 * N + j] + sg[3 * N + j]);
+        o[N + j] = (sb[j] + sb[N + j]) + (sb[2 * N + j] + sb[3 * N + j]);
+    }
+}
+
+__global__ void ln_param_final_kernel(const float* __restrict__ part, int nblk, int N, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta, int accumulate) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    float g = 0.f, b = 0.f;
+    for (int k = 0; k < nblk; ++k) {
+        g += part[(long long)k * 2 * N + j];
+        b += part[(long long)k * 2 * N + N + j];
+    }
+    dgamma[j] = accumulate ? dgamma[j] + g : g;
+    dbeta[j] = accumulate ? dbeta[j] + b : b;
 }
 
 // dgamma[j] = sum_m g[m,j]*xhat[m,j], dbeta[j] = sum_m g[m,j]; one CTA per 32 columns,
@@ -141,74 +185,149 @@ __global__ void __launch_bounds__(1024) ln_param_grad_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------ LN over P of [B,P,16]
-__global__ void __launch_bounds__(256) ln3_fwd_kernel(const float* __restrict__ z, long long zbs, int B, int P,
+// One warp per sample: lane = (ph, e) with e = lane & 15 the embedding column and ph = lane >> 4 the
+// parity of the row it owns (rows ph, ph+2, ...), so every warp load is one contiguous 128-byte line
+// (two 64-byte rows) and a column's P <= 64 values live in 32 registers of two lanes.
+constexpr int LN3_MAXP = 64;
+constexpr int LN3_V = LN3_MAXP / 2;
+
+__global__ void __launch_bounds__(128) ln3_fwd_kernel(const float* __restrict__ z, long long zbs, int B, int P,
                                                       const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, float eps, int relu,
                                                       int p_out, float* __restrict__ y, long long ybs,
                                                       float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                       int accumulate) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B * 16) return;
-    const int b = t >> 4, e = t & 15;
+    const int lane = threadIdx.x & 31, e = lane & 15, ph = lane >> 4;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
     const float* zp = z + (long long)b * zbs + e;
+    float v[LN3_V];
     float s = 0.f;
-    for (int p = 0; p < P; ++p) s += zp[p * 16];
+#pragma unroll
+    for (int k = 0; k < LN3_V; ++k) {
+        const int p = 2 * k + ph;
+        v[k] = p < P ? zp[p * 16] : 0.f;
+        s += v[k];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
     const float mean = s / (float)P;
     float q = 0.f;
-    for (int p = 0; p < P; ++p) {
-        const float d = zp[p * 16] - mean;
+#pragma unroll
+    for (int k = 0; k < LN3_V; ++k) {
+        const int p = 2 * k + ph;
+        const float d = p < P ? v[k] - mean : 0.f;
         q += d * d;
     }
+    q += __shfl_xor_sync(0xffffffffu, q, 16);
     const float rstd = 1.0f / sqrtf(q / (float)P + eps);
-    mean_out[t] = mean;
-    rstd_out[t] = rstd;
+    if (ph == 0) {
+        mean_out[b * 16 + e] = mean;
+        rstd_out[b * 16 + e] = rstd;
+    }
     float* yp = y + (long long)b * ybs + e;
-    for (int p = 0; p < p_out; ++p) {
-        float o = (zp[p * 16] - mean) * rstd * gamma[p] + beta[p];
-        if (relu) o = fmaxf(o, 0.f);
-        yp[p * 16] = accumulate ? yp[p * 16] + o : o;
+#pragma unroll
+    for (int k = 0; k < LN3_V; ++k) {
+        const int p = 2 * k + ph;
+        if (p < p_out) {
+            float o = (v[k] - mean) * rstd * gamma[p] + beta[p];
+            if (relu) o = fmaxf(o, 0.f);
+            yp[p * 16] = accumulate ? yp[p * 16] + o : o;
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) ln3_bwd_kernel(const float* __restrict__ dy, long long dybs, int p_out,
+// dz for every sample; when `part` is given, also this CTA's partial sums of dgamma/dbeta
+// (part[cta][0][p], part[cta][1][p]) for the fixed-order second stage below.
+__global__ void __launch_bounds__(128) ln3_bwd_kernel(const float* __restrict__ dy, long long dybs, int p_out,
                                                       const float* __restrict__ z, long long zbs, int B, int P,
                                                       const float* __restrict__ gamma,
                                                       const float* __restrict__ beta,
                                                       const float* __restrict__ mean_in,
                                                       const float* __restrict__ rstd_in, int relu,
-                                                      float* __restrict__ dz, long long dzbs) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B * 16) return;
-    const int b = t >> 4, e = t & 15;
-    const float mean = mean_in[t], rstd = rstd_in[t];
-    const float* zp = z + (long long)b * zbs + e;
-    const float* dp = dy + (long long)b * dybs + e;
-    float s1 = 0.f, s2 = 0.f;
-    for (int p = 0; p < p_out; ++p) {
-        const float xh = (zp[p * 16] - mean) * rstd;
-        const float g = gamma[p];
-        float d = dp[p * 16];
-        if (relu && (xh * g + beta[p]) <= 0.f) d = 0.f;
-        const float a = d * g;
-        s1 += a;
-        s2 += a * xh;
+                                                      float* __restrict__ dz, long long dzbs,
+                                                      float* __restrict__ part) {
+    __shared__ float sg[4][LN3_MAXP], sb[4][LN3_MAXP];
+    const int lane = threadIdx.x & 31, e = lane & 15, ph = lane >> 4, w = threadIdx.x >> 5;
+    float accg[LN3_V], accb[LN3_V];
+#pragma unroll
+    for (int k = 0; k < LN3_V; ++k) {
+        accg[k] = 0.f;
+        accb[k] = 0.f;
     }
-    const float c1 = s1 / (float)P, c2 = s2 / (float)P;
-    float* op = dz + (long long)b * dzbs + e;
-    for (int p = 0; p < P; ++p) {
-        const float xh = (zp[p * 16] - mean) * rstd;
-        float a = 0.f;
-        if (p < p_out) {
-            const float g = gamma[p];
-            float d = dp[p * 16];
-            if (relu && (xh * g + beta[p]) <= 0.f) d = 0.f;
-            a = d * g;
+    for (int b = blockIdx.x * 4 + w; b < B; b += gridDim.x * 4) {
+        const float mean = mean_in[b * 16 + e], rstd = rstd_in[b * 16 + e];
+        const float* zp = z + (long long)b * zbs + e;
+        const float* dp = dy + (long long)b * dybs + e;
+        float xh[LN3_V], a[LN3_V];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN3_V; ++k) {
+            const int p = 2 * k + ph;
+            xh[k] = 0.f;
+            a[k] = 0.f;
+            if (p < P) {
+                xh[k] = (zp[p * 16] - mean) * rstd;
+                if (p < p_out) {
+                    const float g = gamma[p];
+                    float d = dp[p * 16];
+                    if (relu && (xh[k] * g + beta[p]) <= 0.f) d = 0.f;
+                    a[k] = d * g;
+                    accg[k] = fmaf(d, xh[k], accg[k]);
+                    accb[k] += d;
+                }
+            }
+            s1 += a[k];
+            s2 = fmaf(a[k], xh[k], s2);
         }
-        op[p * 16] = rstd * (a - c1 - xh * c2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+        const float c1 = s1 / (float)P, c2 = s2 / (float)P;
+        if (dz) {
+            float* op = dz + (long long)b * dzbs + e;
+#pragma unroll
+            for (int k = 0; k < LN3_V; ++k) {
+                const int p = 2 * k + ph;
+                if (p < P) op[p * 16] = rstd * (a[k] - c1 - xh[k] * c2);
+            }
+        }
+    }
+    if (!part) return;
+    // sum over the 16 embedding columns (lanes with equal ph), then over the CTA's 4 warps
+#pragma unroll
+    for (int k = 0; k < LN3_V; ++k) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            accg[k] += __shfl_xor_sync(0xffffffffu, accg[k], o);
+            accb[k] += __shfl_xor_sync(0xffffffffu, accb[k], o);
+        }
+        if (e == 0) {
+            sg[w][2 * k + ph] = accg[k];
+            sb[w][2 * k + ph] = accb[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < LN3_MAXP) {
+        const int p = threadIdx.x;
+        float* o = part + (long long)blockIdx.x * 2 * LN3_MAXP;
+        o[p] = (sg[0][p] + sg[1][p]) + (sg[2][p] + sg[3][p]);
+        o[LN3_MAXP + p] = (sb[0][p] + sb[1][p]) + (sb[2][p] + sb[3][p]);
     }
 }
 
-// one CTA per p: dgamma[p] = sum_{b,e} g*xhat, dbeta[p] = sum g
+__global__ void ln3_param_final_kernel(const float* __restrict__ part, int nblk, int P, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate) {
+    const int p = threadIdx.x;
+    if (p >= P) return;
+    float g = 0.f, b = 0.f;
+    for (int k = 0; k < nblk; ++k) {
+        g += part[(long long)k * 2 * LN3_MAXP + p];
+        b += part[(long long)k * 2 * LN3_MAXP + LN3_MAXP + p];
+    }
+    dgamma[p] = accumulate ? dgamma[p] + g : g;
+    dbeta[p] = accumulate ? dbeta[p] + b : b;
+}
+
+// fallback when no workspace is attached: one CTA per p, dgamma[p] = sum_{b,e} g*xhat, dbeta[p] = sum g
 __global__ void __launch_bounds__(256) ln3_param_grad_kernel(const float* __restrict__ dy, long long dybs,
                                                              int p_out, const float* __restrict__ z,
                                                              long long zbs, int B, int P,
@@ -322,13 +441,26 @@ int nasrec_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* x, int6
     CHECK_ARG(dy && x && gamma && beta && mean && rstd && M > 0 && N > 0 && d_out >= 0 && d_out <= N);
     if (N > LN_MAXN) return NASREC_ETOOBIG;
     cudaStream_t st = as_stream(stream);
-    if (dx) {
-        ln_bwd_kernel<<<cdiv(M, 4), 128, 0, st>>>(dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx,
-                                                  lddx);
+    const bool want = dgamma && dbeta;
+    if (!dx && !want) return 0;
+    float* ws = nullptr;
+    long long nws = 0;
+    nasrec_internal_workspace(&ws, &nws);
+    int grid = cdiv(M, 4);
+    if (grid > 296) grid = 296;                    // persistent warps: fixed row -> warp assignment
+    const bool fused = want && ws && nws >= (long long)grid * 2 * N;
+    if (dx || fused) {
+        const size_t smem = fused ? (size_t)8 * N * sizeof(float) : 0;
+        ln_bwd_kernel<<<grid, 128, smem, st>>>(dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx, lddx,
+                                               fused ? ws : nullptr);
         int rc = nasrec_launch_status();
         if (rc) return rc;
     }
-    if (dgamma && dbeta) {
+    if (fused) {
+        ln_param_final_kernel<<<cdiv(N, 256), 256, 0, st>>>(ws, grid, N, dgamma, dbeta, accumulate_params);
+        return nasrec_launch_status();
+    }
+    if (want) {
         ln_param_grad_kernel<<<cdiv(N, 32), 1024, 0, st>>>(dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd,
                                                            relu, dgamma, dbeta, accumulate_params);
         return nasrec_launch_status();
@@ -340,8 +472,9 @@ int nasrec_ln3_fwd(const float* z, int64_t z_bstride, int B, int P, const float*
                    float eps, int relu, int p_out, float* y, int64_t y_bstride, float* mean, float* rstd,
                    int accumulate, void* stream) {
     CHECK_ARG(z && gamma && beta && y && mean && rstd && B > 0 && P > 0 && p_out >= 0 && p_out <= P);
-    ln3_fwd_kernel<<<cdiv((long long)B * 16, 256), 256, 0, as_stream(stream)>>>(
-        z, z_bstride, B, P, gamma, beta, eps, relu, p_out, y, y_bstride, mean, rstd, accumulate);
+    if (P > LN3_MAXP) return NASREC_ETOOBIG;
+    ln3_fwd_kernel<<<cdiv(B, 4), 128, 0, as_stream(stream)>>>(z, z_bstride, B, P, gamma, beta, eps, relu, p_out, y,
+                                                             y_bstride, mean, rstd, accumulate);
     return nasrec_launch_status();
 }
 
@@ -350,14 +483,27 @@ int nasrec_ln3_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* 
                    float* dz, int64_t dz_bstride, float* dgamma, float* dbeta, int accumulate_params,
                    void* stream) {
     CHECK_ARG(dy && z && gamma && beta && mean && rstd && B > 0 && P > 0 && p_out >= 0 && p_out <= P);
+    if (P > LN3_MAXP) return NASREC_ETOOBIG;
     cudaStream_t st = as_stream(stream);
-    if (dz) {
-        ln3_bwd_kernel<<<cdiv((long long)B * 16, 256), 256, 0, st>>>(dy, dy_bstride, p_out, z, z_bstride, B, P,
-                                                                     gamma, beta, mean, rstd, relu, dz, dz_bstride);
+    const bool want = dgamma && dbeta;
+    if (!dz && !want) return 0;
+    float* ws = nullptr;
+    long long nws = 0;
+    nasrec_internal_workspace(&ws, &nws);
+    int grid = cdiv(B, 4);
+    if (grid > 148) grid = 148;                    // persistent warps: fixed sample -> warp assignment
+    const bool fused = want && ws && nws >= (long long)grid * 2 * LN3_MAXP;
+    if (dz || fused) {
+        ln3_bwd_kernel<<<grid, 128, 0, st>>>(dy, dy_bstride, p_out, z, z_bstride, B, P, gamma, beta, mean, rstd, relu,
+                                             dz, dz_bstride, fused ? ws : nullptr);
         int rc = nasrec_launch_status();
         if (rc) return rc;
     }
-    if (dgamma && dbeta) {
+    if (fused) {
+        ln3_param_final_kernel<<<1, LN3_MAXP, 0, st>>>(ws, grid, P, dgamma, dbeta, accumulate_params);
+        return nasrec_launch_status();
+    }
+    if (want) {
         ln3_param_grad_kernel<<<P, 256, 0, st>>>(dy, dy_bstride, p_out, z, z_bstride, B, P, gamma, beta, mean, rstd,
                                                  relu, dgamma, dbeta, accumulate_params);
         return nasrec_launch_status();
