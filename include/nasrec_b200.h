@@ -227,6 +227,21 @@ int nasrec_attn_bwd(const float* dy, int64_t dy_bstride, const float* x, int64_t
  * loss[0] = mean(max(z,0) - z*y + log1p(exp(-|z|))); dlogits[b] = (sigmoid(z)-y)/B * grad_scale. */
 int nasrec_bce_fwd_bwd(const float* logits, const float* y, int B, float grad_scale, float* loss,
                        float* dlogits, void* stream);
+/* f3  evaluation metrics over n concatenated predictions (train_utils.py:158-178):
+ * out3[0] = accuracy of (sigmoid(z) > 0.5) vs y; out3[1] = ROC-AUC, ties counted 1/2 (==
+ * sklearn.metrics.roc_auc_score on the fp32 sigmoid outputs; exact integer pair count);
+ * out3[2] = mean BCE-with-logits.  out3: 3 device doubles.  ws: nasrec_binary_metrics_ws_bytes(n). */
+int64_t nasrec_binary_metrics_ws_bytes(int64_t n);
+int nasrec_binary_metrics(const float* logits, const float* y, int64_t n, void* ws, int64_t ws_bytes,
+                          double* out3, void* stream);
+/* f2  raw batch -> model inputs (data_pipes.py:135-175, VanillaTransform{Criteo,Avazu,KDD}):
+ * int_x[b,c] = log(max(0, dense_raw[b,c]) + 1);
+ * cat_x[b,f] = (int(hex[b,f], 16) if non-empty else -1).fmod(num_rows[f] - 1) + 1.
+ * hex: [B,F,width] bytes, each field NUL-padded hex digits (width <= 15); a non-hex byte sets
+ * err_flag.  num_rows: F device int64.  For Avazu pass nd = 0 (its dense input is all zeros). */
+int nasrec_input_transform(const float* dense_raw, int nd, const uint8_t* hex, int width, int F,
+                           const int64_t* num_rows, int64_t B, float* int_x, int64_t* cat_x, int* err_flag,
+                           void* stream);
 /* (grads/sizes/w/state below are HOST arrays of device pointers / element counts.)
  * Global L2 norm of n tensors + extra pre-reduced sums of squares, then the
  * clip_grad_norm_ coefficient (train_utils.py:285): out[0] = total_norm,

@@ -31,6 +31,22 @@ def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def rank_world(group=None) -> Tuple[int, int]:
+    """(rank, world) of the current process; (0, 1) outside torch.distributed."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def allgather_records(local: list, group=None) -> list:
+    """Every rank contributes a list of per-candidate records (host objects); every rank gets
+    the concatenation in rank order == candidate order (shards are contiguous)."""
+    world = dist.get_world_size(group)
+    parts: List[Optional[list]] = [None] * world
+    dist.all_gather_object(parts, list(local), group=group)
+    return [r for part in parts for r in part]
+
+
 def allreduce_flat(tensors: Sequence[torch.Tensor], group=None) -> List[torch.Tensor]:
     """Sum-all-reduce a list of tensors as ONE bucket; returns views into the bucket
     (replacing the inputs), so no copy-back pass is needed."""

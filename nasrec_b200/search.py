@@ -10,15 +10,57 @@ each evaluation batch once, and streams candidates through it.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+import copy
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import engine as eng
-from .engine import Tape, Var
+from .engine import Seg, Tape, Var
 from .supernet.modules import Run
 from .supernet.supernet import SuperNet
+from .utils.lr_schedule import finetune_lr_sequence
+
+_MACRO_KEYS = ("dense_idx", "sparse_idx", "dense_left_idx", "dense_right_idx")
+_MICRO_KEYS = ("active_nodes", "dense_in_dims", "sparse_in_dims", "dense_sparse_interact", "deep_fm")
+
+
+def _plain(o):
+    """numpy scalars/arrays -> builtin ints/lists (choices travel through pickle/JSON)."""
+    if isinstance(o, dict):
+        return {str(k): _plain(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_plain(v) for v in o]
+    if isinstance(o, np.ndarray):
+        return [_plain(v) for v in o.tolist()]
+    if isinstance(o, np.generic):
+        return o.item()
+    return o
+
+
+def _draw_macro(b: int) -> Dict[str, List[int]]:
+    """One block's connection draw shared by generate_random_choice and mutate_spec
+    (tokenizer.py:199-227, 280-308): at most 4 dense and 4 sparse sources, one left/right pair."""
+    n_dense = 1 + np.random.choice(min(4, b + 1))
+    n_sparse = 1 + np.random.choice(min(4, b + 1))
+    bi = np.random.choice(b + 1, 2)
+    return {"dense_idx": np.random.choice(b + 1, n_dense, replace=False).reshape(-1).tolist(),
+            "sparse_idx": np.random.choice(b + 1, n_sparse, replace=False).reshape(-1).tolist(),
+            "dense_left_idx": bi[:1].reshape(-1).tolist(), "dense_right_idx": bi[1:].reshape(-1).tolist()}
+
+
+def _draw_micro(cfg: Dict[str, Any]) -> Dict[str, Any]:
+    """One block's operator draw, rejecting the all-zero pair (tokenizer.py:246-258, 310-330)."""
+    while True:
+        micro = {"active_nodes": sorted([int(np.random.choice(cfg["dense_nodes"]))] +
+                                        [int(np.random.choice(cfg["sparse_nodes"]))]),
+                 "dense_in_dims": int(np.random.choice(cfg["dense_node_dims"])),
+                 "sparse_in_dims": int(np.random.choice(cfg["sparse_node_dims"])),
+                 "dense_sparse_interact": int(np.random.choice([0, 1])),
+                 "deep_fm": int(np.random.choice([0, 1]))}
+        if micro["active_nodes"] != cfg["zero_nodes"]:
+            return micro
 
 
 def generate_random_choice(num_blocks: int, ops_config: Dict[str, Any]) -> Dict[str, Any]:
@@ -27,25 +69,61 @@ def generate_random_choice(num_blocks: int, ops_config: Dict[str, Any]) -> Dict[
     np.random.choice(num_blocks)                      # tokenizer.py:272 draws and discards a block index
     choice = {"macro": [], "micro": []}
     for b in range(num_blocks):
-        n_dense = 1 + np.random.choice(min(4, b + 1))
-        n_sparse = 1 + np.random.choice(min(4, b + 1))
-        bi = np.random.choice(b + 1, 2)
-        macro = {"dense_idx": np.random.choice(b + 1, n_dense, replace=False).reshape(-1).tolist(),
-                 "sparse_idx": np.random.choice(b + 1, n_sparse, replace=False).reshape(-1).tolist(),
-                 "dense_left_idx": bi[:1].reshape(-1).tolist(), "dense_right_idx": bi[1:].reshape(-1).tolist()}
-        cfg = ops_config[b] if isinstance(ops_config, list) else ops_config
-        while True:
-            micro = {"active_nodes": sorted([int(np.random.choice(cfg["dense_nodes"]))] +
-                                            [int(np.random.choice(cfg["sparse_nodes"]))]),
-                     "dense_in_dims": int(np.random.choice(cfg["dense_node_dims"])),
-                     "sparse_in_dims": int(np.random.choice(cfg["sparse_node_dims"])),
-                     "dense_sparse_interact": int(np.random.choice([0, 1])),
-                     "deep_fm": int(np.random.choice([0, 1]))}
-            if micro["active_nodes"] != cfg["zero_nodes"]:
-                break
-        choice["macro"].append(macro)
-        choice["micro"].append(micro)
+        choice["macro"].append(_draw_macro(b))
+        choice["micro"].append(_draw_micro(ops_config[b] if isinstance(ops_config, list) else ops_config))
     return choice
+
+
+class Tokenizer:
+    """searcher/tokenizer.py:30-336: choice -> integer token / hash string (the EA's duplicate
+    filter and the ``hash_token`` field of results.pickle) and the mutation operator."""
+
+    def __init__(self, num_blocks: int, ops_config: Any):
+        self._num_blocks = num_blocks
+        self._ops_config = ops_config
+
+    def _cfg(self, b: int) -> Dict[str, Any]:
+        return self._ops_config[b] if isinstance(self._ops_config, list) else self._ops_config
+
+    def tokenize(self, choice: Dict[str, Any]) -> np.ndarray:
+        """tokenizer.py:158-186: per block 4 x num_blocks connection bits; then per block
+        num_nodes activity bits, the two width indices and two one-hot pairs."""
+        nb = self._num_blocks
+        enc: List[int] = []
+        for mac in choice["macro"]:
+            for key in _MACRO_KEYS:
+                picked = set(int(v) for v in np.asarray(mac[key]).reshape(-1))
+                enc += [1 if i in picked else 0 for i in range(nb)]
+        for b, mic in enumerate(choice["micro"]):
+            cfg = self._cfg(b)
+            active = set(int(v) for v in np.asarray(mic["active_nodes"]).reshape(-1))
+            enc += [1 if i in active else 0 for i in range(cfg["num_nodes"])]
+            enc.append(list(cfg["dense_node_dims"]).index(int(mic["dense_in_dims"])))
+            enc.append(list(cfg["sparse_node_dims"]).index(int(mic["sparse_in_dims"])))
+            enc += [1, 0] if mic["dense_sparse_interact"] == 0 else [0, 1]
+            enc += [1, 0] if mic["deep_fm"] == 0 else [0, 1]
+        return np.asarray(enc, dtype=np.int64)
+
+    def hash_token(self, token) -> str:               # tokenizer.py:188-190
+        return "".join(str(int(x)) for x in token)
+
+    def generate_random_choice(self) -> Dict[str, Any]:
+        return generate_random_choice(self._num_blocks, self._ops_config)
+
+    def mutate_spec(self, choice: Dict[str, Any]) -> Dict[str, Any]:
+        """tokenizer.py:192-265: redraw ONE field of ONE block (a whole fresh draw is made and
+        one key of it kept, so the RNG consumption matches the reference)."""
+        b = int(np.random.choice(self._num_blocks))
+        level = "macro" if np.random.random() > 0.5 else "micro"
+        out = copy.deepcopy(choice)
+        if level == "macro":
+            fresh = _draw_macro(b)
+            key = str(np.random.choice(list(_MACRO_KEYS)))
+        else:
+            fresh = _draw_micro(self._cfg(b))
+            key = str(np.random.choice(list(_MICRO_KEYS)))
+        out[level][b][key] = copy.deepcopy(fresh[key])
+        return out
 
 
 def binary_metrics_device(logits: torch.Tensor, y: torch.Tensor) -> Tuple[float, float, float]:
@@ -147,5 +225,186 @@ class SubnetEvaluator:
             del g
         return res
 
+    def finetune_and_score(self, choice: Dict[str, Any],
+                           train_batches: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
+                           eval_batches: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
+                           lr: float = 0.04, eps: float = 1e-2, clip: Optional[float] = 5.0,
+                           trunk_samples: int = 8192, restore: bool = True) -> Dict[str, Any]:
+        """The reference's per-candidate recipe (eval_subnet_from_supernet.py:71-207 with
+        --finetune_whole_supernet 0): Adagrad(lr, eps) + clip on ``_final`` only, one step per
+        training batch under the cosine schedule with warm-up = steps // 10
+        (lr_schedule.finetune_lr_sequence), then log-loss / AUC / accuracy on the evaluation batches.
+
+        Everything below ``_final`` is frozen, so the trunk is a pure function of the batch: it is run
+        once over groups of up to ``trunk_samples`` concatenated training samples, and the optimizer
+        steps then walk the cached penultimate features batch by batch (same batches, same order, same
+        update as the reference's loop; only the redundant trunk launches are gone).  ``restore``
+        puts the supernet's ``_final`` back afterwards so candidates stay independent."""
+        from .utils.train_utils import FusedTrainer
+        m = self.model
+        if m._needs_materialize():
+            m.materialize(train_batches[0][0].shape[1] if train_batches else eval_batches[0][0].shape[1])
+        W, b = m._final.weight, m._final.bias
+        saved = (W.detach().clone(), b.detach().clone())
+        macro, micro = choice["macro"], choice["micro"]
+        n = len(train_batches)
+        lrs = finetune_lr_sequence(n, lr) if n else []
+        trainer = FusedTrainer(m, lr, eps, clip)
+        ok = {id(W), id(b)}
+        losses: List[torch.Tensor] = []
+        i = 0
+        with _lib_pin():
+            while i < n:
+                j, tot = i, 0
+                while j < n and (j == i or tot + train_batches[j][0].shape[0] <= trunk_samples):
+                    tot += train_batches[j][0].shape[0]
+                    j += 1
+                group = train_batches[i:j]
+                int_x = group[0][0] if j - i == 1 else torch.cat([g[0] for g in group])
+                cat_x = group[0][1] if j - i == 1 else torch.cat([g[1] for g in group])
+                cat_x = cat_x if cat_x.dtype == torch.int64 else cat_x.long()
+                with torch.no_grad():
+                    segs = m._run_trunk(Run(Tape(False)), Var(int_x.contiguous()), cat_x.contiguous(), macro, micro)
+                row = 0
+                for k in range(i, j):
+                    Bk = train_batches[k][0].shape[0]
+                    tape = Tape(True)
+                    run = Run(tape, grad_ok=ok)
+                    sl = [Seg(sg.v, sg.off + row * sg.ld, sg.ld, sg.width, sg.w_off) for sg in segs]
+                    logits = m._run_head(run, sl, Bk)
+                    loss, dl = eng.bce_with_logits(logits.t, train_batches[k][2])
+                    logits.g = dl
+                    tape.backward()
+                    trainer.apply(run, None, lrs[k])
+                    losses.append(loss)
+                    row += Bk
+                i = j
+        res = self.score([choice], eval_batches)[0]
+        res["train_loss"] = [float(v) for v in torch.cat([l.reshape(1) for l in losses]).tolist()] if losses else []
+        res["choice"] = choice
+        if restore:
+            with torch.no_grad():
+                W.copy_(saved[0])
+                b.copy_(saved[1])
+        else:
+            res["final_weight"], res["final_bias"] = W.detach().clone(), b.detach().clone()
+        return res
+
     def release(self):
         self._emb_cache.clear()
+
+
+def _lib_pin():
+    from . import _lib
+    return _lib.pin_stream()
+
+
+def draw_fixed_path_candidate(model: SuperNet) -> Dict[str, Any]:
+    """How the reference's random phase obtains a candidate: a fresh supernet switched to
+    'fixed-path' draws its subnet on the first forward (searcher_utils.py:57-70 with choice=None,
+    eval_subnet_from_supernet.py:103; samplers supernet.py:772-812, 1305-1313)."""
+    model.macro_last_choice = None
+    model._fixed_path_called = False
+    for blk in model._blocks:
+        blk.micro_last_choice = None
+        blk._fixed_path_called = False
+    model.configure_path_sampling_strategy("fixed-path")
+    model._sample()
+    return _plain(model.choice)
+
+
+class Searcher:
+    """In-process, GPU-resident restatement of searcher/searcher.py:26-295.
+
+    The reference evaluates each candidate in a fresh OS process (one per GPU id) that rebuilds the
+    supernet, warms it up and reloads the checkpoint; here one resident supernet per rank scores a
+    contiguous shard of every batch of candidates (candidates are independent units, no
+    data-path collective) and the per-candidate records are gathered to every rank, so all ranks
+    take identical EA decisions from identical numpy RNG streams.  Records keep the results.pickle
+    schema: {"choice", "test_acc", "test_auroc", "test_loss", "hash_token"}."""
+
+    CRITERIA = ("test_loss", "test_acc", "test_auroc")
+
+    def __init__(self, evaluator: SubnetEvaluator, tokenizer: Tokenizer, train_batches, eval_batches,
+                 lr: float = 0.04, finetune: bool = True, group=None):
+        self.evaluator = evaluator
+        self._tokenizer = tokenizer
+        self.train_batches = train_batches
+        self.eval_batches = eval_batches
+        self.lr = lr
+        self.finetune = finetune
+        self.group = group
+        self.all_results: List[Dict[str, Any]] = []
+
+    # -- evaluation of a batch of candidates, sharded over ranks
+    def evaluate(self, choices: Sequence[Dict[str, Any]]) -> List[Dict[str, Any]]:
+        from . import parallel
+        rank, world = parallel.rank_world(self.group)
+        lo, hi = parallel.shard_range(len(choices), world, rank)
+        mine = []
+        for ch in choices[lo:hi]:
+            if self.finetune and self.train_batches:
+                r = self.evaluator.finetune_and_score(ch, self.train_batches, self.eval_batches, lr=self.lr)
+                r.pop("train_loss", None)
+            else:
+                r = self.evaluator.score([ch], self.eval_batches)[0]
+            r["choice"] = _plain(ch)
+            r["hash_token"] = self._tokenizer.hash_token(self._tokenizer.tokenize(ch))
+            mine.append(r)
+        return parallel.allgather_records(mine, self.group) if world > 1 else mine
+
+    @classmethod
+    def _sort_results_with_criterion(cls, results: Sequence[Dict[str, Any]], criterion: str = "test_loss"):
+        """searcher.py:56-80: ascending loss, descending accuracy / AUROC (stable argsort)."""
+        order = np.argsort(np.asarray([r[criterion] for r in results]).flatten())
+        if criterion in ("test_acc", "test_auroc"):
+            order = order[::-1]
+        return [results[int(i)] for i in order]
+
+    def random_search_from_supernet(self, budget: int = 200, criterion: str = "test_loss", top_k: int = 5,
+                                    sorted: bool = True) -> List[Dict[str, Any]]:   # searcher.py:88-165
+        assert top_k <= budget, "Should have 'top_k' smaller than 'budget'."
+        assert criterion in self.CRITERIA, NotImplementedError("Criterion {} is not supported!".format(criterion))
+        cands = [draw_fixed_path_candidate(self.evaluator.model) for _ in range(budget)]
+        self.all_results = self.evaluate(cands)
+        if sorted:
+            return self._sort_results_with_criterion(self.all_results, criterion)[:top_k]
+        return self.all_results[:top_k]
+
+    def regularized_evolution_from_supernet(self, n_generations: int = 50, n_childs: int = 16,
+                                            init_population: int = 100, sample_size: int = 5,
+                                            criterion: str = "test_loss", top_k: int = 2) -> List[Dict[str, Any]]:
+        """searcher.py:167-295: aging evolution.  Each generation samples ``sample_size`` members,
+        mutates the best of them ``num_mutations`` times per child (more early, fewer late), rejects
+        already-visited hashes, scores the ``n_childs`` children as ONE sharded batch, appends them and
+        retires the ``n_childs`` oldest members.  Returns the per-generation top_k history."""
+        assert criterion in self.CRITERIA, NotImplementedError("Criterion {} is not supported!".format(criterion))
+        assert top_k <= sample_size, ValueError(
+            "You must maintain more than 'top_k' children to append 'top_k' archs to history.")
+        assert sample_size < init_population, ValueError(
+            "Sample size must be no greater than the number of population ('init_population')!")
+        population = list(self.random_search_from_supernet(budget=init_population, criterion=criterion,
+                                                           top_k=init_population, sorted=False))
+        history: List[Dict[str, Any]] = []
+        visited = set()
+        for gen in range(n_generations):
+            picked = np.random.choice(len(population), sample_size, replace=False)     # searcher.py:82-86
+            parent = self._sort_results_with_criterion([population[int(i)] for i in picked], criterion)[0]
+            num_mutations = (n_generations - gen) // (max(20, n_generations // 5)) + 1
+            children = []
+            for _ in range(n_childs):
+                child = copy.deepcopy(parent["choice"])
+                while True:
+                    for _ in range(num_mutations):
+                        child = self._tokenizer.mutate_spec(child)
+                    h = self._tokenizer.hash_token(self._tokenizer.tokenize(child))
+                    if h not in visited:
+                        visited.add(h)
+                        break
+                children.append(child)
+            scored = self.evaluate(children)
+            population += scored
+            history += self._sort_results_with_criterion(scored, criterion)[:top_k]
+            population = population[n_childs:]
+        self.all_results = population
+        return history

@@ -442,6 +442,17 @@ class SuperNet(nn.Module):
         return need[1:]
 
     def _run_network(self, run: Run, int_x: Var, cat_x: torch.Tensor, macro, micro) -> Var:
+        segs = self._run_trunk(run, int_x, cat_x, macro, micro)
+        return self._run_head(run, segs, int_x.t.shape[0])
+
+    def _run_head(self, run: Run, segs: Sequence[Seg], B: int) -> Var:
+        """The final projection to the logit (supernet.py:592-598) on the trunk's segment list."""
+        return eng.linear_ln(run.tape, segs, B, run.pv(self._final.weight), run.pv(self._final.bias), None, False, 1,
+                             w_full_support=self._fixed)
+
+    def _run_trunk(self, run: Run, int_x: Var, cat_x: torch.Tensor, macro, micro) -> List[Seg]:
+        """Stem + choice blocks; returns the last block's outputs as the segment list the
+        final layer consumes (what the reference concatenates at supernet.py:592-597)."""
         B, nd_ = int_x.t.shape
         F = self._sparse_input_size
         if cat_x.shape != (B, F):
@@ -470,8 +481,7 @@ class SuperNet(nn.Module):
             segs = [Seg(dl.v, 0, dl.w, dl.w, 0), Seg(sl.v, 0, bs, sl.s * EMB, maxd)]
             if sl.g:
                 segs.append(Seg(sl.v, sl.s * EMB, bs, sl.g * EMB, maxd + maxs * EMB))
-        return eng.linear_ln(run.tape, segs, B, run.pv(self._final.weight), run.pv(self._final.bias), None, False, 1,
-                             w_full_support=self._fixed)
+        return segs
 
     def to(self, *args, **kwargs):                       # supernet.py:826-840 (CPU-embedding branch dropped)
         self._device_args = args

@@ -448,6 +448,46 @@ class OracleTrainer:
         return supernet_forward(self.params, self.cfg, choice, int_x, cat_x)
 
 
+def finetune_last_only(sd, cfg, choice, train_batches, eval_batches, lr: float, clip: float = 5.0,
+                       eps: float = 1e-2, min_lr: float = 1e-8):
+    """The EA's per-candidate recipe (eval_subnet_from_supernet.py:118-200 with
+    --finetune_whole_supernet 0; loop train_utils.py:262-300,386): only ``_final`` trains
+    (supernet.py:850-853), Adagrad(eps=1e-2) + clip 5.0, cosine schedule with warm-up = steps // 10
+    positioned by step(epoch=-1) (lr_schedule.py:98-159), one scheduler step after every batch but
+    the last.  Returns (per-step losses, per-step lrs, tuned final weight/bias, eval logits)."""
+    import math
+    steps = len(train_batches)
+    warm = steps // 10
+    params = {k: v.clone() for k, v in sd.items()}
+    fw = torch.nn.Parameter(params["_final.weight"])
+    fb = torch.nn.Parameter(params["_final.bias"])
+    params["_final.weight"], params["_final.bias"] = fw, fb
+    opt = torch.optim.Adagrad([fw, fb], lr=lr, eps=eps)
+
+    def lr_at(pos):                                  # lr_schedule.py:98-120 with base_lr == min_lr
+        if pos == -1:
+            return min_lr
+        if pos < warm:
+            return (lr - min_lr) * pos / warm + min_lr
+        return min_lr + (lr - min_lr) * (1 + math.cos(math.pi * (pos - warm) / (steps - warm))) / 2
+
+    losses, lrs = [], []
+    for b, (int_x, cat_x, y) in enumerate(train_batches):
+        cur = lr_at(b - 1)
+        for g in opt.param_groups:
+            g["lr"] = cur
+        opt.zero_grad()
+        loss = F.binary_cross_entropy_with_logits(supernet_forward(params, cfg, choice, int_x, cat_x), y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([fw, fb], clip)
+        opt.step()
+        losses.append(float(loss.detach()))
+        lrs.append(cur)
+    with torch.no_grad():
+        outs = [supernet_forward(params, cfg, choice, bx[0], bx[1]) for bx in eval_batches]
+    return losses, lrs, fw.detach(), fb.detach(), (torch.cat(outs) if outs else None)
+
+
 def loss_and_grads(sd, cfg, choice, int_x, cat_x, y):
     """Logits, BCE loss and dense grads of every tensor that takes part."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}

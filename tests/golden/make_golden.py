@@ -209,6 +209,115 @@ def step_fixture():
     save("train_steps", meta, arrays)
 
 
+def lr_fixture():
+    """lr sequences of the reference schedulers (utils/lr_schedule.py) as the EA fine-tune
+    and main_train.py drive them: construct, step(epoch=-1), then step() per batch."""
+    from nasrec.utils.lr_schedule import CosineAnnealingWarmupRestarts, ConstantWithWarmup
+    out = {}
+
+    def opt(lr):
+        return torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr)
+
+    for tag, kw, n in (("cosine_20_w2", dict(first_cycle_steps=20, warmup_steps=2, max_lr=0.04, min_lr=1e-8), 45),
+                       ("cosine_mult2_gamma", dict(first_cycle_steps=10, warmup_steps=3, max_lr=0.1, min_lr=0.001,
+                                                   cycle_mult=2.0, gamma=0.5), 40)):
+        o = opt(0.04)
+        s = CosineAnnealingWarmupRestarts(o, **kw)
+        seq = [o.param_groups[0]["lr"]]
+        s.step(epoch=-1); seq.append(o.param_groups[0]["lr"])
+        for _ in range(n):
+            s.step(); seq.append(o.param_groups[0]["lr"])
+        seeks = []
+        for e in (0, 1, 5, 19, 20, 33, 71):
+            s.step(epoch=e); seeks.append([e, o.param_groups[0]["lr"], s.cycle, s.step_in_cycle])
+        out[tag] = dict(kwargs=kw, opt_lr=0.04, seq=seq, seeks=seeks)
+    o = opt(0.12)
+    s = ConstantWithWarmup(o, num_warmup_steps=5)
+    seq = [o.param_groups[0]["lr"]]
+    for _ in range(12):
+        o.step(); s.step(); seq.append(o.param_groups[0]["lr"])
+    out["constant_w5"] = dict(opt_lr=0.12, seq=seq)
+    with open(os.path.join(HERE, "lr_schedules.json"), "w") as f:
+        json.dump(out, f)
+    print("wrote lr_schedules")
+
+
+def finetune_fixture():
+    """The EA's one-shot scoring recipe on the reference (eval_subnet_from_supernet.py:118-200,
+    train_utils.py:262-300,129-180): last-layer-only fine-tune with Adagrad + cosine warm-up
+    schedule + clip 5.0 on a pinned candidate, then log-loss on held-out batches."""
+    from nasrec.utils.lr_schedule import CosineAnnealingWarmupRestarts
+    meta = dict(cands=[])
+    arrays = {}
+    m, ne = build("criteo", "xlarge", True)
+    shapes = load_filled(m, seed=33)
+    base = {k: v.clone() for k, v in m.state_dict().items()}
+    tok = Tokenizer(7, ops_config_lib["xlarge"])
+    np.random.seed(77)
+    cands = [jsonable(tok.generate_random_choice()) for _ in range(2)]
+    steps, lr = 12, 0.04
+    for ci, ch in enumerate(cands):
+        m.load_state_dict(base, strict=True)
+        m.configure_choice(ch)
+        m.configure_path_sampling_strategy("fixed-path")
+        m.set_mode_to_finelune_last_only()
+        opt = torch.optim.Adagrad(m.parameters(), lr=lr, eps=1e-2)
+        sch = CosineAnnealingWarmupRestarts(opt, first_cycle_steps=steps, warmup_steps=steps // 10, max_lr=lr,
+                                            min_lr=1e-8)
+        sch.step(epoch=-1)
+        losses, lrs = [], []
+        m.train()
+        for b in range(steps):
+            int_x, cat_x, y = orc.synth_batch(16, 13, ne, seed=500 + b)
+            opt.zero_grad()
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(m(int_x, cat_x), y)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+            lrs.append(opt.param_groups[0]["lr"])
+            opt.step()
+            losses.append(float(loss))
+            if b < steps - 1:
+                sch.step()
+        m.eval()
+        outs, ys = [], []
+        with torch.no_grad():
+            for b in range(3):
+                int_x, cat_x, y = orc.synth_batch(32, 13, ne, seed=900 + b)
+                outs.append(m(int_x, cat_x)); ys.append(y)
+        z = torch.cat(outs); yy = torch.cat(ys)
+        test_loss = float(torch.nn.functional.binary_cross_entropy_with_logits(z, yy))
+        arrays["cand%d/final_weight" % ci] = m._final.weight.detach().numpy().copy()
+        arrays["cand%d/final_bias" % ci] = m._final.bias.detach().numpy().copy()
+        arrays["cand%d/eval_logits" % ci] = z.numpy().copy()
+        meta["cands"].append(dict(choice=ch, losses=losses, lrs=lrs, test_loss=test_loss))
+    meta.update(cfg=dict(ops="xlarge", use_layernorm=True, fixed=False, num_blocks=7), num_embeddings=ne,
+                state_seed=33, steps=steps, lr=lr, train_seeds=[500, 16], eval_seeds=[900, 32, 3],
+                shapes={k: list(v) for k, v in shapes.items()})
+    save("ea_finetune", meta, arrays)
+
+
+def tokenizer_fixture():
+    """Tokenizer goldens (searcher/tokenizer.py:158-265): token/hash of random candidates and a
+    chain of mutate_spec draws from numpy's global RNG."""
+    out = {}
+    for ops in ("xlarge", "autoctr"):
+        tok = Tokenizer(7, ops_config_lib[ops])
+        np.random.seed(4321)
+        cands = [tok.generate_random_choice() for _ in range(3)]
+        rec = dict(cands=jsonable(cands), tokens=[tok.tokenize(c).tolist() for c in cands],
+                   hashes=[tok.hash_token(tok.tokenize(c)) for c in cands])
+        np.random.seed(99)
+        chain, cur = [], cands[0]
+        for _ in range(16):
+            cur = tok.mutate_spec(cur)
+            chain.append(dict(choice=jsonable(cur), hash=tok.hash_token(tok.tokenize(cur))))
+        rec["mutations_seed99"] = chain
+        out[ops] = rec
+    with open(os.path.join(HERE, "tokenizer.json"), "w") as f:
+        json.dump(out, f)
+    print("wrote tokenizer")
+
+
 def sampler_fixture():
     """RNG-order goldens: what the reference draws from numpy's
     global legacy RNG, forward by forward."""
@@ -244,7 +353,7 @@ def sampler_fixture():
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps"]
+    which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps", "lr", "finetune", "tokenizer"]
     if "samplers" in which:
         sampler_fixture()
     if "fixed" in which:
@@ -257,3 +366,9 @@ if __name__ == "__main__":
         supernet_fixture("supernet_xlarge_kdd", "kdd", "xlarge", nchoices=2)
     if "steps" in which:
         step_fixture()
+    if "lr" in which:
+        lr_fixture()
+    if "finetune" in which:
+        finetune_fixture()
+    if "tokenizer" in which:
+        tokenizer_fixture()

@@ -1,0 +1,83 @@
+"""GPU: the EA's per-candidate recipe (last-layer fine-tune + scoring) through the CUDA path
+against the unmodified reference's recorded run (tests/golden/ea_finetune.*), and the
+in-process Searcher end to end on a resident supernet."""
+import numpy as np
+import pytest
+import torch
+
+from nasrec_b200 import SuperNet, ops_config_lib
+from nasrec_b200.search import Searcher, SubnetEvaluator, Tokenizer
+from oracle import nasrec_oracle as orc
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _resident(G):
+    cfg, ne = G["cfg"], G["num_embeddings"]
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib[cfg["ops"]], use_layernorm=True, num_embeddings=ne,
+                 sparse_input_size=len(ne), path_sampling_strategy="full-path").to("cuda")
+    m.materialize(13)
+    sd = orc.fill_state_dict({k: tuple(v) for k, v in G["shapes"].items()}, G["state_seed"])
+    m.load_state_dict(sd, strict=True)
+    return m, sd
+
+
+def _batches(G):
+    ne = G["num_embeddings"]
+    tr = [orc.synth_batch(G["train_seeds"][1], 13, ne, seed=G["train_seeds"][0] + b) for b in range(G["steps"])]
+    ev = [orc.synth_batch(G["eval_seeds"][1], 13, ne, seed=G["eval_seeds"][0] + b) for b in range(G["eval_seeds"][2])]
+    cu = lambda bs: [tuple(t.cuda() for t in b) for b in bs]
+    return cu(tr), cu(ev)
+
+
+@pytest.mark.parametrize("trunk_samples", [8192, 40, 1])
+def test_finetune_and_score_matches_reference_golden(trunk_samples):
+    """trunk_samples only regroups the frozen trunk's launches (all 12 batches at once, 2 at a
+    time, one by one): the optimizer walk and its result must not change."""
+    G, A = load_golden("ea_finetune")
+    m, sd = _resident(G)
+    tr, ev = _batches(G)
+    ev_obj = SubnetEvaluator(m)
+    w0 = m._final.weight.detach().clone()
+    for ci, c in enumerate(G["cands"]):
+        r = ev_obj.finetune_and_score(c["choice"], tr, ev, lr=G["lr"], trunk_samples=trunk_samples, restore=False)
+        assert np.abs(np.asarray(r["train_loss"]) - np.asarray(c["losses"])).max() < 2e-5
+        assert np.abs(r["final_weight"].cpu().numpy() - A["cand%d/final_weight" % ci]).max() < 1e-5
+        assert np.abs(r["final_bias"].cpu().numpy() - A["cand%d/final_bias" % ci]).max() < 1e-5
+        assert abs(r["test_loss"] - c["test_loss"]) < 1e-5
+        z = torch.cat([ev_obj.logits(c["choice"], b[0], b[1]).reshape(-1) for b in ev]).cpu().numpy()
+        assert np.abs(z - A["cand%d/eval_logits" % ci].reshape(-1)).max() < 3e-5
+        with torch.no_grad():                      # next candidate starts from the checkpoint again
+            m._final.weight.copy_(sd["_final.weight"].cuda())
+            m._final.bias.copy_(sd["_final.bias"].cuda())
+    # restore=True leaves the resident supernet untouched
+    ev_obj.finetune_and_score(G["cands"][0]["choice"], tr, ev, lr=G["lr"])
+    assert torch.equal(m._final.weight, w0)
+    # nothing but _final may have moved
+    for k, v in m.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+
+
+def test_searcher_end_to_end_on_gpu():
+    G, _ = load_golden("ea_finetune")
+    m, sd = _resident(G)
+    tr, ev = _batches(G)
+    tok = Tokenizer(7, ops_config_lib["xlarge"])
+    s = Searcher(SubnetEvaluator(m), tok, tr[:4], ev, lr=G["lr"])
+    np.random.seed(11)
+    hist = s.regularized_evolution_from_supernet(n_generations=2, n_childs=3, init_population=5, sample_size=3,
+                                                 criterion="test_loss", top_k=1)
+    assert len(hist) == 2 and len(s.all_results) == 5
+    for r in hist + list(s.all_results):
+        assert set(r) == {"choice", "test_acc", "test_auroc", "test_loss", "hash_token"}
+        assert np.isfinite(r["test_loss"]) and 0.0 <= r["test_auroc"] <= 1.0
+        # the record is reproducible from its choice alone: oracle recipe on the same batches
+    r = hist[0]
+    host = lambda bs: [tuple(t.cpu() for t in b) for b in bs]
+    _, _, _, _, z = orc.finetune_last_only(sd, G["cfg"], r["choice"], host(tr[:4]), host(ev), G["lr"])
+    ys = torch.cat([b[2] for b in host(ev)])
+    acc, auc, loss = orc.binary_metrics(z.numpy(), ys.numpy())
+    assert abs(loss - r["test_loss"]) < 1e-5 and abs(auc - r["test_auroc"]) < 1e-4
+    for k, v in m.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k

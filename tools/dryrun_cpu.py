@@ -63,6 +63,20 @@ smeta, _ = load_golden("samplers")
 meta, _ = load_golden("supernet_xlarge_criteo")
 for ch in smeta["ea_candidates"]["xlarge"]:
     run_model(meta["cfg"], meta["num_embeddings"], 13, meta["shapes"], ch)
+import nasrec_b200.search as srch
+G, _ = load_golden("ea_finetune")
+m = sn.SuperNet(num_blocks=7, ops_config=sn.ops_config_lib["xlarge"], use_layernorm=True,
+                num_embeddings=G["num_embeddings"], sparse_input_size=26, path_sampling_strategy="full-path")
+m.materialize(13)
+tr = [orc.synth_batch(16, 13, G["num_embeddings"], seed=500 + b) for b in range(5)]
+ev = [orc.synth_batch(32, 13, G["num_embeddings"], seed=900 + b) for b in range(2)]
+srch.binary_metrics_device = lambda z, y: (0.5, 0.5, 0.7)
+se = srch.SubnetEvaluator(m)
+for ts in (8192, 40, 1):
+    r = se.finetune_and_score(G["cands"][0]["choice"], tr, ev, lr=0.04, trunk_samples=ts)
+S = srch.Searcher(se, srch.Tokenizer(7, sn.ops_config_lib["xlarge"]), tr, ev)
+np.random.seed(3)
+S.regularized_evolution_from_supernet(n_generations=2, n_childs=2, init_population=4, sample_size=2, top_k=1)
 print("ea ok")
 # module-level standalone
 for ln, fixed in ((True, False), (False, True)):
