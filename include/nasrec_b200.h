@@ -237,9 +237,12 @@ int nasrec_binary_metrics(const float* logits, const float* y, int64_t n, void* 
 /* f2  raw batch -> model inputs (data_pipes.py:135-175, VanillaTransform{Criteo,Avazu,KDD}):
  * int_x[b,c] = log(max(0, dense_raw[b,c]) + 1);
  * cat_x[b,f] = (int(hex[b,f], 16) if non-empty else -1).fmod(num_rows[f] - 1) + 1.
- * hex: [B,F,width] bytes, each field NUL-padded hex digits (width <= 15); a non-hex byte sets
- * err_flag.  num_rows: F device int64.  For Avazu pass nd = 0 (its dense input is all zeros). */
-int nasrec_input_transform(const float* dense_raw, int nd, const uint8_t* hex, int width, int F,
+ * dense_raw[b,c] sits at dense_raw[b*dense_stride_b + c*dense_stride_c] (row- or column-major raw
+ * columns); field (b,f) is `width` bytes at hex + b*hex_stride_b + f*hex_stride_f, NUL-padded hex
+ * digits of either case (width <= 15); a non-hex byte sets err_flag.  num_rows: F device int64.
+ * Outputs are contiguous [B,nd] float and [B,F] int64.  For Avazu pass nd = 0 (all-zero dense input). */
+int nasrec_input_transform(const float* dense_raw, int64_t dense_stride_b, int64_t dense_stride_c, int nd,
+                           const uint8_t* hex, int64_t hex_stride_b, int64_t hex_stride_f, int width, int F,
                            const int64_t* num_rows, int64_t B, float* int_x, int64_t* cat_x, int* err_flag,
                            void* stream);
 /* (grads/sizes/w/state below are HOST arrays of device pointers / element counts.)

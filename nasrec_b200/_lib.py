@@ -61,11 +61,14 @@ _SIGS = {
     "nasrec_bce_fwd_bwd": ([_f, _f, _i, _fl, _f, _f, _f], 1),
     "nasrec_grad_norm_clip": ([_f, _f, _i, _f, _i, _fl, _f, _f, _f], 2),
     "nasrec_adagrad_multi": ([_f, _f, _f, _f, _i, _fl, _fl, _f, _f], 1),
+    "nasrec_binary_metrics": ([_f, _f, _l, _f, _l, _f, _f], 6),     # prepare, sort (3 passes), scan, pairs, final
+    "nasrec_input_transform": ([_f, _l, _l, _i, _f, _l, _l, _i, _i, _f, _l, _f, _f, _f, _f], 1),
 }
 _SIGS_I64 = {
     "nasrec_sproj_wgrad_ws_floats": [_i, _l, _i],
     "nasrec_attn_bwd_ws_floats": [_i],
     "nasrec_sumsq_ws_floats": [_f, _i],
+    "nasrec_binary_metrics_ws_bytes": [_l],
 }
 EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace"] + list(_SIGS) + list(_SIGS_I64)
 

@@ -116,8 +116,9 @@ __device__ __forceinline__ int hex_digit(uint8_t c) {
     return -1;
 }
 
-__global__ void __launch_bounds__(256) input_transform_kernel(const float* __restrict__ dense_raw, int nd,
-                                                              const uint8_t* __restrict__ hex, int width, int F,
+__global__ void __launch_bounds__(256) input_transform_kernel(const float* __restrict__ dense_raw, long long dsb,
+                                                              long long dsc, int nd, const uint8_t* __restrict__ hex,
+                                                              long long hsb, long long hsf, int width, int F,
                                                               const int64_t* __restrict__ num_rows, long long B,
                                                               float* __restrict__ int_x, int64_t* __restrict__ cat_x,
                                                               int* __restrict__ err_flag) {
@@ -126,11 +127,11 @@ __global__ void __launch_bounds__(256) input_transform_kernel(const float* __res
         const long long b = t / per;
         const int c = (int)(t - b * per);
         if (c < nd) {                                      // log(max(0, x) + 1), rounded like the reference's two ops
-            const float x = dense_raw[b * nd + c];
+            const float x = dense_raw[b * dsb + c * dsc];
             int_x[b * nd + c] = logf(fmaxf(x, 0.f) + 1.f);
         } else {
             const int f = c - nd;
-            const uint8_t* s = hex + (b * F + f) * (long long)width;
+            const uint8_t* s = hex + b * hsb + f * hsf;
             long long v = 0;
             int len = 0;
             bool bad = false;
@@ -183,15 +184,17 @@ extern "C" int nasrec_binary_metrics(const float* logits, const float* y, int64_
     return nasrec_launch_status();
 }
 
-extern "C" int nasrec_input_transform(const float* dense_raw, int nd, const uint8_t* hex, int width, int F,
+extern "C" int nasrec_input_transform(const float* dense_raw, int64_t dense_stride_b, int64_t dense_stride_c, int nd,
+                                      const uint8_t* hex, int64_t hex_stride_b, int64_t hex_stride_f, int width, int F,
                                       const int64_t* num_rows, int64_t B, float* int_x, int64_t* cat_x,
                                       int* err_flag, void* stream) {
     CHECK_ARG(B >= 0 && nd >= 0 && F >= 0 && width >= 1 && width <= 15);
+    if (B == 0 || nd + F == 0) return 0;
     CHECK_ARG((nd == 0 || (dense_raw && int_x)) && (F == 0 || (hex && num_rows && cat_x)));
-    if (B == 0 || nd + F == 0) return NASREC_OK;
     const long long total = B * ((long long)nd + F);
     const int blocks = (int)((total + 255) / 256 < 148LL * 8 ? (total + 255) / 256 : 148 * 8);
-    input_transform_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dense_raw, nd, hex, width, F, num_rows, B, int_x, cat_x,
+    input_transform_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dense_raw, dense_stride_b, dense_stride_c, nd, hex, hex_stride_b,
+                                                                  hex_stride_f, width, F, num_rows, B, int_x, cat_x,
                                                                   err_flag);
     return nasrec_launch_status();
 }

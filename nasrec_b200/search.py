@@ -126,31 +126,29 @@ class Tokenizer:
         return out
 
 
+_metrics_ws: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
 def binary_metrics_device(logits: torch.Tensor, y: torch.Tensor) -> Tuple[float, float, float]:
-    """(accuracy@0.5, ROC-AUC, log-loss) over concatenated predictions, as
-    train_utils.py:158-178.  Log-loss comes from the fused BCE kernel; AUC is the rank
-    statistic with average ranks for ties (== sklearn.metrics.roc_auc_score)."""
-    z = logits.reshape(-1).contiguous()
-    t = y.reshape(-1).contiguous()
-    loss, _ = eng.bce_with_logits(z, t, want_grad=False)
+    """(accuracy@0.5, ROC-AUC, log-loss) over concatenated predictions, as train_utils.py:158-178,
+    computed by ``nasrec_binary_metrics`` (device radix sort on the fp32 sigmoid outputs + exact
+    integer Mann-Whitney count with ties at 1/2 == sklearn.metrics.roc_auc_score); only three
+    doubles cross to the host."""
+    from . import _lib
+    z = logits.reshape(-1).contiguous().float()
+    t = y.reshape(-1).contiguous().float()
     n = z.numel()
-    order = torch.argsort(z, stable=True)
-    zs = z[order]
-    ts = t[order]
-    # average ranks of tied groups
-    new = torch.ones(n, dtype=torch.bool, device=z.device)
-    new[1:] = zs[1:] != zs[:-1]
-    gid = torch.cumsum(new.to(torch.int64), 0) - 1
-    pos = torch.arange(1, n + 1, dtype=torch.float64, device=z.device)
-    ng = int(gid[-1].item()) + 1
-    gsum = torch.zeros(ng, dtype=torch.float64, device=z.device).index_add_(0, gid, pos)
-    gcnt = torch.zeros(ng, dtype=torch.float64, device=z.device).index_add_(0, gid, torch.ones_like(pos))
-    ranks = (gsum / gcnt)[gid]
-    npos = ts.double().sum()
-    nneg = n - npos
-    auc = (ranks[ts > 0.5].sum() - npos * (npos + 1) / 2) / (npos * nneg)
-    acc = ((z > 0).float() == t).float().mean()      # sigmoid(z) > 0.5  <=>  z > 0
-    return float(acc.item()), float(auc.item()), float(loss.item())
+    if t.numel() != n or n == 0:
+        raise ValueError("logits and labels must be non-empty and of equal length")
+    need = _lib.query("nasrec_binary_metrics_ws_bytes", n)
+    key = (z.device.index or 0, 0)
+    ws = _metrics_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _metrics_ws[key] = torch.empty(int(need * 1.25), dtype=torch.uint8, device=z.device)
+    out = torch.empty(3, dtype=torch.float64, device=z.device)
+    _lib.call("nasrec_binary_metrics", z.data_ptr(), t.data_ptr(), n, ws.data_ptr(), ws.numel(), out.data_ptr())
+    acc, auc, loss = out.tolist()
+    return float(acc), float(auc), float(loss)
 
 
 class SubnetEvaluator:

@@ -498,6 +498,23 @@ def loss_and_grads(sd, cfg, choice, int_x, cat_x, y):
     return logits.detach(), loss.detach(), {n: g for n, g in zip(names, grads) if g is not None}
 
 
+def input_transform(ints: np.ndarray, hex_cols: Sequence[Sequence[str]], num_embeddings: Sequence[int],
+                    zero_dense: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """VanillaTransform{Criteo,KDD,Avazu} (data_pipes.py:135-252) on raw columns:
+    dense log(max(0,x)+1) in fp32 (Avazu: zeros); id = int(v,16) (or -1 when empty) .fmod(N_f-1) + 1."""
+    x = np.asarray(ints, dtype=np.int64)
+    if zero_dense:
+        int_x = np.zeros(x.shape, dtype=np.float32)
+    else:
+        int_x = torch.log(torch.from_numpy(np.maximum(x, 0) + 1)).numpy().astype(np.float32)
+    B = len(hex_cols[0]) if len(hex_cols) else x.shape[0]
+    cat_x = np.zeros((B, len(hex_cols)), dtype=np.int64)
+    for f, col in enumerate(hex_cols):
+        raw = np.asarray([int(v, 16) if v else -1 for v in col], dtype=np.int64)
+        cat_x[:, f] = np.fmod(raw, num_embeddings[f] - 1) + 1
+    return int_x, cat_x
+
+
 def binary_metrics(logits: np.ndarray, y: np.ndarray) -> Tuple[float, float, float]:
     """accuracy@0.5 on sigmoid, ROC-AUC (rank statistic with average ranks for
     ties == sklearn.metrics.roc_auc_score), BCE log-loss.  train_utils.py:158-178."""

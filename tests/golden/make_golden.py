@@ -318,6 +318,47 @@ def tokenizer_fixture():
     print("wrote tokenizer")
 
 
+def transform_fixture():
+    """Raw batch -> (int_x, cat_x, y) through the reference's VanillaTransform* (data_pipes.py:135-252)
+    on synthetic raw rows: negative / zero / large ints, hex ids of 1-8 digits, upper case, and
+    missing fields (empty string -> row 0)."""
+    from nasrec.utils import data_pipes as dp
+    from nasrec.utils.config import NUM_EMBEDDINGS_CRITEO, NUM_EMBEDDINGS_AVAZU, NUM_EMBEDDINGS_KDD
+    out = {}
+    rng = np.random.RandomState(2024)
+    for ds, fn, nd, F, ne in (("criteo", dp.VanillaTransformCriteo, 13, 26, NUM_EMBEDDINGS_CRITEO),
+                              ("avazu", dp.VanillaTransformAvazu, 1, 23, NUM_EMBEDDINGS_AVAZU),
+                              ("kdd", dp.VanillaTransformKDD, 3, 10, NUM_EMBEDDINGS_KDD)):
+        B = 48
+        ints = rng.randint(-3, 60, size=(B, nd)).astype(np.int64)
+        ints[rng.rand(B, nd) < 0.1] = rng.randint(1 << 20, 1 << 23)
+        hexs = []
+        for f in range(F):
+            col = []
+            for b in range(B):
+                u = rng.rand()
+                if u < 0.12:
+                    col.append("")
+                else:
+                    digits = int(rng.randint(1, 9))
+                    v = "%x" % int(rng.randint(0, 16 ** digits, dtype=np.int64))
+                    col.append(v.upper() if u > 0.9 else v)
+            hexs.append(col)
+        label = rng.randint(0, 2, size=B).astype(np.int64)
+        batch = {"label": torch.tensor(label)}
+        for c in range(nd):
+            batch["int_%d" % c] = torch.tensor(ints[:, c])
+        for f in range(F):
+            batch["cat_%d" % f] = list(hexs[f])
+        int_x, cat_x, y = fn(batch)
+        out[ds] = dict(nd=nd, F=F, num_embeddings=list(ne), ints=ints.tolist(), hex=hexs, label=label.tolist(),
+                       int_x=int_x.numpy().astype(np.float32).tolist(), cat_x=cat_x.numpy().tolist(),
+                       y=y.numpy().tolist(), int_dtype=str(int_x.dtype), cat_dtype=str(cat_x.dtype))
+    with open(os.path.join(HERE, "input_transform.json"), "w") as f:
+        json.dump(out, f)
+    print("wrote input_transform")
+
+
 def sampler_fixture():
     """RNG-order goldens: what the reference draws from numpy's
     global legacy RNG, forward by forward."""
@@ -353,7 +394,7 @@ def sampler_fixture():
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps", "lr", "finetune", "tokenizer"]
+    which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps", "lr", "finetune", "tokenizer", "transform"]
     if "samplers" in which:
         sampler_fixture()
     if "fixed" in which:
@@ -372,3 +413,5 @@ if __name__ == "__main__":
         finetune_fixture()
     if "tokenizer" in which:
         tokenizer_fixture()
+    if "transform" in which:
+        transform_fixture()

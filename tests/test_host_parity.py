@@ -11,6 +11,7 @@ import torch
 
 from nasrec_b200 import SuperNet, ops_config_lib, _lib
 from nasrec_b200.supernet.supernet import _ints
+from oracle import nasrec_oracle as orc
 from tests.helpers import load_golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -171,3 +172,44 @@ def test_c_abi_library_exports_every_declared_symbol():
     sm = ctypes.c_int(0)
     lib.nasrec_version.argtypes = [ctypes.POINTER(ctypes.c_int)]
     assert lib.nasrec_version(ctypes.byref(sm)) >= 100 and sm.value == 100
+
+
+def test_checkpoint_bridge_round_trip(tmp_path):
+    """Reference-format checkpoint (io_utils.py:59-79): a file written the reference's way loads
+    strict=True; a file written here has the same top-level schema and tensors."""
+    import pickle
+    from nasrec_b200 import SuperNet, ops_config_lib
+    from nasrec_b200.utils import io_utils
+    meta, _ = load_golden("supernet_autoctr_criteo")
+    ne = meta["num_embeddings"]
+    sd = orc.fill_state_dict({k: tuple(v) for k, v in meta["shapes"].items()}, 3)
+    ref_style = tmp_path / "supernet_checkpoint.pt"
+    with open(ref_style, "wb") as fh:                         # what the reference's save_model_checkpoint writes
+        torch.save({"model_state_dict": sd}, fh)
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib["autoctr"], use_layernorm=True, num_embeddings=ne,
+                 sparse_input_size=len(ne))
+    m.materialize(meta["nd"])
+    ckpt = io_utils.load_model_checkpoint(str(ref_style))
+    m.load_state_dict(ckpt["model_state_dict"], strict=True)
+    out = tmp_path / "ours.pt"
+    io_utils.save_model_checkpoint(m, str(out))
+    back = torch.load(out, map_location="cpu")
+    assert list(back) == ["model_state_dict"] and list(back["model_state_dict"]) == list(sd)
+    assert all(torch.equal(back["model_state_dict"][k], sd[k]) for k in sd)
+    # fused-trainer accumulators travel in torch.optim.Adagrad's own layout
+    from nasrec_b200.utils.train_utils import FusedTrainer
+    tr = FusedTrainer(m, lr=0.12)
+    p0 = next(m.parameters())
+    tr.state[id(p0)] = torch.full_like(p0, 0.25)
+    osd = io_utils.adagrad_state_dict(tr, m, step=7)
+    opt = torch.optim.Adagrad(m.parameters(), lr=0.12, eps=1e-2)
+    opt.load_state_dict(osd)                                  # accepted by the stock optimizer
+    assert torch.equal(opt.state[p0]["sum"], torch.full_like(p0, 0.25)) and float(opt.state[p0]["step"]) == 7.0
+    tr2 = FusedTrainer(m, lr=0.12)
+    io_utils.load_adagrad_state(tr2, m, opt.state_dict())
+    assert torch.equal(tr2.state[id(p0)], torch.full_like(p0, 0.25))
+    rec = [{"choice": {"macro": [], "micro": []}, "test_acc": 0.7, "test_auroc": 0.8, "test_loss": 0.45, "hash_token": "01"}]
+    io_utils.dump_pickle_data(str(tmp_path / "results.pickle"), rec)
+    with open(tmp_path / "results.pickle", "rb") as fh:
+        assert pickle.load(fh) == rec
+    assert io_utils.load_pickle_data(str(tmp_path / "results.pickle")) == rec

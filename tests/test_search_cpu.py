@@ -196,3 +196,27 @@ def test_searcher_sharded_over_two_ranks_equals_single_rank():
         assert h == [r["hash_token"] for r in hist]
         assert calls < ev.calls                                       # each rank scored only its shard
     assert sum(g[3] for g in got) == ev.calls
+
+
+# ------------------------------------------------------------------ input transform
+@pytest.mark.parametrize("ds", ["criteo", "avazu", "kdd"])
+def test_oracle_input_transform_matches_reference_golden(ds):
+    G = load_golden("input_transform")[0][ds]
+    int_x, cat_x = orc.input_transform(np.asarray(G["ints"]), G["hex"], G["num_embeddings"], zero_dense=(ds == "avazu"))
+    assert np.array_equal(cat_x, np.asarray(G["cat_x"]))                     # bit-exact indices
+    assert np.array_equal(int_x, np.asarray(G["int_x"], dtype=np.float32))
+    missing = np.asarray([[v == "" for v in col] for col in G["hex"]]).T
+    assert (cat_x[missing] == 0).all() and (cat_x[~missing] >= 1).all()     # missing -> row 0, ids in [1, N-1]
+    assert (cat_x < np.asarray(G["num_embeddings"])[None, :]).all()
+
+
+def test_pack_hex_columns_layout_and_limits():
+    from nasrec_b200.utils.data_pipes import pack_hex_columns
+    p = pack_hex_columns([["a", "", "0fF3"], ["12345678", "9", ""]])
+    assert p.shape == (2, 3, 8) and p.dtype == np.uint8
+    assert bytes(p[0, 0]) == b"a" + b"\0" * 7 and bytes(p[0, 1]) == b"\0" * 8 and bytes(p[1, 0]) == b"12345678"
+    assert pack_hex_columns([["", ""]]).shape == (1, 2, 1)
+    with pytest.raises(ValueError):
+        pack_hex_columns([["0123456789abcdef"]])                              # 16 digits do not fit int64
+    with pytest.raises(ValueError):
+        pack_hex_columns([["a"], ["b", "c"]])
