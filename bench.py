@@ -515,7 +515,44 @@ def extra_ea_eval(torch, _lib, dev, n_cand=16, n_batches=8, B=8192):
         out["ea_subnets_per_sec_%dx%d_%s" % (n_batches, B, tag)] = n_cand / sec
         out["ea_eval_samples_per_sec_%s" % tag] = n_cand * n_batches * B / sec
     out["ea_mean_auc"] = float(np.mean([r["test_auroc"] for r in res]))
-    del m, ev, batches
+    # the reference's full per-candidate recipe: 500 last-layer fine-tune steps of B=512 under the cosine
+    # schedule, then scoring (here on the same n_batches x B evaluation set)
+    m.requires_grad_(True)
+    tr = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in synth_pool(500, 512, 13, ne, 12)]
+    ev.finetune_and_score(cands[0], tr[:32], batches[:1])
+    torch.cuda.synchronize()
+    e0.record()
+    for ch in cands[2:6]:
+        r = ev.finetune_and_score(ch, tr, batches)
+    e1.record()
+    torch.cuda.synchronize()
+    out["ea_recipe_subnets_per_sec_ft500x512_eval%dx%d" % (n_batches, B)] = 4 / (e0.elapsed_time(e1) * 1e-3)
+    out["ea_recipe_last_train_loss"] = r["train_loss"][-1]
+    # raw-batch transform (hex parse + hash + log) and device metrics, per call
+    from nasrec_b200.utils.data_pipes import InputTransform
+    from nasrec_b200.search import binary_metrics_device
+    rng = np.random.RandomState(3)
+    Bt = 8192
+    hexs = [["%x" % v for v in rng.randint(0, 1 << 32, size=Bt, dtype=np.int64)] for _ in range(26)]
+    ints = [rng.randint(0, 1000, size=Bt) for _ in range(13)]
+    tf = InputTransform(ne, 13)
+    tf.transform_columns(ints, hexs)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        tf.transform_columns(ints, hexs)
+    torch.cuda.synchronize()
+    out["input_transform_rows_per_sec_host_strings_to_device_B8192"] = 5 * Bt / (time.perf_counter() - t0)
+    z = torch.randn(150 * 8192, device=dev)
+    yy = (torch.rand(150 * 8192, device=dev) < 0.3).float()
+    binary_metrics_device(z, yy)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        binary_metrics_device(z, yy)
+    e1.record()
+    torch.cuda.synchronize()
+    out["binary_metrics_ms_1228800_preds"] = e0.elapsed_time(e1) / 5
+    del m, ev, batches, tr
     torch.cuda.empty_cache()
     return out
 

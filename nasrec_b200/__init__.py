@@ -16,7 +16,8 @@ def install_as_nasrec():
     import sys
     from . import supernet as _sn, utils as _ut
     from .supernet import modules as _m, supernet as _s, utils as _u
-    from .utils import config as _c
+    from .utils import config as _c, data_pipes as _dp, io_utils as _io, lr_schedule as _lr, train_utils as _tu
+    from . import search as _se
     sys.modules.setdefault("nasrec", sys.modules[__name__])
     sys.modules.setdefault("nasrec.supernet", _sn)
     sys.modules.setdefault("nasrec.supernet.supernet", _s)
@@ -24,3 +25,10 @@ def install_as_nasrec():
     sys.modules.setdefault("nasrec.supernet.utils", _u)
     sys.modules.setdefault("nasrec.utils", _ut)
     sys.modules.setdefault("nasrec.utils.config", _c)
+    sys.modules.setdefault("nasrec.utils.lr_schedule", _lr)
+    sys.modules.setdefault("nasrec.utils.io_utils", _io)
+    sys.modules.setdefault("nasrec.utils.train_utils", _tu)
+    sys.modules.setdefault("nasrec.utils.data_pipes", _dp)       # transform half only (VanillaTransform*)
+    sys.modules.setdefault("nasrec.searcher", _se)
+    sys.modules.setdefault("nasrec.searcher.tokenizer", _se)     # Tokenizer
+    sys.modules.setdefault("nasrec.searcher.searcher", _se)      # Searcher (in-process, GPU-resident)

@@ -94,6 +94,101 @@ def reference_style_step(model, optimizer, loss_fn, int_x, cat_x, y, grad_clip_v
     return res, loss
 
 
+def test_one_epoch(model, test_loader, loss_fn=None, gpu=None, max_steps: int = -1, use_amp: bool = False):
+    """train_utils.py:129-178: forward over the evaluation loader, then accuracy / ROC-AUC /
+    log-loss over the concatenated predictions -- computed on the device
+    (``nasrec_binary_metrics``), so only three scalars reach the host.  ``loss_fn`` is accepted
+    for signature compatibility; the metric is BCE-with-logits, the only loss the reference wires."""
+    from ..search import binary_metrics_device
+    assert not use_amp, "mixed precision is not part of the B200 path (SURVEY 0.5)"
+    was_training = model.training
+    model.eval()
+    preds, labels = [], []
+    with torch.no_grad():
+        for counter, (int_x, cat_x, y) in enumerate(test_loader, start=1):
+            preds.append(model(int_x.to(gpu, non_blocking=True), cat_x.to(gpu, non_blocking=True)).reshape(-1))
+            labels.append(y.to(gpu, non_blocking=True).reshape(-1))
+            if max_steps != -1 and counter >= max_steps:
+                break
+    model.train(was_training)
+    return binary_metrics_device(torch.cat(preds), torch.cat(labels))
+
+
+def train_and_test_one_epoch(model, epoch: int, optimizer, lr_scheduler, train_loader, test_loader, loss_fn,
+                             l2_loss_fn, train_batch_size: int, gpu, display_interval: int = 100,
+                             test_interval: int = 2000, max_train_steps: int = -1, max_eval_steps: int = -1,
+                             test_only_at_last_step: bool = False, grad_clip_value: Optional[float] = None,
+                             tb_writer=None, use_amp: bool = False):
+    """train_utils.py:181-390 with the same arguments and ``logs`` dictionary.
+
+    ``optimizer`` is either a torch optimizer -- the reference's own step body on the CUDA model
+    (``reference_style_step`` + the L2 term) -- or a ``FusedTrainer``, which replaces that body by
+    the fused step when ``l2_loss_fn`` is None / weight decay is 0 (the shipped recipes)."""
+    from ..search import binary_metrics_device
+    assert not use_amp, "mixed precision is not part of the B200 path (SURVEY 0.5)"
+    logs = {k: [] for k in ("train_loss", "train_AUROC", "train_Accuracy", "test_loss", "test_AUROC", "test_Accuracy",
+                            "epoch", "iters")}
+    fused = isinstance(optimizer, FusedTrainer)
+    model.train()
+    for batch_num, (int_x, cat_x, y) in enumerate(train_loader):
+        int_x, cat_x, y = (t.to(gpu, non_blocking=True) for t in (int_x, cat_x, y))
+        full = len(y) == train_batch_size                       # the ragged last batch is only evaluated
+        if fused:
+            lr = None
+            if lr_scheduler is not None:
+                lr = lr_scheduler.get_last_lr()[0] if hasattr(lr_scheduler, "get_last_lr") else lr_scheduler.lr()
+            if full:
+                res, loss = optimizer.step(int_x, cat_x, y, lr=lr)
+            else:
+                with torch.no_grad():
+                    res = model(int_x, cat_x)
+                    loss = torch.nn.functional.binary_cross_entropy_with_logits(res, y)
+            l2_loss = torch.zeros((), device=res.device)
+        else:
+            optimizer.zero_grad()
+            res = model(int_x, cat_x)
+            loss = loss_fn(res, y)
+            l2_loss = l2_loss_fn(model) if l2_loss_fn is not None else torch.zeros((), device=res.device)
+            if full:
+                (loss + l2_loss).backward()
+                if grad_clip_value is not None:
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), grad_clip_value)
+                optimizer.step()
+        last = batch_num == max_train_steps - 1
+        if batch_num % display_interval == 0 or last:
+            if bool(torch.isnan(loss)):                          # train_utils.py:294-300 (diverged KDD runs)
+                logs["test_loss"].append(999.99)
+                logs["test_AUROC"].append(-1)
+                logs["test_Accuracy"].append(-1)
+                return logs
+            yv = y.detach().reshape(-1)
+            if bool((yv == yv[0]).all()):                        # sklearn raises on one-class batches
+                train_acc = float(((res.detach().reshape(-1) > 0).float() == yv).float().mean())
+                train_auroc = 1.0
+            else:
+                train_acc, train_auroc, _ = binary_metrics_device(res.detach(), yv)
+            logs["train_loss"].append(float(loss))
+            logs["train_AUROC"].append(train_auroc)
+            logs["train_Accuracy"].append(train_acc)
+            logs["epoch"].append(epoch)
+            logs["iters"].append(batch_num)
+            if tb_writer is not None:
+                tb_writer.add_scalar("Loss/train/epoch{}".format(epoch), float(loss), batch_num * train_batch_size)
+        if (batch_num % test_interval == 0 or last) and ((not test_only_at_last_step) or last):
+            test_acc, test_auroc, test_loss = test_one_epoch(model, test_loader, loss_fn, gpu, max_steps=max_eval_steps)
+            logs["test_loss"].append(test_loss)
+            logs["test_AUROC"].append(test_auroc)
+            logs["test_Accuracy"].append(test_acc)
+            if tb_writer is not None:
+                tb_writer.add_scalar("Loss/test/epoch{}".format(epoch), test_loss, batch_num * train_batch_size)
+            model.train()
+        if max_train_steps != -1 and batch_num >= max_train_steps - 1:
+            return logs
+        if lr_scheduler is not None:
+            lr_scheduler.step() if not hasattr(lr_scheduler, "advance") else lr_scheduler.advance()
+    return logs
+
+
 class FusedTrainer:
     """Fused step for SuperNet training (weight sharing or fixed), wd == 0."""
 

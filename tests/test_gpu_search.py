@@ -81,3 +81,32 @@ def test_searcher_end_to_end_on_gpu():
     assert abs(loss - r["test_loss"]) < 1e-5 and abs(auc - r["test_auroc"]) < 1e-4
     for k, v in m.state_dict().items():
         assert torch.equal(v.cpu(), sd[k]), k
+
+
+def test_reference_training_loop_drop_in_matches_golden():
+    """The reference's own per-candidate flow (eval_subnet_from_supernet.py:118-200) written against
+    the mirrored API -- stock torch Adagrad, the mirrored cosine scheduler and
+    train_and_test_one_epoch -- reproduces the run recorded from the unmodified reference."""
+    from nasrec_b200.utils import train_utils as tu
+    from nasrec_b200.utils.lr_schedule import CosineAnnealingWarmupRestarts
+    G, A = load_golden("ea_finetune")
+    m, sd = _resident(G)
+    ne, steps, lr = G["num_embeddings"], G["steps"], G["lr"]
+    tr = [orc.synth_batch(G["train_seeds"][1], 13, ne, seed=G["train_seeds"][0] + b) for b in range(steps)]
+    ev = [orc.synth_batch(G["eval_seeds"][1], 13, ne, seed=G["eval_seeds"][0] + b) for b in range(G["eval_seeds"][2])]
+    c = G["cands"][1]
+    m.configure_choice(c["choice"])
+    m.configure_path_sampling_strategy("fixed-path")
+    m.set_mode_to_finelune_last_only()
+    opt = torch.optim.Adagrad(m.parameters(), lr=lr, eps=1e-2)
+    sch = CosineAnnealingWarmupRestarts(opt, first_cycle_steps=steps, warmup_steps=steps // 10, max_lr=lr, min_lr=1e-8)
+    sch.step(epoch=-1)
+    logs = tu.train_and_test_one_epoch(m, 0, opt, sch, tr, ev, torch.nn.BCEWithLogitsLoss(),
+                                       lambda mod: tu.get_l2_loss(mod, 0, None, gpu="cuda"), G["train_seeds"][1], "cuda",
+                                       display_interval=1, max_train_steps=steps, max_eval_steps=len(ev),
+                                       test_interval=max(2, steps), test_only_at_last_step=True, grad_clip_value=5.0)
+    assert np.abs(np.asarray(logs["train_loss"]) - np.asarray(c["losses"])).max() < 2e-5
+    assert logs["iters"] == list(range(steps)) and len(logs["test_loss"]) == 1
+    assert abs(logs["test_loss"][0] - c["test_loss"]) < 1e-5
+    assert np.abs(m._final.weight.detach().cpu().numpy() - A["cand1/final_weight"]).max() < 1e-5
+    assert 0.0 <= logs["test_AUROC"][0] <= 1.0 and 0.0 <= logs["test_Accuracy"][0] <= 1.0
