@@ -266,7 +266,13 @@ def run_ours(args):
                      supernet_training_steps=0).to(dev)
     model.materialize(13)
     model.apply(init_weights)
-    trainer = DataParallelTrainer(model, lr=LR) if world > 1 else FusedTrainer(model, lr=LR)
+    native = os.environ.get("NASREC_NATIVE", "1") != "0"          # C++ step executor (default) vs Python engine
+    if native:
+        from nasrec_b200.native import NativeTrainer
+        from nasrec_b200.parallel import NativeDataParallelTrainer
+        trainer = NativeDataParallelTrainer(model, lr=LR) if world > 1 else NativeTrainer(model, lr=LR)
+    else:
+        trainer = DataParallelTrainer(model, lr=LR) if world > 1 else FusedTrainer(model, lr=LR)
 
     pool_h = synth_pool(64, B_TRAIN, 13, ne, seed=1234 + rank)      # different data per rank, same choices
     pool_d = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in pool_h]
@@ -337,7 +343,7 @@ def run_ours(args):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_batch": B_TRAIN, "global_batch": B_TRAIN * world,
-                           "arithmetic": "fp32 storage and accumulation; GEMMs as 3xTF32-split tcgen05 MMAs "
+                           "host": "C++ step executor" if native else "Python engine", "arithmetic": "fp32 storage and accumulation; GEMMs as 3xTF32-split tcgen05 MMAs "
                                          "(fp32-parity, logits within 1e-5 of the fp32 reference)",
                            "parallelism": "dp%d" % world, "l2": "256 MB flush write between timed steps",
                            "ids": "zipf(1.05)"},
@@ -353,7 +359,7 @@ def run_ours(args):
         with GemmTimer(torch, _lib) as gt:
             for i in range(min(K, 10)):
                 flush.zero_()
-                trainer.step(*pool_d[i % 64])
+                FusedTrainer.step(trainer, *pool_d[i % 64])     # Python engine: every entry point goes through _lib.call
         _eng.FUSED_CALLS = True
         n, ms, fl = gt.summary()
         try:

@@ -35,6 +35,7 @@ extern "C" {
 
 #define NASREC_EINVAL (-1)         /* bad argument (null pointer, size out of range) */
 #define NASREC_ETOOBIG (-2)        /* size beyond what this build supports */
+#define NASREC_ENOSPACE (-3)       /* a caller-provided arena is too small (nasrec_net_*): grow it and retry */
 
 /* One source of a zero-padded concat.  2-D: `ptr` is [M, >=width] with row stride
  * `ld`; 3-D: `ptr` is [B, >=width, 16] with batch stride `ld` (floats).  `width`
@@ -62,6 +63,14 @@ int nasrec_get_gemm_mode(void);
  * launches that would occupy fewer than 64 SMs split their K range over several CTAs and finish
  * with a fixed-order reduction (deterministic).  Pass (NULL, 0) to detach. */
 int nasrec_set_workspace(float* ws, int64_t nfloats);
+/* Optional overlap of weight-gradient GEMMs with the dY -> dX chain: with a side stream attached, the
+ * op-level backward entry points (nasrec_linear_ln_bwd, nasrec_sproj_ln_bwd) fork their wgrad / bias-grad
+ * launches onto it (event-ordered after their LayerNorm backward); nasrec_side_join(stream) makes `stream`
+ * wait for all forked work and must be called before the gradients are read (and before a CUDA-graph
+ * capture ends).  Buffers handed to those entry points must stay allocated until the join.
+ * stream == NULL detaches.  The split-K workspace is halved between the two streams while attached. */
+int nasrec_set_side_stream(void* stream);
+int nasrec_side_join(void* stream);
 
 /* ------------------------------------------------------------------ embedding
  * a1  SuperNet._input_stem_layers_bi_output, supernet.py:404-430:

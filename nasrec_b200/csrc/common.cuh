@@ -44,5 +44,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 // library scratch attached with nasrec_set_workspace (gemm.cu); stream-ordered reuse by every kernel family
 void nasrec_internal_workspace(float** ws, long long* nfloats);
+// optional second stream on which the op-level backward entry points issue weight-gradient work
+cudaStream_t nasrec_internal_side_stream();
+void nasrec_internal_set_side_stream(cudaStream_t s);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -17,9 +17,56 @@ void split_targets(const nasrec_seg_t* dsegs, const int* acc_flags, int nseg, Se
         else s.fresh[s.nf++] = dsegs[i];
     }
 }
+
+// ---- fork / join between the caller's stream and the optional side stream ----------------------
+// Weight gradients are consumed only by the optimizer at the end of the step, so they need not sit on
+// the critical path dY -> dX of the backward pass.  With a side stream attached, each backward entry
+// point forks after its LayerNorm-backward kernel: wgrad (+ bias grad) go to the side stream, dgrad
+// stays on the caller's stream; nasrec_side_join() makes the caller's stream wait for everything forked.
+// Works under CUDA-graph capture (the side stream joins the capture through the event wait).
+constexpr int NEV = 64;
+cudaEvent_t g_ev[NEV];
+int g_ev_made = 0, g_ev_next = 0;
+bool g_forked = false;
+
+cudaEvent_t next_event() {
+    if (g_ev_made < NEV) {
+        cudaEventCreateWithFlags(&g_ev[g_ev_made], cudaEventDisableTiming);
+        return g_ev[g_ev_made++];
+    }
+    g_ev_next = (g_ev_next + 1) % NEV;
+    return g_ev[g_ev_next];
+}
+
+// returns the stream wgrad work should use
+cudaStream_t fork_for_wgrad(cudaStream_t main) {
+    cudaStream_t side = nasrec_internal_side_stream();
+    if (!side || side == main) return main;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, main);
+    cudaStreamWaitEvent(side, e, 0);
+    g_forked = true;
+    return side;
+}
 }  // namespace
 
 extern "C" {
+
+int nasrec_set_side_stream(void* stream) {
+    nasrec_internal_set_side_stream((cudaStream_t)stream);
+    g_forked = false;
+    return 0;
+}
+
+int nasrec_side_join(void* stream) {
+    cudaStream_t side = nasrec_internal_side_stream();
+    if (!side || !g_forked) return 0;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, side);
+    cudaStreamWaitEvent(as_stream(stream), e, 0);
+    g_forked = false;
+    return nasrec_launch_status();
+}
 
 // y[:, :d_out] (+)= act(LN(concat(segs) @ W[n_off:n_off+N].T + bias))   (LN skipped when gamma == null)
 int nasrec_linear_ln_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off, int N,
@@ -42,13 +89,16 @@ int nasrec_linear_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* 
     if (gamma) rc = nasrec_ln_bwd(dy, lddy, d_out, z, N, M, N, gamma, beta, mean, rstd, relu, dz, N, dgamma, dbeta, 0, stream);
     else rc = nasrec_act_bwd(dy, lddy, z, N, M, N, relu, dz, N, stream);
     if (rc) return rc;
-    if (dW) {
-        rc = nasrec_seg_linear_wgrad(dz, N, N, segs, nseg, dW, ldw, n_off, M, 0, stream);
-        if (rc) return rc;
-    }
-    if (dbias) {
-        rc = nasrec_colsum(dz, N, M, N, dbias + n_off, 0, stream);
-        if (rc) return rc;
+    if (dW || dbias) {
+        void* ws_stream = fork_for_wgrad(as_stream(stream));
+        if (dW) {
+            rc = nasrec_seg_linear_wgrad(dz, N, N, segs, nseg, dW, ldw, n_off, M, 0, ws_stream);
+            if (rc) return rc;
+        }
+        if (dbias) {
+            rc = nasrec_colsum(dz, N, M, N, dbias + n_off, 0, ws_stream);
+            if (rc) return rc;
+        }
     }
     SegSplit s;
     split_targets(dsegs, dseg_accumulate, nseg, s);
@@ -84,13 +134,16 @@ int nasrec_sproj_ln_bwd(const float* dy, int64_t dy_bstride, int p_out, const fl
     if (gamma) rc = nasrec_ln3_bwd(dy, dy_bstride, p_out, z, zbs, B, P, gamma, beta, mean, rstd, relu, dz, zbs, dgamma, dbeta, 0, stream);
     else rc = nasrec_act_bwd(dy, dy_bstride, z, zbs, B, P * NASREC_EMB_DIM, relu, dz, zbs, stream);
     if (rc) return rc;
-    if (dW) {
-        rc = nasrec_sproj_wgrad(dz, zbs, P, segs, nseg, dW, ldw, B, 0, ws, stream);
-        if (rc) return rc;
-    }
-    if (dbias) {
-        rc = nasrec_sproj_bias_grad(dz, zbs, P, B, dbias, 0, stream);
-        if (rc) return rc;
+    if (dW || dbias) {
+        void* ws_stream = fork_for_wgrad(as_stream(stream));
+        if (dW) {
+            rc = nasrec_sproj_wgrad(dz, zbs, P, segs, nseg, dW, ldw, B, 0, ws, ws_stream);
+            if (rc) return rc;
+        }
+        if (dbias) {
+            rc = nasrec_sproj_bias_grad(dz, zbs, P, B, dbias, 0, ws_stream);
+            if (rc) return rc;
+        }
     }
     SegSplit s;
     split_targets(dsegs, dseg_accumulate, nseg, s);

@@ -163,6 +163,16 @@ int launch_reduce(const RedBatch& rb, cudaStream_t st) {
 
 float* g_ws = nullptr;          // library workspace for automatic split-K (nasrec_set_workspace)
 long long g_ws_floats = 0;
+cudaStream_t g_side = nullptr;  // optional second stream for weight-gradient GEMMs (nasrec_set_side_stream)
+
+// Work on the side stream runs concurrently with the main stream: it gets its own half of the workspace.
+void ws_region(cudaStream_t st, float** base, long long* n) {
+    if (!g_ws) { *base = nullptr; *n = 0; return; }
+    if (!g_side) { *base = g_ws; *n = g_ws_floats; return; }
+    const long long half = (g_ws_floats / 2) & ~63LL;
+    *base = (st == g_side) ? g_ws + half : g_ws;
+    *n = half;
+}
 
 int g_gemm_mode = 3;   // 0: fp32 FFMA; 1/3/4: tcgen05 kind::tf32 with 1/3/4 split products (default 3xTF32)
 
@@ -199,7 +209,10 @@ int launch(Batch& bt, cudaStream_t st) {
         // partials into the library workspace, fixed-order reduction (deterministic).
         RedBatch rb{};
         const long long ctas = nasrec_gemm::tc_cta_count(bt, nasrec_gemm::tc_pick_bn(bt, maxN));
-        if (g_ws && ctas < 64) {
+        float* wsb = nullptr;
+        long long wsn = 0;
+        ws_region(st, &wsb, &wsn);
+        if (wsb && ctas < 64) {
             long long off = 0;
             const int want = (int)(128 / (ctas > 0 ? ctas : 1));
             for (int p = 0; p < bt.nprob; ++p) {
@@ -211,9 +224,9 @@ int launch(Batch& bt, cudaStream_t st) {
                 int ns = want < ktiles / 4 ? want : ktiles / 4;
                 if (ns > 16) ns = 16;
                 const long long need = (long long)ns * pr.M * pr.N;
-                if (ns < 2 || off + need > g_ws_floats) continue;
+                if (ns < 2 || off + need > wsn) continue;
                 RedSeg& rs = rb.seg[rb.nseg++];
-                rs.ws = g_ws + off;
+                rs.ws = wsb + off;
                 rs.c = pr.c;
                 rs.bias = pr.bias;
                 rs.ldc = pr.c_hi_i;
@@ -221,7 +234,7 @@ int launch(Batch& bt, cudaStream_t st) {
                 rs.N = pr.N;
                 rs.nsplit = ns;
                 rs.accumulate = pr.addend != nullptr;
-                pr.c = g_ws + off;
+                pr.c = wsb + off;
                 pr.c_hi_i = pr.N;
                 pr.bias = nullptr;
                 pr.addend = nullptr;
@@ -250,10 +263,12 @@ bool segs_ok(const nasrec_seg_t* segs, int nseg) {
 
 }  // namespace
 
-void nasrec_internal_workspace(float** ws, long long* nfloats) {
-    *ws = g_ws;
-    *nfloats = g_ws_floats;
+void nasrec_internal_workspace(float** ws, long long* nfloats) {   // main-stream region
+    ws_region(nullptr, ws, nfloats);
 }
+
+cudaStream_t nasrec_internal_side_stream() { return g_side; }
+void nasrec_internal_set_side_stream(cudaStream_t s) { g_side = s; }
 
 extern "C" {
 

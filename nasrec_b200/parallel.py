@@ -121,3 +121,42 @@ class DataParallelTrainer(FusedTrainer):
             sparse = eng.reduce_sparse(allgather_cat(cat_l, self.group), allgather_cat(gout_l, self.group))
         self.apply(run, sparse, lr)
         return logits, loss
+
+
+class NativeDataParallelTrainer(DataParallelTrainer):
+    """DataParallelTrainer on the C++ step executor (nasrec_b200/native.py).  The executor lays the
+    step's dense parameter gradients out back to back in one arena, in first-touch order -- identical on
+    every rank because the sampled subnet is -- so the flat bucket that is all-reduced IS the gradient
+    storage: no concatenation, no copy back.  The embedding gradient is all-gathered raw and reduced by
+    the same deterministic sorted-row kernel on every replica."""
+
+    def __init__(self, model, lr, eps: float = 1e-2, clip: Optional[float] = 5.0, group=None):
+        super().__init__(model, lr, eps, clip, group)
+        from .native import NativeTrainer
+        self._nt = NativeTrainer(model, lr, eps, clip)
+        self._nt.state = self.state                       # one set of Adagrad accumulators for both paths
+
+    def step(self, int_x, cat_x, y, lr: Optional[float] = None):
+        net = self._nt._native(int_x)
+        if net is None:
+            return super().step(int_x, cat_x, y, lr)
+        if self.world == 1:
+            out = self._nt.step(int_x, cat_x, y, lr)
+            self.last_total_norm = self._nt.last_total_norm
+            return out
+        from . import _lib
+        net.refresh()
+        cat = (cat_x if cat_x.dtype == torch.int64 else cat_x.long()).contiguous()
+        with _lib.pin_stream():
+            logits, loss = net.forward_backward(self._nt._choice(), int_x.contiguous(), cat, y.contiguous(),
+                                                grad_scale=1.0 / self.world)
+            bucket = net.grad_bucket()
+            if bucket.numel():
+                dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group)
+            raw = net.sparse_raw(cat)
+            if raw is not None:
+                cat_all, g_all = allgather_cat(cat, self.group), allgather_cat(raw, self.group)
+                net.sparse_reduce(cat_all, g_all)
+            norm = net.apply(self.lr if lr is None else lr, self.eps, self.clip)
+        self.last_total_norm = norm[0:1]
+        return logits, loss

@@ -1,0 +1,152 @@
+"""GPU: the C++ step executor (nasrec_b200/csrc/net.cu) must reproduce the Python engine
+bit for bit -- it issues the same kernels in the same order -- and therefore inherits its
+parity with the reference; a direct check against the reference's recorded training run
+is included as well."""
+import numpy as np
+import pytest
+import torch
+
+from nasrec_b200 import SuperNet, ops_config_lib
+from nasrec_b200.native import NativeNet, NativeTrainer
+from nasrec_b200.utils.train_utils import FusedTrainer
+from oracle import nasrec_oracle as orc
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(cfg, ne, nd, shapes, seed):
+    m = SuperNet(num_blocks=cfg["num_blocks"], ops_config=ops_config_lib[cfg["ops"]], use_layernorm=cfg["use_layernorm"],
+                 num_embeddings=ne, sparse_input_size=len(ne), path_sampling_strategy="full-path").to("cuda")
+    m.materialize(nd)
+    m.load_state_dict(orc.fill_state_dict(shapes, seed), strict=True)
+    return m
+
+
+def _pin(m, choice):
+    m.configure_choice(choice)
+    m.configure_path_sampling_strategy("fixed-path")
+
+
+@pytest.mark.parametrize("name", ["supernet_autoctr_criteo", "supernet_xlarge_criteo", "supernet_xlarge_kdd"])
+def test_native_steps_are_bit_identical_to_python_engine(name):
+    meta, _ = load_golden(name)
+    smeta, _ = load_golden("samplers")
+    cfg, ne, nd = meta["cfg"], meta["num_embeddings"], meta["nd"]
+    choices = [c["choice"] for c in meta["cases"]]
+    if name == "supernet_xlarge_criteo":
+        choices += smeta["ea_candidates"]["xlarge"][:4]
+    a = _model(cfg, ne, nd, meta["shapes"], 5)
+    b = _model(cfg, ne, nd, meta["shapes"], 5)
+    ta, tb = FusedTrainer(a, lr=0.12), NativeTrainer(b, lr=0.12)
+    for si, ch in enumerate(choices * 2):
+        int_x, cat_x, y = (t.cuda() for t in orc.synth_batch(37 + si, nd, ne, seed=40 + si, all_zero_dense=False))
+        _pin(a, ch)
+        _pin(b, ch)
+        la, lossa = ta.step(int_x, cat_x, y)
+        lb, lossb = tb.step(int_x, cat_x, y)
+        assert tb.net is not None, tb.fallback_reason
+        assert torch.equal(la, lb), (name, si)
+        assert torch.equal(lossa, lossb)
+        assert torch.equal(ta.last_total_norm, tb.last_total_norm)
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    for p, q in zip(a.parameters(), b.parameters()):            # Adagrad accumulators too
+        s1, s2 = ta.state.get(id(p)), tb.state.get(id(q))
+        if s1 is not None:
+            assert torch.equal(s1, s2)
+        else:
+            assert float(s2.abs().sum()) == 0.0
+
+
+def test_native_training_matches_reference_golden_run():
+    meta, arrays = load_golden("train_steps")
+    for tag, run in meta["runs"].items():
+        cfg, ne = run["cfg"], run["num_embeddings"]
+        m = _model(cfg, ne, 13, {k: tuple(v) for k, v in run["shapes"].items()}, run["state_seed"])
+        tr = NativeTrainer(m, lr=run["lr"])
+        for si, ch in enumerate(run["choices"]):
+            int_x, cat_x, y = (t.cuda() for t in orc.synth_batch(8, 13, ne, seed=300 + si))
+            _pin(m, ch)
+            logits, loss = tr.step(int_x, cat_x, y)
+            assert tr.net is not None
+            ref = arrays["%s/logits_%d" % (tag, si)]
+            assert np.abs(logits.cpu().numpy() - ref).max() <= 5e-4 * max(1.0, np.abs(ref).max())
+            assert abs(float(loss) - run["losses"][si]) <= 5e-4 * max(1.0, abs(run["losses"][si]))
+            assert abs(float(tr.last_total_norm) - run["total_norms"][si]) <= 1e-3 * run["total_norms"][si]
+        fw = m._final.weight.detach().cpu().numpy()
+        assert np.abs(fw - arrays[tag + "/final_weight"]).max() < 1e-4
+
+
+def test_native_forward_and_frozen_modes():
+    meta, _ = load_golden("supernet_xlarge_criteo")
+    cfg, ne, nd = meta["cfg"], meta["num_embeddings"], meta["nd"]
+    a = _model(cfg, ne, nd, meta["shapes"], 9)
+    b = _model(cfg, ne, nd, meta["shapes"], 9)
+    ch = meta["cases"][1]["choice"]
+    int_x, cat_x, y = (t.cuda() for t in orc.synth_batch(300, nd, ne, seed=77))
+    net = NativeNet(b)
+    enc = NativeNet.encode_choice(ch["macro"], ch["micro"])
+    with torch.no_grad():
+        ref = a(int_x, cat_x, choices=ch)
+    assert torch.equal(net.forward(enc, int_x, cat_x), ref)
+    # pre-gathered rows (shared across candidates in one-shot scoring)
+    rows = torch.stack([e.weight.detach()[cat_x[:, f]] for f, e in enumerate(b._embedding)], dim=1).contiguous()
+    assert torch.equal(net.forward(enc, int_x, None, emb_rows=rows), ref)
+    # last-layer-only fine-tuning: nothing but _final moves, and it moves exactly as in the Python engine
+    for m in (a, b):
+        _pin(m, ch)
+        m.set_mode_to_finelune_last_only()
+    ta, tb = FusedTrainer(a, lr=0.1), NativeTrainer(b, lr=0.1)
+    before = {k: v.clone() for k, v in b.state_dict().items()}
+    for _ in range(3):
+        la, _ = ta.step(int_x, cat_x, y)
+        lb, _ = tb.step(int_x, cat_x, y)
+        assert torch.equal(la, lb)
+    assert tb.net is not None
+    for k, v in b.state_dict().items():
+        if k.startswith("_final"):
+            assert torch.equal(v, a.state_dict()[k]) and not torch.equal(v, before[k])
+        else:
+            assert torch.equal(v, before[k]), k
+    # back to full training: the flags are re-read every step
+    for m in (a, b):
+        m.set_mode_to_normal_mode()
+    la, _ = ta.step(int_x, cat_x, y)
+    lb, _ = tb.step(int_x, cat_x, y)
+    assert torch.equal(la, lb)
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, a.state_dict()[k]), k
+
+
+def test_native_arena_growth_and_fallback():
+    meta, _ = load_golden("supernet_autoctr_criteo")
+    cfg, ne, nd = meta["cfg"], meta["num_embeddings"], meta["nd"]
+    a = _model(cfg, ne, nd, meta["shapes"], 2)
+    b = _model(cfg, ne, nd, meta["shapes"], 2)
+    ch = meta["cases"][0]["choice"]
+    ta, tb = FusedTrainer(a, lr=0.1), NativeTrainer(b, lr=0.1)
+    int_x, cat_x, y = (t.cuda() for t in orc.synth_batch(64, nd, ne, seed=5))
+    _pin(a, ch)
+    _pin(b, ch)
+    tb._native(int_x)
+    tb.net._alloc_arenas(1 << 16, 1 << 16)             # far too small: must grow transparently, results unchanged
+    for _ in range(2):
+        la, _ = ta.step(int_x, cat_x, y)
+        lb, _ = tb.step(int_x, cat_x, y)
+        assert torch.equal(la, lb)
+    assert tb.net.act.numel() > (1 << 16)
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, a.state_dict()[k]), k
+    # a fixed model is not a native case: the trainer says why and still trains
+    fmeta, _ = load_golden("fixed_best")
+    tag, mm = next(iter(fmeta["models"].items()))
+    fm = SuperNet(num_blocks=7, ops_config=ops_config_lib[mm["cfg"]["ops"]], use_layernorm=mm["cfg"]["use_layernorm"],
+                  num_embeddings=mm["num_embeddings"], sparse_input_size=len(mm["num_embeddings"]),
+                  path_sampling_strategy="fixed-path", fixed=True, fixed_choice=mm["choice"]).to("cuda")
+    fm.materialize(mm["nd"])
+    tr = NativeTrainer(fm, lr=0.1)
+    bx = tuple(t.cuda() for t in orc.synth_batch(16, mm["nd"], mm["num_embeddings"], seed=1))
+    tr.step(*bx)
+    assert tr.net is None and "fixed" in tr.fallback_reason
