@@ -271,6 +271,8 @@ def run_ours(args):
         from nasrec_b200.native import NativeTrainer
         from nasrec_b200.parallel import NativeDataParallelTrainer
         trainer = NativeDataParallelTrainer(model, lr=LR) if world > 1 else NativeTrainer(model, lr=LR)
+        if os.environ.get("NASREC_OVERLAP", "1") == "0":
+            (trainer._nt if world > 1 else trainer).overlap_wgrad = False
     else:
         trainer = DataParallelTrainer(model, lr=LR) if world > 1 else FusedTrainer(model, lr=LR)
 

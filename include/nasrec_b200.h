@@ -267,6 +267,49 @@ int nasrec_adagrad_multi(float* const* w, const float* const* grads, float* cons
                          const int64_t* sizes, int n, float lr, float eps, const float* clip_coef,
                          void* stream);
 
+/* ---------------------------------------------------------------- step executor
+ * The whole hot path behind one handle: SuperNet.forward (supernet.py:513-603), SuperNetBlock.forward
+ * (:1067-1162) with every weight-sharing module of supernet/modules.py, BCE, backward, clip and Adagrad
+ * (train_utils.py:262-286), sequenced on the host in C++ from (a) a one-off description of the model and
+ * (b) the sampled subnet as a flat int array -- the "kernel path that takes the sampled subnet's
+ * mask/choice directly".  Same kernels and launch order as the per-operator entry points above.
+ *
+ * desc_i: [num_blocks, nd, F, final_w, final_b, emb_param[F], then per block: num_nodes, max_dense,
+ *          max_sparse, dotproduct_P, merger{W,b,ln_g,ln_b}, fm{W,b,ln_g,ln_b}, num_nodes x {type, p[24]}]
+ *   (values are indices into the parameter table, -1 = absent; node types 0 FC, 1 DotProduct, 2 Sum,
+ *   3 SigmoidGating, 4 EFC, 5 Transformer, 6 Zeros2D, 7 Zeros3D; p[] in state-dict order of the node).
+ * w/state: HOST arrays of n_params device pointers (state = Adagrad accumulators, may be NULL for
+ *   inference); numel/rows/cols/req per parameter.  d_tables/d_rows/d_tables_rw/d_states/d_err: DEVICE
+ *   arrays as for nasrec_emb_gather_fwd / nasrec_emb_rowwise_adagrad.
+ * choice: per block 49 ints: 5 lists {count, idx[8]} (dense_idx, sparse_idx, dense_left_idx,
+ *   dense_right_idx, active_nodes) then dense_in_dims, sparse_in_dims, dense_sparse_interact, deep_fm.
+ * Arenas are caller-owned device memory; NASREC_ENOSPACE asks for bigger ones
+ * (nasrec_net_arena_high_water says how big).  Fixed (standalone) models are not handled here. */
+void* nasrec_net_create(const int* desc_i, int desc_len, int n_params, float* const* w, float* const* state,
+                        const int64_t* numel, const int* rows, const int* cols, const int* req,
+                        const float* const* d_tables, const int64_t* d_rows, float* const* d_tables_rw,
+                        float* const* d_states, int* d_err);
+void nasrec_net_destroy(void* net);
+int nasrec_net_set_arenas(void* net, void* act, int64_t act_bytes, void* pgrad, int64_t pgrad_bytes);
+int nasrec_net_set_requires_grad(void* net, const int* req, int n_params);
+int nasrec_net_set_overlap(void* net, int on);      /* join the side stream (nasrec_set_side_stream) after backward */
+/* logits [B] for one subnet; emb_rows (optional) = [B,F,16] rows gathered once and shared by many candidates. */
+int nasrec_net_forward(void* net, const int* choice, const float* int_x, const int64_t* cat_x, const float* emb_rows,
+                       int B, float* logits, void* stream);
+/* forward + BCEWithLogits(mean)*grad_scale + backward.  Afterwards the dense parameter gradients lie back to
+ * back in the pgrad arena (nasrec_net_grad_bucket: what data-parallel training all-reduces in place) and the
+ * raw embedding gradient [B,F,16] is exposed by nasrec_net_sparse_raw. */
+int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x, const int64_t* cat_x, const float* y,
+                                int B, float grad_scale, float* logits, float* loss, void* stream);
+int nasrec_net_grad_bucket(void* net, float** ptr, int64_t* nfloats);
+int nasrec_net_sparse_raw(void* net, const int64_t** cat_x, float** gout);
+/* sorted-row reduction of the step's own embedding gradient (cat_all == NULL) or of an all-gathered one */
+int nasrec_net_sparse_reduce(void* net, const int64_t* cat_all, const float* gout_all, int B_all, void* stream);
+/* clip_grad_norm_(max_norm; <= 0: off) + Adagrad on what received a gradient; norm_out: 2 device floats */
+int nasrec_net_apply(void* net, float lr, float eps, float max_norm, float* norm_out, void* stream);
+int64_t nasrec_net_launches(void);
+int64_t nasrec_net_arena_high_water(void* net, int which);
+
 #ifdef __cplusplus
 }
 #endif

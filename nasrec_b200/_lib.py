@@ -70,7 +70,8 @@ _SIGS_I64 = {
     "nasrec_sumsq_ws_floats": [_f, _i],
     "nasrec_binary_metrics_ws_bytes": [_l],
 }
-EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace"] + list(_SIGS) + list(_SIGS_I64)
+EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace",
+           "nasrec_set_side_stream", "nasrec_side_join"] + list(_SIGS) + list(_SIGS_I64)
 
 
 class _Lib:

@@ -315,10 +315,26 @@ class NativeTrainer(FusedTrainer):
     """FusedTrainer whose steps run on the C++ executor when the model allows it (weight-sharing
     supernet, every parameter's Adagrad state pre-allocated); otherwise it is a FusedTrainer."""
 
-    def __init__(self, model: SuperNet, lr: float, eps: float = 1e-2, clip: Optional[float] = 5.0):
+    def __init__(self, model: SuperNet, lr: float, eps: float = 1e-2, clip: Optional[float] = 5.0,
+                 overlap_wgrad: bool = True):
         super().__init__(model, lr, eps, clip)
         self.net: Optional[NativeNet] = None
         self.fallback_reason: Optional[str] = None
+        # weight-gradient GEMMs on a second stream, off the dY -> dX critical path (joined before the optimizer)
+        self.overlap_wgrad = overlap_wgrad
+        self._side: Optional[torch.cuda.Stream] = None
+
+    def _fork_on(self, net: "NativeNet"):
+        if not self.overlap_wgrad:
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+            _check(_fn("nasrec_net_set_overlap")(net.handle, 1), "nasrec_net_set_overlap")
+        _fn("nasrec_set_side_stream")(self._side.cuda_stream)
+
+    def _fork_off(self):
+        if self.overlap_wgrad:
+            _fn("nasrec_set_side_stream")(None)       # the Python engine's entry points must not fork
 
     def _native(self, int_x) -> Optional[NativeNet]:
         if self.net is None and self.fallback_reason is None:
@@ -341,7 +357,12 @@ class NativeTrainer(FusedTrainer):
         net.refresh()
         cat = cat_x if cat_x.dtype == torch.int64 else cat_x.long()
         with _lib.pin_stream():
-            logits, loss = net.forward_backward(self._choice(), int_x.contiguous(), cat.contiguous(), y.contiguous())
+            self._fork_on(net)
+            try:
+                logits, loss = net.forward_backward(self._choice(), int_x.contiguous(), cat.contiguous(),
+                                                    y.contiguous())
+            finally:
+                self._fork_off()
             net.sparse_reduce()
             norm = net.apply(self.lr if lr is None else lr, self.eps, self.clip)
         self.last_total_norm = norm[0:1]

@@ -148,8 +148,12 @@ class NativeDataParallelTrainer(DataParallelTrainer):
         net.refresh()
         cat = (cat_x if cat_x.dtype == torch.int64 else cat_x.long()).contiguous()
         with _lib.pin_stream():
-            logits, loss = net.forward_backward(self._nt._choice(), int_x.contiguous(), cat, y.contiguous(),
-                                                grad_scale=1.0 / self.world)
+            self._nt._fork_on(net)
+            try:
+                logits, loss = net.forward_backward(self._nt._choice(), int_x.contiguous(), cat, y.contiguous(),
+                                                    grad_scale=1.0 / self.world)
+            finally:
+                self._nt._fork_off()
             bucket = net.grad_bucket()
             if bucket.numel():
                 dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group)

@@ -159,16 +159,20 @@ def test_cpu_tensors_are_rejected_not_emulated():
 
 def test_c_abi_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "nasrec_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|int64_t)\s+(nasrec_\w+)\s*\(", hdr, flags=re.M))
-    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    from nasrec_b200 import native
+    declared = set(re.findall(r"^(?:int|int64_t|void\s*\*?)\s*(nasrec_\w+)\s*\(", hdr, flags=re.M))
+    bound = set(_lib.EXPORTS) | set(native.EXPORTS)
+    assert declared == bound, declared ^ bound
     assert os.path.exists(_lib.LIB_PATH), "build the library first (__graft_entry__.build())"
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
     # argument counts of the ctypes table match the header prototypes
-    for name, (argtypes, _n) in _lib._SIGS.items():
-        proto = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, hdr, flags=re.S).group(1)
-        assert len(proto.split(",")) == len(argtypes), name
+    tables = [(n, a) for n, (a, _k) in _lib._SIGS.items()] + [(n, a) for n, (a, _r) in native._PROTOS.items()]
+    for name, argtypes in tables:
+        proto = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, hdr, flags=re.S).group(1).strip()
+        nargs = 0 if proto in ("", "void") else len(proto.split(","))
+        assert nargs == len(argtypes), name
     sm = ctypes.c_int(0)
     lib.nasrec_version.argtypes = [ctypes.POINTER(ctypes.c_int)]
     assert lib.nasrec_version(ctypes.byref(sm)) >= 100 and sm.value == 100
