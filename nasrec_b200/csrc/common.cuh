@@ -42,6 +42,34 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return red[32];
 }
 
+// Predicated loads as inline PTX.  A load inside an `if` ends a basic block, and the compiler then waits for
+// it before the next block's loads are issued: an unrolled loop of guarded loads becomes a chain of
+// full memory latencies.  These keep such loops branch-free so that all loads are in flight together.
+__device__ __forceinline__ float ldg_nc_pred(const float* p, bool pred) {
+    float v = 0.f;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %2, 0;\n\t"
+        "@q ld.global.nc.f32 %0, [%1];\n\t"
+        "}\n"
+        : "+f"(v)
+        : "l"(p), "r"((int)pred));
+    return v;
+}
+__device__ __forceinline__ float ld_pred(const float* p, bool pred) {     // coherent variant (buffers written by this kernel)
+    float v = 0.f;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %2, 0;\n\t"
+        "@q ld.global.f32 %0, [%1];\n\t"
+        "}\n"
+        : "+f"(v)
+        : "l"(p), "r"((int)pred));
+    return v;
+}
+
 // library scratch attached with nasrec_set_workspace (gemm.cu); stream-ordered reuse by every kernel family
 void nasrec_internal_workspace(float** ws, long long* nfloats);
 // optional second stream on which the op-level backward entry points issue weight-gradient work

@@ -25,14 +25,20 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= M) return;
     const float* xr = x + (long long)row * ldx;
-    float v[LN_VPT];
-    float s = 0.f;
+    float* yr = y + (long long)row * ldy;
+    // phase 1: every load of the row is issued before anything waits (see ldg_nc_pred)
+    float v[LN_VPT], gm[LN_VPT], bt[LN_VPT], yo[LN_VPT];
 #pragma unroll
     for (int k = 0; k < LN_VPT; ++k) {
         const int j = lane + 32 * k;
-        v[k] = j < N ? xr[j] : 0.f;
-        s += v[k];
+        v[k] = ldg_nc_pred(xr + j, j < N);
+        gm[k] = ldg_nc_pred(gamma + j, j < d_out);
+        bt[k] = ldg_nc_pred(beta + j, j < d_out);
+        yo[k] = ld_pred(yr + j, accumulate && j < d_out);
     }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_VPT; ++k) s += v[k];
     const float mean = warp_sum(s) / (float)N;
     float q = 0.f;
 #pragma unroll
@@ -46,15 +52,12 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
         mean_out[row] = mean;
         rstd_out[row] = rstd;
     }
-    float* yr = y + (long long)row * ldy;
 #pragma unroll
     for (int k = 0; k < LN_VPT; ++k) {
         const int j = lane + 32 * k;
-        if (j < d_out) {
-            float o = (v[k] - mean) * rstd * gamma[j] + beta[j];
-            if (relu) o = fmaxf(o, 0.f);
-            yr[j] = accumulate ? yr[j] + o : o;
-        }
+        float o = (v[k] - mean) * rstd * gm[k] + bt[k];
+        if (relu) o = fmaxf(o, 0.f);
+        if (j < d_out) yr[j] = accumulate ? yo[k] + o : o;
     }
 }
 
@@ -77,27 +80,29 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
         accb[k] = 0.f;
     }
     for (int row = blockIdx.x * 4 + w; row < M; row += gridDim.x * 4) {
-        const float mean = mean_in[row], rstd = rstd_in[row];
         const float* xr = x + (long long)row * ldx;
         const float* dyr = dy + (long long)row * lddy;
-        float xh[LN_VPT], a[LN_VPT];
+        // phase 1: all loads in flight together
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float xh[LN_VPT], a[LN_VPT], gm[LN_VPT], bt[LN_VPT];
+#pragma unroll
+        for (int k = 0; k < LN_VPT; ++k) {
+            const int j = lane + 32 * k;
+            xh[k] = ldg_nc_pred(xr + j, j < N);
+            a[k] = ldg_nc_pred(dyr + j, j < d_out);
+            gm[k] = ldg_nc_pred(gamma + j, j < d_out);
+            bt[k] = ldg_nc_pred(beta + j, j < d_out);
+        }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < LN_VPT; ++k) {
             const int j = lane + 32 * k;
-            xh[k] = 0.f;
-            a[k] = 0.f;
-            if (j < N) {
-                xh[k] = (xr[j] - mean) * rstd;
-                if (j < d_out) {
-                    const float g = gamma[j];
-                    float d = dyr[j];
-                    if (relu && (xh[k] * g + beta[j]) <= 0.f) d = 0.f;
-                    a[k] = d * g;
-                    accg[k] = fmaf(d, xh[k], accg[k]);
-                    accb[k] += d;
-                }
-            }
+            xh[k] = j < N ? (xh[k] - mean) * rstd : 0.f;
+            float d = a[k];                                      // 0 beyond d_out
+            if (relu && (xh[k] * gm[k] + bt[k]) <= 0.f) d = 0.f;
+            a[k] = d * gm[k];
+            accg[k] = fmaf(d, xh[k], accg[k]);
+            accb[k] += d;
             s1 += a[k];
             s2 += a[k] * xh[k];
         }
@@ -131,21 +136,43 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
     }
 }
 
-__global__ void ln_param_final_kernel(const float* __restrict__ part, int nblk, int N, float* __restrict__ dgamma,
-                                      float* __restrict__ dbeta, int accumulate) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
+// Second stage of the dgamma/dbeta reduction: part[k][0|1][j], k < nblk.  One CTA per 32 columns; warp r
+// sums partial rows r, r+8, ... (coalesced 128-byte reads, 4 independent loads in flight), then the 8
+// warp totals are added in a fixed order -- deterministic for a given nblk.
+__global__ void __launch_bounds__(256) ln_param_final_kernel(const float* __restrict__ part, int nblk, int N,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                             int accumulate) {
+    __shared__ float sg[8][33], sb[8][33];
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + c;
     float g = 0.f, b = 0.f;
-    for (int k = 0; k < nblk; ++k) {
-        g += part[(long long)k * 2 * N + j];
-        b += part[(long long)k * 2 * N + N + j];
+    if (j < N) {
+        int k = r;
+        for (; k + 24 < nblk; k += 32) {
+            const float* p0 = part + (long long)k * 2 * N + j;
+            const float g0 = p0[0], b0 = p0[N];
+            const float g1 = p0[(long long)16 * N], b1 = p0[(long long)16 * N + N];
+            const float g2 = p0[(long long)32 * N], b2 = p0[(long long)32 * N + N];
+            const float g3 = p0[(long long)48 * N], b3 = p0[(long long)48 * N + N];
+            g += (g0 + g1) + (g2 + g3);
+            b += (b0 + b1) + (b2 + b3);
+        }
+        for (; k < nblk; k += 8) {
+            g += part[(long long)k * 2 * N + j];
+            b += part[(long long)k * 2 * N + N + j];
+        }
     }
-    dgamma[j] = accumulate ? dgamma[j] + g : g;
-    dbeta[j] = accumulate ? dbeta[j] + b : b;
+    sg[r][c] = g;
+    sb[r][c] = b;
+    __syncthreads();
+    if (r == 0 && j < N) {
+        const float gt = ((sg[0][c] + sg[1][c]) + (sg[2][c] + sg[3][c])) + ((sg[4][c] + sg[5][c]) + (sg[6][c] + sg[7][c]));
+        const float bt = ((sb[0][c] + sb[1][c]) + (sb[2][c] + sb[3][c])) + ((sb[4][c] + sb[5][c]) + (sb[6][c] + sb[7][c]));
+        dgamma[j] = accumulate ? dgamma[j] + gt : gt;
+        dbeta[j] = accumulate ? dbeta[j] + bt : bt;
+    }
 }
 
-// dgamma[j] = sum_m g[m,j]*xhat[m,j], dbeta[j] = sum_m g[m,j]; one CTA per 32 columns,
-// 32x32 threads, fixed-order reduction over the row lanes.
 __global__ void __launch_bounds__(1024) ln_param_grad_kernel(const float* __restrict__ dy, long long lddy,
                                                              int d_out, const float* __restrict__ x,
                                                              long long ldx, int M, int N,
@@ -201,14 +228,20 @@ __global__ void __launch_bounds__(128) ln3_fwd_kernel(const float* __restrict__ 
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= B) return;
     const float* zp = z + (long long)b * zbs + e;
-    float v[LN3_V];
-    float s = 0.f;
+    float* yp = y + (long long)b * ybs + e;
+    // phase 1: every load in flight before the first use (see ldg_nc_pred)
+    float v[LN3_V], gm[LN3_V], bt[LN3_V], yo[LN3_V];
 #pragma unroll
     for (int k = 0; k < LN3_V; ++k) {
         const int p = 2 * k + ph;
-        v[k] = p < P ? zp[p * 16] : 0.f;
-        s += v[k];
+        v[k] = ldg_nc_pred(zp + p * 16, p < P);
+        gm[k] = ldg_nc_pred(gamma + p, p < p_out);
+        bt[k] = ldg_nc_pred(beta + p, p < p_out);
+        yo[k] = ld_pred(yp + p * 16, accumulate && p < p_out);
     }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN3_V; ++k) s += v[k];
     s += __shfl_xor_sync(0xffffffffu, s, 16);
     const float mean = s / (float)P;
     float q = 0.f;
@@ -224,15 +257,12 @@ __global__ void __launch_bounds__(128) ln3_fwd_kernel(const float* __restrict__ 
         mean_out[b * 16 + e] = mean;
         rstd_out[b * 16 + e] = rstd;
     }
-    float* yp = y + (long long)b * ybs + e;
 #pragma unroll
     for (int k = 0; k < LN3_V; ++k) {
         const int p = 2 * k + ph;
-        if (p < p_out) {
-            float o = (v[k] - mean) * rstd * gamma[p] + beta[p];
-            if (relu) o = fmaxf(o, 0.f);
-            yp[p * 16] = accumulate ? yp[p * 16] + o : o;
-        }
+        float o = (v[k] - mean) * rstd * gm[k] + bt[k];
+        if (relu) o = fmaxf(o, 0.f);
+        if (p < p_out) yp[p * 16] = accumulate ? yo[k] + o : o;
     }
 }
 
@@ -255,27 +285,29 @@ __global__ void __launch_bounds__(128) ln3_bwd_kernel(const float* __restrict__ 
         accb[k] = 0.f;
     }
     for (int b = blockIdx.x * 4 + w; b < B; b += gridDim.x * 4) {
-        const float mean = mean_in[b * 16 + e], rstd = rstd_in[b * 16 + e];
         const float* zp = z + (long long)b * zbs + e;
         const float* dp = dy + (long long)b * dybs + e;
-        float xh[LN3_V], a[LN3_V];
+        // phase 1: all loads in flight together
+        const float mean = mean_in[b * 16 + e], rstd = rstd_in[b * 16 + e];
+        float xh[LN3_V], a[LN3_V], gm[LN3_V], bt[LN3_V];
+#pragma unroll
+        for (int k = 0; k < LN3_V; ++k) {
+            const int p = 2 * k + ph;
+            xh[k] = ldg_nc_pred(zp + p * 16, p < P);
+            a[k] = ldg_nc_pred(dp + p * 16, p < p_out);
+            gm[k] = ldg_nc_pred(gamma + p, p < p_out);
+            bt[k] = ldg_nc_pred(beta + p, p < p_out);
+        }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < LN3_V; ++k) {
             const int p = 2 * k + ph;
-            xh[k] = 0.f;
-            a[k] = 0.f;
-            if (p < P) {
-                xh[k] = (zp[p * 16] - mean) * rstd;
-                if (p < p_out) {
-                    const float g = gamma[p];
-                    float d = dp[p * 16];
-                    if (relu && (xh[k] * g + beta[p]) <= 0.f) d = 0.f;
-                    a[k] = d * g;
-                    accg[k] = fmaf(d, xh[k], accg[k]);
-                    accb[k] += d;
-                }
-            }
+            xh[k] = p < P ? (xh[k] - mean) * rstd : 0.f;
+            float d = a[k];                                      // 0 beyond p_out
+            if (relu && (xh[k] * gm[k] + bt[k]) <= 0.f) d = 0.f;
+            a[k] = d * gm[k];
+            accg[k] = fmaf(d, xh[k], accg[k]);
+            accb[k] += d;
             s1 += a[k];
             s2 = fmaf(a[k], xh[k], s2);
         }
@@ -314,17 +346,29 @@ __global__ void __launch_bounds__(128) ln3_bwd_kernel(const float* __restrict__ 
     }
 }
 
-__global__ void ln3_param_final_kernel(const float* __restrict__ part, int nblk, int P, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int accumulate) {
-    const int p = threadIdx.x;
-    if (p >= P) return;
+// part[k][0|1][p], k < nblk: warp r sums partial rows r, r+8, ...; fixed-order add of the 8 warp totals.
+__global__ void __launch_bounds__(256) ln3_param_final_kernel(const float* __restrict__ part, int nblk, int P,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              int accumulate) {
+    __shared__ float sg[8][33], sb[8][33];
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + c;
     float g = 0.f, b = 0.f;
-    for (int k = 0; k < nblk; ++k) {
-        g += part[(long long)k * 2 * LN3_MAXP + p];
-        b += part[(long long)k * 2 * LN3_MAXP + LN3_MAXP + p];
+    if (p < P) {
+        for (int k = r; k < nblk; k += 8) {
+            g += part[(long long)k * 2 * LN3_MAXP + p];
+            b += part[(long long)k * 2 * LN3_MAXP + LN3_MAXP + p];
+        }
     }
-    dgamma[p] = accumulate ? dgamma[p] + g : g;
-    dbeta[p] = accumulate ? dbeta[p] + b : b;
+    sg[r][c] = g;
+    sb[r][c] = b;
+    __syncthreads();
+    if (r == 0 && p < P) {
+        const float gt = ((sg[0][c] + sg[1][c]) + (sg[2][c] + sg[3][c])) + ((sg[4][c] + sg[5][c]) + (sg[6][c] + sg[7][c]));
+        const float bt = ((sb[0][c] + sb[1][c]) + (sb[2][c] + sb[3][c])) + ((sb[4][c] + sb[5][c]) + (sb[6][c] + sb[7][c]));
+        dgamma[p] = accumulate ? dgamma[p] + gt : gt;
+        dbeta[p] = accumulate ? dbeta[p] + bt : bt;
+    }
 }
 
 // fallback when no workspace is attached: one CTA per p, dgamma[p] = sum_{b,e} g*xhat, dbeta[p] = sum g
@@ -457,7 +501,7 @@ int nasrec_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* x, int6
         if (rc) return rc;
     }
     if (fused) {
-        ln_param_final_kernel<<<cdiv(N, 256), 256, 0, st>>>(ws, grid, N, dgamma, dbeta, accumulate_params);
+        ln_param_final_kernel<<<cdiv(N, 32), 256, 0, st>>>(ws, grid, N, dgamma, dbeta, accumulate_params);
         return nasrec_launch_status();
     }
     if (want) {
@@ -500,7 +544,7 @@ int nasrec_ln3_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* 
         if (rc) return rc;
     }
     if (fused) {
-        ln3_param_final_kernel<<<1, LN3_MAXP, 0, st>>>(ws, grid, P, dgamma, dbeta, accumulate_params);
+        ln3_param_final_kernel<<<cdiv(P, 32), 256, 0, st>>>(ws, grid, P, dgamma, dbeta, accumulate_params);
         return nasrec_launch_status();
     }
     if (want) {
