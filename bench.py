@@ -441,7 +441,8 @@ def extra_xlarge_kdd(torch, _lib, dev, flush, steps=20, warm=5, B=2048):
     """BASELINE configs[4] (per-GPU slice): NASRec-Full (xlarge: FC, DotProduct, Gating, Sum, Attention,
     EFC) supernet training on KDD shapes (3 dense + 10 sparse), 0.5M-capped tables, B=2048 per GPU."""
     from nasrec_b200 import SuperNet, ops_config_lib
-    from nasrec_b200.utils.train_utils import FusedTrainer, init_weights
+    from nasrec_b200.utils.train_utils import init_weights
+    from nasrec_b200.native import NativeTrainer
     kdd = [26274, 641708, 14848, 22122011, 1188090, 3735797, 2934102, 20004011, 4, 8]
     ne = [min(x, CAP) for x in kdd]
     torch.manual_seed(3)
@@ -450,7 +451,7 @@ def extra_xlarge_kdd(torch, _lib, dev, flush, steps=20, warm=5, B=2048):
                  sparse_input_size=10, path_sampling_strategy="default", anypath_choice="binomial-0.5").to(dev)
     m.materialize(3)
     m.apply(init_weights)
-    tr = FusedTrainer(m, lr=0.12)
+    tr = NativeTrainer(m, lr=0.12)
     pool = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in synth_pool(8, B, 3, ne, 9)]
     for i in range(warm):
         tr.step(*pool[i % 8])

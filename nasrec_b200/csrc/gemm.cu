@@ -168,9 +168,10 @@ cudaStream_t g_side = nullptr;  // optional second stream for weight-gradient GE
 // Work on the side stream runs concurrently with the main stream: it gets its own half of the workspace.
 void ws_region(cudaStream_t st, float** base, long long* n) {
     if (!g_ws) { *base = nullptr; *n = 0; return; }
-    if (!g_side) { *base = g_ws; *n = g_ws_floats; return; }
+    // always halves, attached or not, so that split-K decisions (and with them the summation order and the
+    // bits of the result) do not depend on whether a side stream is in use
     const long long half = (g_ws_floats / 2) & ~63LL;
-    *base = (st == g_side) ? g_ws + half : g_ws;
+    *base = (g_side && st == g_side) ? g_ws + half : g_ws;
     *n = half;
 }
 

@@ -139,116 +139,91 @@ __device__ __forceinline__ void store_split4(uint8_t* s_hi, uint8_t* s_lo, uint3
     *reinterpret_cast<float4*>(s_hi + off) = h;
 }
 
-// One [ROWS x 32] fp32 k-tile travels global -> registers (tile_ldg) -> (hi, lo) -> swizzled shared
-// memory (tile_sts), moved by the 256 producer threads.  The two halves are separate so that the
-// loads of k-tile t+1 are in flight while k-tile t is split and stored (register double buffering).
-// Three block-uniform layouts, each branch-free inside:
-//   0 vec16    K-contiguous rows that are 16-byte aligned: one LDG.128 per 16-byte chunk;
-//   1 contig_j K-contiguous but unaligned (weights keep the reference's odd row strides): one warp
-//              instruction reads one whole 128-byte tile row (lane = k), scalar STS;
-//   2 contig_i M/N-contiguous (dgrad/wgrad operands, sparse-axis tensors): lane = row, 4 k per thread.
-// PLAIN views (no two-level index) use pointer arithmetic instead of the general offset formula.
+// One [ROWS x 32] fp32 k-tile travels global -> registers (Stager::load) -> (hi, lo) -> swizzled shared memory
+// (Stager::store), moved by the 256 producer threads; the two halves are separate so that the loads of k-tile
+// t+1 are in flight while k-tile t is split and stored (register double buffering).
+//
+// Everything that does not depend on the k-tile is computed once per term: each thread owns NV 16-byte chunks
+// (row, 4 consecutive k) of the tile, keeps one global pointer per chunk (rows beyond the operand's extent are
+// clamped onto its last row: they only feed output rows/columns that are never stored) and the chunk's swizzled
+// shared-memory offset; a k-tile step is `ptr += step`.  Full tiles load without predicates -- one LDG.128 per
+// chunk when the view is 16-byte aligned and k-contiguous, else four LDG.32 `se` floats apart (k-contiguous but
+// unaligned rows such as the reference's 1037-float weight rows, or M/N-contiguous operands of dgrad/wgrad) --
+// and only the last, partial tile of a term takes the predicated path.  Two-level views (sparse-axis tensors) are
+// linear in k at tile granularity because their inner extent (16) divides the tile (32).
 template <int ROWS>
-struct TileRegs {
-    static constexpr int NV = (ROWS * 32 / 256 + 3) / 4 > 0 ? (ROWS * 32 / 256 + 3) / 4 : 1;   // float4 per thread
-    float4 v[NV];
-    int kind;
-};
+struct Stager {
+    static constexpr int NV = (ROWS * 8 + 255) / 256;
+    const float* ptr[NV];
+    uint32_t soff[NV];
+    long long step, se;
+    int kc0, dkc;          // chunk q covers k = 4 * (kc0 + q * dkc) .. +3 of the tile
+    int K, k0;             // term length; first k of the next tile to load
+    unsigned live;         // bit q: this thread's chunk q exists
+    bool vec;
 
-template <int ROWS, bool PLAIN>
-__device__ __forceinline__ void tile_ldg_impl(const View& v, int i0, int I, int k0, int K, int tid,
-                                              TileRegs<ROWS>& R) {
-    auto at = [&](int i, int k) -> const float* {
-        if (PLAIN) return v.p + (long long)i * v.hi_i + (long long)k * v.hi_j;
-        return v.p + voff(v, i, k);
-    };
-    constexpr int NV = TileRegs<ROWS>::NV;
-    if (v.contig_j && v.vec16 && k0 + TC_BK <= K) {
-        R.kind = 0;
-        const int r0 = tid >> 3, kc = tid & 7;
+    __device__ __forceinline__ void init(const View& v, int i0, int I, int K_, int k_start, int tid) {
+        int row0, drow;
+        if (v.contig_j) { row0 = tid >> 3; kc0 = tid & 7; drow = 32; dkc = 0; }
+        else { row0 = tid % ROWS; kc0 = tid / ROWS; drow = 0; dkc = 256 / ROWS; }
+        step = voff(v, 0, TC_BK) - voff(v, 0, 0);
+        se = voff(v, 0, 1) - voff(v, 0, 0);
+        vec = v.vec16 != 0;
+        K = K_;
+        k0 = k_start;
+        live = 0;
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
-            const int row = r0 + 32 * q;
-            R.v[q] = ldg128_pred(at(i0 + row, k0 + kc * 4), row < ROWS && i0 + row < I);
+            const int row = row0 + q * drow, kc = kc0 + q * dkc;
+            const bool ok = row < ROWS && kc < 8;
+            if (ok) live |= 1u << q;
+            const int r = ok ? row : 0, c = ok ? kc : 0;
+            int i = i0 + r;
+            i = i < I ? i : I - 1;
+            ptr[q] = v.p + voff(v, i, c * 4) + (long long)(k_start / TC_BK) * step;
+            soff[q] = sw128_off(r, c);
         }
-    } else if (v.contig_j) {
-        R.kind = 1;
-        constexpr int RPW = (ROWS + 7) / 8;                   // rows per producer warp
-        const int w = tid >> 5, lane = tid & 31;
-        const bool kok = k0 + lane < K;
-        float* f = reinterpret_cast<float*>(R.v);
+    }
+    __device__ __forceinline__ bool exhausted() const { return k0 >= K; }
+    __device__ __forceinline__ void load(float4 (&r)[NV]) {
+        if (k0 + TC_BK <= K) {
+            if (vec) {
 #pragma unroll
-        for (int r = 0; r < NV * 4; ++r) {
-            const int row = w * RPW + r;
-            f[r] = ldg_pred(at(i0 + row, k0 + lane), r < RPW && kok && row < ROWS && i0 + row < I);
-        }
-    } else {
-        R.kind = 2;
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            const int c = tid + 256 * q, row = c % ROWS, kc = c / ROWS;
-            const int i = i0 + row, k = k0 + kc * 4;
-            const bool ok = i < I && kc < 8;
-            if (PLAIN) {
-                const float* p = at(i, k);
-                const long long sj = v.hi_j;
-                R.v[q].x = ldg_pred(p, ok && k < K);
-                R.v[q].y = ldg_pred(p + sj, ok && k + 1 < K);
-                R.v[q].z = ldg_pred(p + 2 * sj, ok && k + 2 < K);
-                R.v[q].w = ldg_pred(p + 3 * sj, ok && k + 3 < K);
+                for (int q = 0; q < NV; ++q) r[q] = __ldg(reinterpret_cast<const float4*>(ptr[q]));
             } else {
-                R.v[q].x = ldg_pred(at(i, k), ok && k < K);
-                R.v[q].y = ldg_pred(at(i, k + 1), ok && k + 1 < K);
-                R.v[q].z = ldg_pred(at(i, k + 2), ok && k + 2 < K);
-                R.v[q].w = ldg_pred(at(i, k + 3), ok && k + 3 < K);
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    r[q].x = __ldg(ptr[q]);
+                    r[q].y = __ldg(ptr[q] + se);
+                    r[q].z = __ldg(ptr[q] + 2 * se);
+                    r[q].w = __ldg(ptr[q] + 3 * se);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const int k = k0 + 4 * (kc0 + q * dkc);
+                r[q].x = ldg_pred(ptr[q], k < K);
+                r[q].y = ldg_pred(ptr[q] + se, k + 1 < K);
+                r[q].z = ldg_pred(ptr[q] + 2 * se, k + 2 < K);
+                r[q].w = ldg_pred(ptr[q] + 3 * se, k + 3 < K);
             }
         }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) ptr[q] += step;
+        k0 += TC_BK;
     }
-}
-
-template <int ROWS>
-__device__ __forceinline__ void tile_ldg(const View& v, int i0, int I, int k0, int K, int tid, TileRegs<ROWS>& R) {
-    if (v.sh_i == 0 && v.sh_j == 0) tile_ldg_impl<ROWS, true>(v, i0, I, k0, K, tid, R);
-    else tile_ldg_impl<ROWS, false>(v, i0, I, k0, K, tid, R);
-}
-
-template <int ROWS>
-__device__ __forceinline__ void tile_sts(const TileRegs<ROWS>& R, uint8_t* s_hi, uint8_t* s_lo, int tid, bool split) {
-    constexpr int NV = TileRegs<ROWS>::NV;
-    if (R.kind == 0) {
-        const int r0 = tid >> 3, kc = tid & 7;
+    __device__ __forceinline__ void store(const float4 (&r)[NV], uint8_t* s_hi, uint8_t* s_lo, bool split) const {
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            const int row = r0 + 32 * q;
-            if (row < ROWS) store_split4(s_hi, s_lo, sw128_off(row, kc), R.v[q], split);
-        }
-    } else if (R.kind == 1) {
-        constexpr int RPW = (ROWS + 7) / 8;
-        const int w = tid >> 5, lane = tid & 31;
-        const float* f = reinterpret_cast<const float*>(R.v);
-#pragma unroll
-        for (int r = 0; r < NV * 4; ++r) {
-            const int row = w * RPW + r;
-            if (r < RPW && row < ROWS) {
-                const uint32_t off = sw128_off(row, lane >> 2) + (uint32_t)((lane & 3) << 2);
-                float h = f[r], l = 0.f;
-                if (split) split_tf32(f[r], h, l);
-                *reinterpret_cast<float*>(s_hi + off) = h;
-                if (split) *reinterpret_cast<float*>(s_lo + off) = l;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            const int c = tid + 256 * q, row = c % ROWS, kc = c / ROWS;
-            if (kc < 8) store_split4(s_hi, s_lo, sw128_off(row, kc), R.v[q], split);
-        }
+        for (int q = 0; q < NV; ++q)
+            if (live & (1u << q)) store_split4(s_hi, s_lo, soff[q], r[q], split);
     }
-}
+};
 
 template <int BN>
 struct TcCfg {
     static constexpr int STAGES = BN == 128 ? 3 : 4;     // 192 KB / 192 KB / 160 KB / 144 KB of shared memory
+    static constexpr int PREFETCH = BN == 128 ? 2 : (BN == 64 ? 3 : 4);   // k-tiles of global loads kept in registers
     static constexpr int A_BYTES = TC_BM * TC_BK * 4;      // 16 KB
     static constexpr int B_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -320,7 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
     if (warp < 8) {
         // ------------------------------------------------------------ producers
-        // flat walk over this split's k-tiles: (term index, k-tile inside the term)
+        // flat walk over this split's k-tiles: find the term that holds k-tile kt_begin
         int t_cur = 0, kk_cur = 0;
         {
             int kt = 0;
@@ -333,41 +308,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                 kt += nk;
             }
         }
-        TileRegs<TC_BM> ra[2];
-        TileRegs<BN> rb[2];
-        if (ntiles > 0) {
-            const Term& tm = bt.term[pr.term0 + t_cur];
-            tile_ldg<TC_BM>(tm.a, m0, pr.M, kk_cur * TC_BK, tm.K, tid, ra[0]);
-            tile_ldg<BN>(tm.b, n0, pr.N, kk_cur * TC_BK, tm.K, tid, rb[0]);
-        }
-#pragma unroll 1
-        for (int it = 0; it < ntiles; it += 2) {
+        Stager<TC_BM> sa;
+        Stager<BN> sb;
+        // register ring of D k-tiles: tile t+D is requested right after tile t has been stored, so D-1 tiles
+        // of global loads are in flight while one is split -- the k-loop is otherwise bound by load latency
+        // (one CTA per SM, 8 producer warps).
+        constexpr int D = Cfg::PREFETCH;
+        float4 ra[D][Stager<TC_BM>::NV], rb[D][Stager<BN>::NV];
+        auto begin_term = [&](int t, int kk) {
+            const Term& tm = bt.term[pr.term0 + t];
+            sa.init(tm.a, m0, pr.M, tm.K, kk * TC_BK, tid);
+            sb.init(tm.b, n0, pr.N, tm.K, kk * TC_BK, tid);
+        };
+        auto load_next = [&](float4 (&qa)[Stager<TC_BM>::NV], float4 (&qb)[Stager<BN>::NV]) {
+            while (sa.exhausted() && t_cur + 1 < pr.nterm) begin_term(++t_cur, 0);
+            sa.load(qa);
+            sb.load(qb);
+        };
+        if (ntiles > 0) begin_term(t_cur, kk_cur);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < D; ++h)
+            if (h < ntiles) load_next(ra[h], rb[h]);
+#pragma unroll 1
+        for (int it = 0; it < ntiles; it += D) {
+#pragma unroll
+            for (int h = 0; h < D; ++h) {
                 const int cur = it + h;
                 if (cur < ntiles) {
-                    // advance to the next k-tile and put its loads in flight before touching `cur`'s data
-                    int t_nxt = t_cur, kk_nxt = kk_cur + 1;
-                    if (kk_nxt * TC_BK >= bt.term[pr.term0 + t_cur].K) {
-                        ++t_nxt;
-                        kk_nxt = 0;
-                    }
-                    if (cur + 1 < ntiles) {
-                        const Term& tn = bt.term[pr.term0 + t_nxt];
-                        tile_ldg<TC_BM>(tn.a, m0, pr.M, kk_nxt * TC_BK, tn.K, tid, ra[h ^ 1]);
-                        tile_ldg<BN>(tn.b, n0, pr.N, kk_nxt * TC_BK, tn.K, tid, rb[h ^ 1]);
-                    }
                     const int s = cur % Cfg::STAGES;
                     const uint32_t ph = (uint32_t)(cur / Cfg::STAGES) & 1u;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
-                    tile_sts<TC_BM>(ra[h], st, st + Cfg::A_BYTES, tid, nprod > 1);
-                    tile_sts<BN>(rb[h], st + 2 * Cfg::A_BYTES, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, tid, nprod > 1);
+                    sa.store(ra[h], st, st + Cfg::A_BYTES, nprod > 1);
+                    sb.store(rb[h], st + 2 * Cfg::A_BYTES, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, nprod > 1);
                     fence_proxy_async_smem();          // every writer orders its generic-proxy stores
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_full + 8 * s);
-                    t_cur = t_nxt;
-                    kk_cur = kk_nxt;
+                    if (cur + D < ntiles) load_next(ra[h], rb[h]);
                 }
             }
         }

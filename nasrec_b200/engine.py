@@ -29,6 +29,10 @@ def call(name: str, *args):
 E = 16                 # embedding dim (supernet.py:224)
 LN_EPS = 1e-5
 FUSED_CALLS = True     # one C call per operator direction (nasrec_linear_ln_* / nasrec_sproj_ln_*)
+# When the library forks weight-gradient GEMMs onto a side stream (nasrec_set_side_stream), the scratch
+# buffers those GEMMs read must outlive the closure that allocated them: they are parked here until the
+# caller has joined the side stream (FusedTrainer.forward_backward).
+OVERLAP_KEEP: Optional[list] = None
 
 
 class Var:
@@ -232,6 +236,8 @@ def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[
                  dsp, flags, ns, _p(W.t), ldw, n_off, _p(gw) if gw is not None else None,
                  _p(gb) if gb is not None else None, _p(ln[0].grad(True)) if want_ln else None,
                  _p(ln[1].grad(True)) if want_ln else None, _p(dz))
+            if OVERLAP_KEEP is not None:
+                OVERLAP_KEEP.append(dz)
             return
         # general path: the same source feeds two segments (Sum with left == right, modules.py:470-487)
         if ln is not None:
@@ -309,6 +315,8 @@ def sproj_ln(tape: Tape, seg_list: Sequence[Seg], B: int, W: PVar, b: Optional[P
                  sp, dsp, flags, ns, _p(W.t), ldw, _p(gw) if gw is not None else None,
                  _p(gb) if gb is not None else None, _p(ln[0].grad(True)) if want_ln else None,
                  _p(ln[1].grad(True)) if want_ln else None, _p(dz), _p(ws) if ws is not None else None)
+            if OVERLAP_KEEP is not None:
+                OVERLAP_KEEP.extend((dz, ws))
             return
         if ln is not None:
             call("nasrec_ln3_bwd", _p(out.g, out_off), out_bstride, p_out, _p(z), P * E, B, P, gam, bet, pm, pr,

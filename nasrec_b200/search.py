@@ -154,16 +154,34 @@ def binary_metrics_device(logits: torch.Tensor, y: torch.Tensor) -> Tuple[float,
 class SubnetEvaluator:
     """Scores many candidates against shared, resident supernet weights."""
 
-    def __init__(self, model: SuperNet):
+    def __init__(self, model: SuperNet, use_native: bool = True):
         assert not model._fixed, "one-shot scoring needs the weight-sharing supernet"
         self.model = model
         self._emb_cache: Dict[int, torch.Tensor] = {}
+        self.use_native = use_native            # C++ executor (nasrec_b200/native.py) when the model allows it
+        self._net = None
+        self._native_checked = False
+
+    def _native(self):
+        if self.use_native and not self._native_checked:
+            from .native import NativeNet
+            self._native_checked = True
+            if NativeNet.unsupported_reason(self.model) is None:
+                self._net = NativeNet(self.model, state_of=None, pgrad_bytes=1 << 20)
+        return self._net
 
     @torch.no_grad()
     def logits(self, choice, int_x: torch.Tensor, cat_x: torch.Tensor) -> torch.Tensor:
         m = self.model
         if m._needs_materialize():
             m.materialize(int_x.shape[1])
+        net = self._native()
+        if net is not None:
+            from .native import NativeNet
+            net.refresh()
+            rows = self._gathered(cat_x) if not any(e.weight.requires_grad for e in m._embedding) else None
+            return net.forward(NativeNet.encode_choice(choice["macro"], choice["micro"]), int_x.contiguous(),
+                               cat_x if rows is None else None, emb_rows=rows)
         run = Run(Tape(False), emb_cache=self._emb_cache)
         out = m._run_network(run, Var(int_x), cat_x, choice["macro"], choice["micro"])
         return out.t

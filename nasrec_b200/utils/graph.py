@@ -17,8 +17,9 @@ from .train_utils import FusedTrainer
 class GraphedFusedTrainer:
     """Wraps a FusedTrainer whose model always draws the same choice."""
 
-    def __init__(self, trainer: FusedTrainer, warmup_steps: int = 0):
+    def __init__(self, trainer: FusedTrainer, warmup_steps: int = 0, overlap_wgrad: bool = True):
         self.trainer = trainer
+        self.overlap_wgrad = overlap_wgrad      # weight-gradient GEMMs become a parallel branch of the graph
         self.warmup_steps = warmup_steps
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._static = None
@@ -54,5 +55,10 @@ class GraphedFusedTrainer:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._out = self.trainer.step(*self._static, lr=lr)
+        if self.overlap_wgrad:
+            self.trainer.side_stream = torch.cuda.Stream()
+        try:
+            with torch.cuda.graph(self.graph):
+                self._out = self.trainer.step(*self._static, lr=lr)
+        finally:
+            self.trainer.side_stream = None

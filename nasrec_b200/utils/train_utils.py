@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -202,6 +204,8 @@ class FusedTrainer:
         self._emb_ptrs = None
         self.last_total_norm: Optional[torch.Tensor] = None
         self.defer_sparse = False
+        # set by GraphedFusedTrainer during capture: weight-gradient GEMMs fork onto this stream
+        self.side_stream: Optional[torch.cuda.Stream] = None
 
     def _state_of(self, p: torch.Tensor) -> torch.Tensor:
         s = self.state.get(id(p))
@@ -234,7 +238,21 @@ class FusedTrainer:
         logits = model._run_network(run, Var(int_x.contiguous()), cat.contiguous(), macro, micro)
         loss, dl = eng.bce_with_logits(logits.t, y, grad_scale=grad_scale)
         logits.g = dl
-        tape.backward()
+        if self.side_stream is None:
+            tape.backward()
+        else:
+            lib = _lib.LIB.load().cdll
+            eng.OVERLAP_KEEP = keep = []
+            lib.nasrec_set_side_stream(ctypes.c_void_p(self.side_stream.cuda_stream))
+            try:
+                tape.backward()
+                rc = lib.nasrec_side_join(ctypes.c_void_p(_lib.stream_ptr()))
+            finally:
+                lib.nasrec_set_side_stream(None)
+                eng.OVERLAP_KEEP = None
+            if rc != 0:
+                raise RuntimeError("nasrec_side_join failed: %d" % rc)
+            self._keep = keep            # released when the next step replaces it (after the join in stream order)
         return logits.t, loss, run, (sink[0] if sink else None)
 
     def apply(self, run: Run, sparse, lr: Optional[float] = None):

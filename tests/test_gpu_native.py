@@ -150,3 +150,22 @@ def test_native_arena_growth_and_fallback():
     bx = tuple(t.cuda() for t in orc.synth_batch(16, mm["nd"], mm["num_embeddings"], seed=1))
     tr.step(*bx)
     assert tr.net is None and "fixed" in tr.fallback_reason
+
+
+def test_subnet_evaluator_native_equals_python_engine():
+    """One-shot scoring through the C++ executor (shared pre-gathered rows) == the Python engine."""
+    from nasrec_b200.search import SubnetEvaluator
+    meta, _ = load_golden("supernet_xlarge_criteo")
+    smeta, _ = load_golden("samplers")
+    cfg, ne, nd = meta["cfg"], meta["num_embeddings"], meta["nd"]
+    m = _model(cfg, ne, nd, meta["shapes"], 31)
+    m.requires_grad_(False)
+    cands = smeta["ea_candidates"]["xlarge"][:3]
+    batches = [tuple(t.cuda() for t in orc.synth_batch(96, nd, ne, seed=700 + i)) for i in range(3)]
+    a = SubnetEvaluator(m, use_native=True)
+    b = SubnetEvaluator(m, use_native=False)
+    ra, rb = a.score(cands, batches), b.score(cands, batches)
+    assert a._net is not None
+    assert ra == rb
+    for ch in cands:
+        assert torch.equal(a.logits(ch, batches[0][0], batches[0][1]), b.logits(ch, batches[0][0], batches[0][1]))
