@@ -108,10 +108,23 @@ __global__ void __launch_bounds__(1024) emb_sort_reduce_kernel(const int64_t* __
     float sq = 0.f;
     for (int u = tid >> 4; u < U; u += nt >> 4) {
         const int s0 = seg[u], s1 = seg[u + 1];
+        // ascending sample order (fixed summation order); the loads of 8 duplicates are issued together so that a
+        // hot row (hundreds of duplicates under Zipf ids) costs one memory latency per 8 samples, not per sample
         float acc = 0.f;
-        for (int i = s0; i < s1; ++i) {
+        int i = s0;
+        for (; i + 8 <= s1; i += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned b = (unsigned)(keys[i + j] & 0xffffffffu);
+                v[j] = __ldg(gout + ((long long)b * F + f) * NASREC_EMB_DIM + e);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += v[j];
+        }
+        for (; i < s1; ++i) {
             const unsigned b = (unsigned)(keys[i] & 0xffffffffu);
-            acc += gout[((long long)b * F + f) * NASREC_EMB_DIM + e];
+            acc += __ldg(gout + ((long long)b * F + f) * NASREC_EMB_DIM + e);
         }
         row_grad[((long long)f * B + u) * NASREC_EMB_DIM + e] = acc;
         if (e == 0) uniq[(long long)f * B + u] = (int64_t)(keys[s0] >> 32);

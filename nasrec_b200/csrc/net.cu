@@ -92,6 +92,11 @@ struct Net {
     int64_t* uniq = nullptr; int* nuniq = nullptr; float* row_grad = nullptr; float* sumsq = nullptr; int sB = 0;
     bool have_sparse = false;
     bool overlap = false;
+    // data-parallel overlap: called during backward whenever a block's parameter gradients are final, with the
+    // byte range of the gradient bucket that was sealed (the caller all-reduces it while backward continues)
+    void (*seal_cb)(int64_t offset_bytes, int64_t nbytes) = nullptr;
+    size_t seal_min_bytes = 12u << 20;
+    std::vector<size_t> block_mark;           // tape length at the start of each block's forward
 
     Var* var(int64_t n, bool alloc = true) {
         vars.emplace_back();
@@ -730,6 +735,7 @@ void reset_step(Net& n, cudaStream_t st) {
     for (int pi : n.touched) n.par[pi].g = nullptr;
     n.touched.clear();
     n.ref_order.clear();
+    n.block_mark.clear();
     ++n.step_id;
     n.have_sparse = false;
     n.emb_gout = nullptr;
@@ -770,6 +776,7 @@ Var* forward(Net& n, const int* choice, const float* int_x, const int64_t* cat_x
         }
         DSrc d;
         SSrc s;
+        n.block_mark.push_back(n.tape.size());
         run_block(n, i, ch[i], dsrc, ssrc, have, B, d, s);
         dsrc.push_back(d);
         ssrc.push_back(s);
@@ -847,6 +854,12 @@ int nasrec_net_set_requires_grad(void* net, const int* req, int n_params) {
 
 int nasrec_net_set_overlap(void* net, int on) { ((Net*)net)->overlap = on != 0; return 0; }
 
+int nasrec_net_set_seal_callback(void* net, void (*cb)(int64_t, int64_t)) {
+    CHECK_ARG(net);
+    ((Net*)net)->seal_cb = cb;
+    return 0;
+}
+
 // Forward only (candidate scoring / inference).  emb_rows: optional pre-gathered [B,F,16] rows.
 int nasrec_net_forward(void* net, const int* choice, const float* int_x, const int64_t* cat_x, const float* emb_rows,
                        int B, float* logits, void* stream) {
@@ -873,9 +886,24 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
         out->g = n->act.alloc(B);
         ck(nasrec_bce_fwd_bwd(out->t, y, B, grad_scale, loss, out->g, st));
         ck((int)cudaMemcpyAsync(logits, out->t, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
-        for (auto it = n->tape.rbegin(); it != n->tape.rend(); ++it) (*it)();
+        // Backward.  A parameter belongs to exactly one block (or the head), so when the tape index drops below a
+        // block's first record every gradient written so far is final: seal that part of the bucket.
+        size_t sealed = 0;
+        int mark = (int)n->block_mark.size() - 1;
+        for (size_t i = n->tape.size(); i-- > 0;) {
+            n->tape[i]();
+            if (n->seal_cb && mark >= 0 && i == n->block_mark[mark]) {
+                --mark;
+                if (n->pg.off >= sealed + n->seal_min_bytes) {       // few, large exchanges: each one costs host time
+                    if (n->overlap) ck(nasrec_side_join(st), 0);     // the sealed range includes side-stream wgrads
+                    n->seal_cb((int64_t)sealed, (int64_t)(n->pg.off - sealed));
+                    sealed = n->pg.off;
+                }
+            }
+        }
         n->tape.clear();
         if (n->overlap) ck(nasrec_side_join(st), 0);
+        if (n->seal_cb && n->pg.off > sealed) n->seal_cb((int64_t)sealed, (int64_t)(n->pg.off - sealed));
         n->pg_dirty = n->pg.off;
     });
     if (rc) n->pg_dirty = n->pg.cap;       // a failed step may have scribbled anywhere in the bucket: clear all of it next time

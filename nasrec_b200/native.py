@@ -33,6 +33,7 @@ _PROTOS = {
     "nasrec_net_set_arenas": ([_vp, _vp, _l, _vp, _l], _i),
     "nasrec_net_set_requires_grad": ([_vp, _vp, _i], _i),
     "nasrec_net_set_overlap": ([_vp, _i], _i),
+    "nasrec_net_set_seal_callback": ([_vp, _vp], _i),
     "nasrec_net_forward": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp], _i),
     "nasrec_net_forward_backward": ([_vp, _vp, _vp, _vp, _vp, _i, _fl, _vp, _vp, _vp], _i),
     "nasrec_net_grad_bucket": ([_vp, _vp, _vp], _i),
@@ -199,7 +200,7 @@ class NativeNet:
             na, np_ = 2 * a, 2 * p
         if max(na, np_) > (64 << 30):
             raise MemoryError("native executor arena would exceed 64 GiB")
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.synchronize()                # also NCCL work that may still be reading the old gradient bucket
         self.act = self.pg = None
         self._alloc_arenas(na, np_)
 
@@ -279,6 +280,15 @@ class NativeNet:
             self.handle, choice.ctypes.data, int_x.data_ptr(), cat_x.data_ptr(), y.data_ptr(), B, float(grad_scale),
             logits.data_ptr(), loss.data_ptr(), st))
         return logits, loss
+
+    SEAL_CB = C.CFUNCTYPE(None, C.c_int64, C.c_int64)
+
+    def set_seal_callback(self, fn):
+        """fn(offset_bytes, nbytes) is called during forward_backward each time a block's parameter gradients are
+        final (see nasrec_net_set_seal_callback); None switches it off."""
+        self._seal_cb = self.SEAL_CB(fn) if fn is not None else None          # keep the thunk alive
+        _check(_fn("nasrec_net_set_seal_callback")(self.handle, C.cast(self._seal_cb, C.c_void_p) if fn else None),
+               "nasrec_net_set_seal_callback")
 
     def grad_bucket(self) -> torch.Tensor:
         """The step's dense parameter gradients as ONE flat fp32 view of the gradient arena

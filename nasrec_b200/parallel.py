@@ -135,6 +135,14 @@ class NativeDataParallelTrainer(DataParallelTrainer):
         from .native import NativeTrainer
         self._nt = NativeTrainer(model, lr, eps, clip)
         self._nt.state = self.state                       # one set of Adagrad accumulators for both paths
+        self.overlap_comm = True
+        self._cb_net = None
+        self._pending: list = []
+
+    def _seal(self, off: int, nbytes: int):
+        """Called by the executor (on this thread) when gradient-bucket bytes [off, off+nbytes) are final."""
+        chunk = self._cb_net.pg[off: off + nbytes].view(torch.float32)
+        self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def step(self, int_x, cat_x, y, lr: Optional[float] = None):
         net = self._nt._native(int_x)
@@ -148,19 +156,33 @@ class NativeDataParallelTrainer(DataParallelTrainer):
         net.refresh()
         cat = (cat_x if cat_x.dtype == torch.int64 else cat_x.long()).contiguous()
         with _lib.pin_stream():
+            # Sealed ranges of the gradient bucket are all-reduced while backward is still running: NCCL works on
+            # its own stream, ordered after the kernels already queued here (late blocks hold the widest weights and
+            # run their backward first, so most of the exchange hides behind the rest of the backward pass).
+            self._pending = []
+            # the ids are known before the step starts: gather them behind the forward pass
+            cat_all = torch.empty((self.world * cat.shape[0], cat.shape[1]), dtype=cat.dtype, device=cat.device)
+            ids_handle = dist.all_gather_into_tensor(cat_all, cat, group=self.group, async_op=True)
+            if self.overlap_comm and net is not self._cb_net:
+                net.set_seal_callback(self._seal)
+                self._cb_net = net
             self._nt._fork_on(net)
             try:
                 logits, loss = net.forward_backward(self._nt._choice(), int_x.contiguous(), cat, y.contiguous(),
                                                     grad_scale=1.0 / self.world)
             finally:
                 self._nt._fork_off()
-            bucket = net.grad_bucket()
-            if bucket.numel():
-                dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group)
+            if self.overlap_comm:
+                for h in self._pending:
+                    h.wait()
+            else:
+                bucket = net.grad_bucket()
+                if bucket.numel():
+                    dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group)
             raw = net.sparse_raw(cat)
+            ids_handle.wait()
             if raw is not None:
-                cat_all, g_all = allgather_cat(cat, self.group), allgather_cat(raw, self.group)
-                net.sparse_reduce(cat_all, g_all)
+                net.sparse_reduce(cat_all, allgather_cat(raw, self.group))
             norm = net.apply(self.lr if lr is None else lr, self.eps, self.clip)
         self.last_total_norm = norm[0:1]
         return logits, loss

@@ -5,7 +5,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 from nasrec_b200 import SuperNet, ops_config_lib
-from nasrec_b200.parallel import DataParallelTrainer
+from nasrec_b200.parallel import DataParallelTrainer, NativeDataParallelTrainer
 from nasrec_b200.utils.train_utils import FusedTrainer, init_weights
 import bench
 
@@ -23,7 +23,11 @@ def make():
 
 B = 256
 pools = [bench.synth_pool(4, B, 13, ne, seed=100 + r) for r in range(world)]
-m = make(); tr = DataParallelTrainer(m, lr=0.12)
+kind = sys.argv[1] if len(sys.argv) > 1 else "native"      # python | native | native-noverlap
+m = make()
+tr = DataParallelTrainer(m, lr=0.12) if kind == "python" else NativeDataParallelTrainer(m, lr=0.12)
+if kind == "native-noverlap":
+    tr.overlap_comm = False
 for i in range(4):
     b = tuple(torch.from_numpy(a).to(dev) for a in pools[rank][i])
     tr.step(*b)
@@ -45,5 +49,6 @@ if rank == 0:
     for (n, p), q in zip(m.named_parameters(), m1.parameters()):
         d = float((p - q).abs().max() / (q.abs().max() + 1e-12))
         worst = max(worst, d)
-    print("replicas bit-identical:", same, "| dp(2x%d) vs single(%d) max rel weight diff after 4 steps: %.2e" % (B, world * B, worst), flush=True)
+    print(kind, "| native path used:", getattr(getattr(tr, "_nt", None), "net", None) is not None,
+          "| replicas bit-identical:", same, "| dp(2x%d) vs single(%d) max rel weight diff after 4 steps: %.2e" % (B, world * B, worst), flush=True)
 dist.destroy_process_group()
