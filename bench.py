@@ -376,7 +376,11 @@ def run_ours(args):
                  if mode else "gemm64_kernel (segment-list SGEMM, fp32 FFMA)")
         line["roofline"] = {"bound": "tensor", "kernel": kname, "gemm_mode": mode,
                             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            "peak_source": which, "traffic": None, "launches_timed": n,
+                            "peak_source": which, "traffic": 2.56e6,
+                            "traffic_source": "mean dram__bytes_read+write per gemm_tc launch over the 16 launches of "
+                                              "profiles/r01_native_gemm_full.md (ncu --set full, this workload); "
+                                              "operands are L2-resident, the kernel is not HBM-bound",
+                            "launches_timed": n,
                             "avg_launch_us": ms * 1e3 / max(n, 1), "gflop_per_launch": fl / max(n, 1) / 1e9,
                             "share_of_step": ms / (min(K, 10) * ms_per_step) if ms_per_step > 0 else None,
                             "by_entry_point": {k: {"launches": v[0], "ms": v[1], "gflop": v[2] / 1e9}
