@@ -296,7 +296,8 @@ int nasrec_net_set_overlap(void* net, int on);      /* join the side stream (nas
 /* Data-parallel overlap: during nasrec_net_forward_backward, cb(offset_bytes, nbytes) is called on the host each
  * time a block's parameter gradients are final -- the byte range of the gradient bucket sealed since the last call,
  * already ordered on `stream` -- so the caller can start all-reducing it while backward continues.  NULL: off. */
-int nasrec_net_set_seal_callback(void* net, void (*cb)(int64_t offset_bytes, int64_t nbytes));
+typedef void (*nasrec_seal_cb_t)(int64_t offset_bytes, int64_t nbytes);
+int nasrec_net_set_seal_callback(void* net, nasrec_seal_cb_t cb);
 /* logits [B] for one subnet; emb_rows (optional) = [B,F,16] rows gathered once and shared by many candidates. */
 int nasrec_net_forward(void* net, const int* choice, const float* int_x, const int64_t* cat_x, const float* emb_rows,
                        int B, float* logits, void* stream);

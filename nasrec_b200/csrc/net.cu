@@ -854,7 +854,7 @@ int nasrec_net_set_requires_grad(void* net, const int* req, int n_params) {
 
 int nasrec_net_set_overlap(void* net, int on) { ((Net*)net)->overlap = on != 0; return 0; }
 
-int nasrec_net_set_seal_callback(void* net, void (*cb)(int64_t, int64_t)) {
+int nasrec_net_set_seal_callback(void* net, nasrec_seal_cb_t cb) {
     CHECK_ARG(net);
     ((Net*)net)->seal_cb = cb;
     return 0;
