@@ -166,6 +166,7 @@ __device__ __forceinline__ void store_row16(float* p, const float* v) {
 __global__ void __launch_bounds__(LMAX) attn_fwd_kernel(const float* __restrict__ x, long long xbs, int L,
                                                         int s_live, const __grid_constant__ AttnPtrs ap,
                                                         float* __restrict__ y, long long ybs, int B) {
+    pdl_enter();
     __shared__ float P[NPARAM];
     __shared__ float Ks[LMAX * ST], Vs[LMAX * ST];
     const int t = threadIdx.x;
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(LMAX) attn_bwd_kernel(const float* __restrict_
                                                         int s_live, const __grid_constant__ AttnPtrs ap,
                                                         float* __restrict__ dx, long long dxbs,
                                                         float* __restrict__ ws, int B) {
+    pdl_enter();
     extern __shared__ float sm[];
     float* P = sm + S_P;
     float *Ks = sm + S_KS, *Vs = sm + S_VS, *Qs = sm + S_QS, *DOs = sm + S_DOS;
@@ -422,6 +424,7 @@ __global__ void __launch_bounds__(LMAX) attn_bwd_kernel(const float* __restrict_
 
 __global__ void attn_param_reduce_kernel(const float* __restrict__ ws, int nblk, float* __restrict__ dparams,
                                          int accumulate) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NPARAM) return;
     float acc = 0.f;
@@ -453,7 +456,7 @@ int nasrec_attn_fwd(const float* x, int64_t x_bstride, int L, int s_live, const 
     AttnPtrs ap;
     if (fill_ptrs(ap, params)) return NASREC_EINVAL;
     const int grid = B < 148 * 16 ? B : 148 * 16;
-    attn_fwd_kernel<<<grid, LMAX, 0, as_stream(stream)>>>(x, x_bstride, L, s_live, ap, y, y_bstride, B);
+    nasrec_launch(attn_fwd_kernel, grid, LMAX, 0, as_stream(stream), x, x_bstride, L, s_live, ap, y, y_bstride, B);
     return nasrec_launch_status();
 }
 
@@ -474,11 +477,11 @@ int nasrec_attn_bwd(const float* dy, int64_t dy_bstride, const float* x, int64_t
     }
     const int grid = attn_grid(B);
     cudaStream_t st = as_stream(stream);
-    attn_bwd_kernel<<<grid, LMAX, smem, st>>>(dy, dy_bstride, x, x_bstride, L, s_live, ap, dx, dx_bstride, ws, B);
+    nasrec_launch(attn_bwd_kernel, grid, LMAX, smem, st, dy, dy_bstride, x, x_bstride, L, s_live, ap, dx, dx_bstride, ws, B);
     int rc = nasrec_launch_status();
     if (rc) return rc;
     if (dparams) {
-        attn_param_reduce_kernel<<<cdiv(NPARAM, 256), 256, 0, st>>>(ws, grid, dparams, accumulate_params);
+        nasrec_launch(attn_param_reduce_kernel, cdiv(NPARAM, 256), 256, 0, st, ws, grid, dparams, accumulate_params);
         return nasrec_launch_status();
     }
     return 0;

@@ -70,6 +70,35 @@ __device__ __forceinline__ float ld_pred(const float* p, bool pred) {     // coh
     return v;
 }
 
+// ---- programmatic dependent launch -------------------------------------------------------------
+// A training step is ~210 small dependent kernels; between two of them the GPU idles for the launch latency of
+// the second (~1-2 us).  Every kernel of the library is launched with the programmatic-stream-serialization
+// attribute and starts with pdl_enter(): it lets its successor be scheduled at once (launch_dependents) and then
+// waits for its own predecessors to finish and flush (wait) before touching global memory -- so the successor's
+// launch, its CTA set-up and any prologue ahead of its wait overlap the tail of the running kernel.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_trigger();
+    pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t nasrec_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // library scratch attached with nasrec_set_workspace (gemm.cu); stream-ordered reuse by every kernel family
 void nasrec_internal_workspace(float** ws, long long* nfloats);
 // optional second stream on which the op-level backward entry points issue weight-gradient work

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) emb_gather_kernel(const float* const* __r
                                                          const int64_t* __restrict__ idx,
                                                          float* __restrict__ out, long long n_pairs, int F,
                                                          int* err_flag) {
+    pdl_enter();
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long pair = t >> 2;          // (b,f) flattened, same order as idx and out
     if (pair >= n_pairs) return;
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(1024) emb_sort_reduce_kernel(const int64_t* __
                                                                float* __restrict__ row_grad,
                                                                float* __restrict__ sumsq,
                                                                int* __restrict__ seg_scratch) {
+    pdl_enter();
     extern __shared__ unsigned long long keys[];
     __shared__ int wsum[32];
     __shared__ float red[34];
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(256) emb_to_dense_kernel(const int64_t* __rest
                                                            const int* __restrict__ nuniq,
                                                            const float* __restrict__ row_grad,
                                                            float* const* __restrict__ grad_tables, int B) {
+    pdl_enter();
     const int f = blockIdx.y;
     const int U = nuniq[f];
     const int e = threadIdx.x & 15;
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(256) emb_adagrad_kernel(const int64_t* __restr
                                                           float* const* __restrict__ tables,
                                                           float* const* __restrict__ states, int B, float lr,
                                                           float eps, const float* __restrict__ clip_coef) {
+    pdl_enter();
     const int f = blockIdx.y;
     const int U = nuniq[f];
     const int e = threadIdx.x & 15;
@@ -179,7 +183,7 @@ int nasrec_emb_gather_fwd(const float* const* tables, const int64_t* num_rows, c
                           int B, int F, int* err_flag, void* stream) {
     CHECK_ARG(tables && num_rows && idx && out && B > 0 && F > 0);
     const long long n_pairs = (long long)B * F;
-    emb_gather_kernel<<<cdiv(n_pairs * 4, 256), 256, 0, as_stream(stream)>>>(tables, num_rows, idx, out, n_pairs, F,
+    nasrec_launch(emb_gather_kernel, cdiv(n_pairs * 4, 256), 256, 0, as_stream(stream), tables, num_rows, idx, out, n_pairs, F,
                                                                             err_flag);
     return nasrec_launch_status();
 }
@@ -199,7 +203,7 @@ int nasrec_emb_grad_sort_reduce(const int64_t* idx, const float* gout, int B, in
         attr_set = true;
     }
     const int threads = Bpad >= 1024 ? 1024 : (Bpad < 64 ? 64 : Bpad);
-    emb_sort_reduce_kernel<<<F, threads, smem, as_stream(stream)>>>(idx, gout, B, Bpad, F, uniq, nuniq, row_grad,
+    nasrec_launch(emb_sort_reduce_kernel, F, threads, smem, as_stream(stream), idx, gout, B, Bpad, F, uniq, nuniq, row_grad,
                                                                     sumsq, seg_scratch);
     return nasrec_launch_status();
 }
@@ -208,7 +212,7 @@ int nasrec_emb_grad_to_dense(const int64_t* uniq, const int* nuniq, const float*
                              float* const* grad_tables, int B, int F, void* stream) {
     CHECK_ARG(uniq && nuniq && row_grad && grad_tables && B > 0 && F > 0);
     dim3 grid(cdiv(B, 16), F);
-    emb_to_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(uniq, nuniq, row_grad, grad_tables, B);
+    nasrec_launch(emb_to_dense_kernel, grid, 256, 0, as_stream(stream), uniq, nuniq, row_grad, grad_tables, B);
     return nasrec_launch_status();
 }
 
@@ -217,7 +221,7 @@ int nasrec_emb_rowwise_adagrad(const int64_t* uniq, const int* nuniq, const floa
                                void* stream) {
     CHECK_ARG(uniq && nuniq && row_grad && tables && states && B > 0 && F > 0);
     dim3 grid(cdiv(B, 16), F);
-    emb_adagrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(uniq, nuniq, row_grad, tables, states, B, lr, eps,
+    nasrec_launch(emb_adagrad_kernel, grid, 256, 0, as_stream(stream), uniq, nuniq, row_grad, tables, states, B, lr, eps,
                                                             clip_coef);
     return nasrec_launch_status();
 }

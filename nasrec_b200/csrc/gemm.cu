@@ -44,6 +44,7 @@ __device__ __forceinline__ void load_tile(float (*S)[BM + PADM], const View& v, 
 }
 
 __global__ void __launch_bounds__(256) gemm64_kernel(const __grid_constant__ Batch bt) {
+    pdl_enter();
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
     int z = blockIdx.z, pi = 0;
@@ -134,6 +135,7 @@ struct RedBatch {
 
 // Deterministic second stage of split-K: fixed-order sum of the partials (+bias, +in-place accumulate).
 __global__ void splitk_reduce_kernel(const __grid_constant__ RedBatch rb) {
+    pdl_enter();
     const RedSeg& s = rb.seg[blockIdx.y];
     const long long total = (long long)s.M * s.N;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -157,7 +159,7 @@ int launch_reduce(const RedBatch& rb, cudaStream_t st) {
     long long gx = (maxtot + 255) / 256;
     if (gx > 1024) gx = 1024;
     dim3 grid((unsigned)gx, rb.nseg);
-    splitk_reduce_kernel<<<grid, 256, 0, st>>>(rb);
+    nasrec_launch(splitk_reduce_kernel, grid, 256, 0, st, rb);
     return nasrec_launch_status();
 }
 
@@ -251,7 +253,7 @@ int launch(Batch& bt, cudaStream_t st) {
     }
     dim3 grid(cdiv(maxN, BN), cdiv(maxM, BM), totz);
     if (grid.y > 65535 || grid.z > 65535) return NASREC_ETOOBIG;
-    gemm64_kernel<<<grid, 256, 0, st>>>(bt);
+    nasrec_launch(gemm64_kernel, grid, 256, 0, st, bt);
     return nasrec_launch_status();
 }
 

@@ -239,6 +239,7 @@ struct TcCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Batch bt, int nprod) {
+    pdl_trigger();
     using Cfg = TcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t s_tmem_base;
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
+    pdl_wait();          // everything above (problem lookup, barrier init, TMEM allocation) overlapped the predecessor
 
     if (warp < 8) {
         // ------------------------------------------------------------ producers
@@ -472,7 +474,7 @@ inline int launch_tc_bn(const Batch& bt, int maxM, int maxN, int totz, int nprod
     }
     dim3 grid((maxN + BN - 1) / BN, (maxM + TC_BM - 1) / TC_BM, totz);
     if (grid.y > 65535 || grid.z > 65535) return NASREC_ETOOBIG;
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(bt, nprod);
+    nasrec_launch(gemm_tc_kernel<BN>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, bt, nprod);
     return (int)cudaGetLastError();
 }
 

@@ -21,6 +21,7 @@ __device__ __forceinline__ void tril_pair(int r, int& i, int& j) {
 __global__ void __launch_bounds__(256) dot_tril_fwd_kernel(const float* __restrict__ x, long long ldx,
                                                            const float* __restrict__ y, long long ybs, int P,
                                                            float* __restrict__ R, long long ldr, int B) {
+    pdl_enter();
     __shared__ float T[TMAX][17];
     const int Tn = P + 1, NR = Tn * (Tn - 1) / 2;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) dot_tril_bwd_kernel(const float* __restri
                                                            const float* __restrict__ y, long long ybs, int P,
                                                            float* __restrict__ dx, long long lddx,
                                                            float* __restrict__ dy, long long dybs, int B) {
+    pdl_enter();
     __shared__ float T[TMAX][17];
     __shared__ float G[TMAX * (TMAX - 1) / 2];
     const int Tn = P + 1, NR = Tn * (Tn - 1) / 2;
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(256) dot_tril_bwd_kernel(const float* __restri
 // ------------------------------------------------------------------ FM
 __global__ void __launch_bounds__(256) fm_fwd_kernel(const float* __restrict__ x, long long xbs, int rows,
                                                      float* __restrict__ ix, int B) {
+    pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * 16) return;
     const int b = t >> 4, e = t & 15;
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(256) fm_bwd_kernel(const float* __restrict__ d
                                                      long long xbs, int rows, const float* __restrict__ dx_in,
                                                      long long dxin_bs, float* __restrict__ dx, long long dxbs,
                                                      int B) {
+    pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * 16) return;
     const int b = t >> 4, e = t & 15;
@@ -118,6 +122,7 @@ struct SegPack {
 
 __global__ void gate_fwd_kernel(const float* __restrict__ pre, long long ldp, const __grid_constant__ SegPack sp,
                                 float* __restrict__ out, long long ldo, int M) {
+    pdl_enter();
     const nasrec_seg_t& s = sp.a[blockIdx.y];
     const int w = (int)s.width, ko = sp.koff[blockIdx.y];
     const long long total = (long long)M * w;
@@ -133,6 +138,7 @@ __global__ void gate_fwd_kernel(const float* __restrict__ pre, long long ldp, co
 __global__ void gate_bwd_kernel(const float* __restrict__ dout, long long ldo, const float* __restrict__ pre,
                                 long long ldp, const __grid_constant__ SegPack sp, float* __restrict__ dpre,
                                 long long lddp, int M, int accumulate) {
+    pdl_enter();
     const nasrec_seg_t& s = sp.a[blockIdx.y];
     const nasrec_seg_t& ds = sp.d[blockIdx.y];
     const int w = (int)s.width, ko = sp.koff[blockIdx.y];
@@ -154,6 +160,7 @@ __global__ void gate_bwd_kernel(const float* __restrict__ dout, long long ldo, c
 
 __global__ void concat_kernel(const __grid_constant__ SegPack sp, float* __restrict__ out, long long ldo, int M,
                               int accumulate) {
+    pdl_enter();
     const nasrec_seg_t& s = sp.a[blockIdx.y];
     const int w = (int)s.width;
     const long long total = (long long)M * w;
@@ -199,7 +206,7 @@ int nasrec_dot_tril_fwd(const float* x, int64_t ldx, const float* y, int64_t y_b
     CHECK_ARG(x && y && R && B > 0 && P > 0);
     if (P + 1 > TMAX) return NASREC_ETOOBIG;
     const int grid = B < 148 * 8 ? B : 148 * 8;
-    dot_tril_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, ldx, y, y_bstride, P, R, ldr, B);
+    nasrec_launch(dot_tril_fwd_kernel, grid, 256, 0, as_stream(stream), x, ldx, y, y_bstride, P, R, ldr, B);
     return nasrec_launch_status();
 }
 
@@ -209,21 +216,21 @@ int nasrec_dot_tril_bwd(const float* dR, int64_t ldr, const float* x, int64_t ld
     CHECK_ARG(dR && x && y && B > 0 && P > 0);
     if (P + 1 > TMAX) return NASREC_ETOOBIG;
     const int grid = B < 148 * 8 ? B : 148 * 8;
-    dot_tril_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dR, ldr, x, ldx, y, y_bstride, P, dx, lddx, dy,
+    nasrec_launch(dot_tril_bwd_kernel, grid, 256, 0, as_stream(stream), dR, ldr, x, ldx, y, y_bstride, P, dx, lddx, dy,
                                                              dy_bstride, B);
     return nasrec_launch_status();
 }
 
 int nasrec_fm_fwd(const float* x, int64_t x_bstride, int rows, float* ix, int B, void* stream) {
     CHECK_ARG(x && ix && B > 0 && rows > 0);
-    fm_fwd_kernel<<<cdiv((long long)B * 16, 256), 256, 0, as_stream(stream)>>>(x, x_bstride, rows, ix, B);
+    nasrec_launch(fm_fwd_kernel, cdiv((long long)B * 16, 256), 256, 0, as_stream(stream), x, x_bstride, rows, ix, B);
     return nasrec_launch_status();
 }
 
 int nasrec_fm_bwd(const float* dix, const float* x, int64_t x_bstride, int rows, const float* dx_in,
                   int64_t dxin_bstride, float* dx, int64_t dx_bstride, int B, void* stream) {
     CHECK_ARG(dix && x && dx && B > 0 && rows > 0);
-    fm_bwd_kernel<<<cdiv((long long)B * 16, 256), 256, 0, as_stream(stream)>>>(dix, x, x_bstride, rows, dx_in,
+    nasrec_launch(fm_bwd_kernel, cdiv((long long)B * 16, 256), 256, 0, as_stream(stream), dix, x, x_bstride, rows, dx_in,
                                                                               dxin_bstride, dx, dx_bstride, B);
     return nasrec_launch_status();
 }
@@ -237,7 +244,7 @@ int nasrec_gate_fwd(const float* pre, int64_t ldp, const nasrec_seg_t* right, in
     if (rc) return rc;
     if (maxw == 0) return 0;
     dim3 grid(seg_grid((long long)M * maxw), nseg);
-    gate_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(pre, ldp, sp, out, ldo, M);
+    nasrec_launch(gate_fwd_kernel, grid, 256, 0, as_stream(stream), pre, ldp, sp, out, ldo, M);
     return nasrec_launch_status();
 }
 
@@ -251,7 +258,7 @@ int nasrec_gate_bwd(const float* dout, int64_t ldo, const float* pre, int64_t ld
     if (rc) return rc;
     if (maxw == 0) return 0;
     dim3 grid(seg_grid((long long)M * maxw), nseg);
-    gate_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dout, ldo, pre, ldp, sp, dpre, lddp, M, accumulate);
+    nasrec_launch(gate_bwd_kernel, grid, 256, 0, as_stream(stream), dout, ldo, pre, ldp, sp, dpre, lddp, M, accumulate);
     return nasrec_launch_status();
 }
 
@@ -264,7 +271,7 @@ int nasrec_concat_segs(const nasrec_seg_t* segs, int nseg, float* out, int64_t l
     if (rc) return rc;
     if (maxw == 0) return 0;
     dim3 grid(seg_grid((long long)M * maxw), nseg);
-    concat_kernel<<<grid, 256, 0, as_stream(stream)>>>(sp, out, ldo, M, accumulate);
+    nasrec_launch(concat_kernel, grid, 256, 0, as_stream(stream), sp, out, ldo, M, accumulate);
     return nasrec_launch_status();
 }
 

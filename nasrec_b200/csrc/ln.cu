@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
                                                      int d_out, float* __restrict__ y, long long ldy,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      int accumulate) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ rstd_in, int relu,
                                                      float* __restrict__ dx, long long lddx,
                                                      float* __restrict__ part) {
+    pdl_enter();
     extern __shared__ float sred[];          // [2][4][N] when part != null
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float accg[LN_VPT], accb[LN_VPT];
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
 __global__ void __launch_bounds__(256) ln_param_final_kernel(const float* __restrict__ part, int nblk, int N,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                              int accumulate) {
+    pdl_enter();
     __shared__ float sg[8][33], sb[8][33];
     const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + c;
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(1024) ln_param_grad_kernel(const float* __rest
                                                              const float* __restrict__ rstd_in, int relu,
                                                              float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, int accumulate) {
+    pdl_enter();
     __shared__ float sg[32][33], sb[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + tx;
@@ -224,6 +228,7 @@ __global__ void __launch_bounds__(128) ln3_fwd_kernel(const float* __restrict__ 
                                                       int p_out, float* __restrict__ y, long long ybs,
                                                       float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                       int accumulate) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, e = lane & 15, ph = lane >> 4;
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(128) ln3_bwd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ rstd_in, int relu,
                                                       float* __restrict__ dz, long long dzbs,
                                                       float* __restrict__ part) {
+    pdl_enter();
     __shared__ float sg[4][LN3_MAXP], sb[4][LN3_MAXP];
     const int lane = threadIdx.x & 31, e = lane & 15, ph = lane >> 4, w = threadIdx.x >> 5;
     float accg[LN3_V], accb[LN3_V];
@@ -350,6 +356,7 @@ __global__ void __launch_bounds__(128) ln3_bwd_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) ln3_param_final_kernel(const float* __restrict__ part, int nblk, int P,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                               int accumulate) {
+    pdl_enter();
     __shared__ float sg[8][33], sb[8][33];
     const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int p = blockIdx.x * 32 + c;
@@ -381,6 +388,7 @@ __global__ void __launch_bounds__(256) ln3_param_grad_kernel(const float* __rest
                                                              const float* __restrict__ rstd_in, int relu,
                                                              float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, int accumulate) {
+    pdl_enter();
     __shared__ float red[34];
     const int p = blockIdx.x;
     float ag = 0.f, ab = 0.f;
@@ -406,6 +414,7 @@ __global__ void __launch_bounds__(256) ln3_param_grad_kernel(const float* __rest
 // db[p] = sum_{b,e} dz[b,p,e]  (bias of a sparse-axis projection; use_layernorm=False models)
 __global__ void __launch_bounds__(256) sproj_bias_grad_kernel(const float* __restrict__ dz, long long dzbs, int B,
                                                               float* __restrict__ db, int accumulate) {
+    pdl_enter();
     __shared__ float red[34];
     const int p = blockIdx.x;
     float a = 0.f;
@@ -417,6 +426,7 @@ __global__ void __launch_bounds__(256) sproj_bias_grad_kernel(const float* __res
 // ------------------------------------------------------------------ plain activation
 __global__ void act_fwd_kernel(const float* __restrict__ x, long long ldx, int M, int N, int relu,
                                float* __restrict__ y, long long ldy, int accumulate) {
+    pdl_enter();
     const long long total = (long long)M * N;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -430,6 +440,7 @@ __global__ void act_fwd_kernel(const float* __restrict__ x, long long ldx, int M
 
 __global__ void act_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x,
                                long long ldx, int M, int N, int relu, float* __restrict__ dx, long long lddx) {
+    pdl_enter();
     const long long total = (long long)M * N;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -442,6 +453,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, long long lddy, con
 
 __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ x, long long ld, int M, int N,
                                                       float* __restrict__ out, int accumulate) {
+    pdl_enter();
     __shared__ float sm[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + tx;
@@ -474,7 +486,7 @@ int nasrec_ln_fwd(const float* x, int64_t ldx, int M, int N, const float* gamma,
                   void* stream) {
     CHECK_ARG(x && gamma && beta && y && mean && rstd && M > 0 && N > 0 && d_out >= 0 && d_out <= N);
     if (N > LN_MAXN) return NASREC_ETOOBIG;
-    ln_fwd_kernel<<<cdiv(M, 4), 128, 0, as_stream(stream)>>>(x, ldx, M, N, gamma, beta, eps, relu, d_out, y, ldy,
+    nasrec_launch(ln_fwd_kernel, cdiv(M, 4), 128, 0, as_stream(stream), x, ldx, M, N, gamma, beta, eps, relu, d_out, y, ldy,
                                                              mean, rstd, accumulate);
     return nasrec_launch_status();
 }
@@ -495,17 +507,17 @@ int nasrec_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* x, int6
     const bool fused = want && ws && nws >= (long long)grid * 2 * N;
     if (dx || fused) {
         const size_t smem = fused ? (size_t)8 * N * sizeof(float) : 0;
-        ln_bwd_kernel<<<grid, 128, smem, st>>>(dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx, lddx,
+        nasrec_launch(ln_bwd_kernel, grid, 128, smem, st, dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx, lddx,
                                                fused ? ws : nullptr);
         int rc = nasrec_launch_status();
         if (rc) return rc;
     }
     if (fused) {
-        ln_param_final_kernel<<<cdiv(N, 32), 256, 0, st>>>(ws, grid, N, dgamma, dbeta, accumulate_params);
+        nasrec_launch(ln_param_final_kernel, cdiv(N, 32), 256, 0, st, ws, grid, N, dgamma, dbeta, accumulate_params);
         return nasrec_launch_status();
     }
     if (want) {
-        ln_param_grad_kernel<<<cdiv(N, 32), 1024, 0, st>>>(dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd,
+        nasrec_launch(ln_param_grad_kernel, cdiv(N, 32), 1024, 0, st, dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd,
                                                            relu, dgamma, dbeta, accumulate_params);
         return nasrec_launch_status();
     }
@@ -517,7 +529,7 @@ int nasrec_ln3_fwd(const float* z, int64_t z_bstride, int B, int P, const float*
                    int accumulate, void* stream) {
     CHECK_ARG(z && gamma && beta && y && mean && rstd && B > 0 && P > 0 && p_out >= 0 && p_out <= P);
     if (P > LN3_MAXP) return NASREC_ETOOBIG;
-    ln3_fwd_kernel<<<cdiv(B, 4), 128, 0, as_stream(stream)>>>(z, z_bstride, B, P, gamma, beta, eps, relu, p_out, y,
+    nasrec_launch(ln3_fwd_kernel, cdiv(B, 4), 128, 0, as_stream(stream), z, z_bstride, B, P, gamma, beta, eps, relu, p_out, y,
                                                              y_bstride, mean, rstd, accumulate);
     return nasrec_launch_status();
 }
@@ -538,17 +550,17 @@ int nasrec_ln3_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* 
     if (grid > 148) grid = 148;                    // persistent warps: fixed sample -> warp assignment
     const bool fused = want && ws && nws >= (long long)grid * 2 * LN3_MAXP;
     if (dz || fused) {
-        ln3_bwd_kernel<<<grid, 128, 0, st>>>(dy, dy_bstride, p_out, z, z_bstride, B, P, gamma, beta, mean, rstd, relu,
+        nasrec_launch(ln3_bwd_kernel, grid, 128, 0, st, dy, dy_bstride, p_out, z, z_bstride, B, P, gamma, beta, mean, rstd, relu,
                                              dz, dz_bstride, fused ? ws : nullptr);
         int rc = nasrec_launch_status();
         if (rc) return rc;
     }
     if (fused) {
-        ln3_param_final_kernel<<<cdiv(P, 32), 256, 0, st>>>(ws, grid, P, dgamma, dbeta, accumulate_params);
+        nasrec_launch(ln3_param_final_kernel, cdiv(P, 32), 256, 0, st, ws, grid, P, dgamma, dbeta, accumulate_params);
         return nasrec_launch_status();
     }
     if (want) {
-        ln3_param_grad_kernel<<<P, 256, 0, st>>>(dy, dy_bstride, p_out, z, z_bstride, B, P, gamma, beta, mean, rstd,
+        nasrec_launch(ln3_param_grad_kernel, P, 256, 0, st, dy, dy_bstride, p_out, z, z_bstride, B, P, gamma, beta, mean, rstd,
                                                  relu, dgamma, dbeta, accumulate_params);
         return nasrec_launch_status();
     }
@@ -558,14 +570,14 @@ int nasrec_ln3_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* 
 int nasrec_sproj_bias_grad(const float* dZ, int64_t dz_bstride, int P, int B, float* db, int accumulate,
                            void* stream) {
     CHECK_ARG(dZ && db && P > 0 && B > 0);
-    sproj_bias_grad_kernel<<<P, 256, 0, as_stream(stream)>>>(dZ, dz_bstride, B, db, accumulate);
+    nasrec_launch(sproj_bias_grad_kernel, P, 256, 0, as_stream(stream), dZ, dz_bstride, B, db, accumulate);
     return nasrec_launch_status();
 }
 
 int nasrec_act_fwd(const float* x, int64_t ldx, int M, int N, int relu, float* y, int64_t ldy, int accumulate,
                    void* stream) {
     CHECK_ARG(x && y && M > 0 && N > 0);
-    act_fwd_kernel<<<ew_grid((long long)M * N), 256, 0, as_stream(stream)>>>(x, ldx, M, N, relu, y, ldy,
+    nasrec_launch(act_fwd_kernel, ew_grid((long long)M * N), 256, 0, as_stream(stream), x, ldx, M, N, relu, y, ldy,
                                                                             accumulate);
     return nasrec_launch_status();
 }
@@ -573,14 +585,14 @@ int nasrec_act_fwd(const float* x, int64_t ldx, int M, int N, int relu, float* y
 int nasrec_act_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, int M, int N, int relu, float* dx,
                    int64_t lddx, void* stream) {
     CHECK_ARG(dy && x && dx && M > 0 && N > 0);
-    act_bwd_kernel<<<ew_grid((long long)M * N), 256, 0, as_stream(stream)>>>(dy, lddy, x, ldx, M, N, relu, dx,
+    nasrec_launch(act_bwd_kernel, ew_grid((long long)M * N), 256, 0, as_stream(stream), dy, lddy, x, ldx, M, N, relu, dx,
                                                                             lddx);
     return nasrec_launch_status();
 }
 
 int nasrec_colsum(const float* x, int64_t ld, int M, int N, float* out, int accumulate, void* stream) {
     CHECK_ARG(x && out && M > 0 && N > 0);
-    colsum_kernel<<<cdiv(N, 32), 1024, 0, as_stream(stream)>>>(x, ld, M, N, out, accumulate);
+    nasrec_launch(colsum_kernel, cdiv(N, 32), 1024, 0, as_stream(stream), x, ld, M, N, out, accumulate);
     return nasrec_launch_status();
 }
 

@@ -23,6 +23,7 @@ struct Partial { double loss; long long correct; };
 __global__ void __launch_bounds__(MT) metrics_prepare_kernel(const float* __restrict__ z, const float* __restrict__ y,
                                                              long long n, uint32_t* __restrict__ key,
                                                              uint8_t* __restrict__ isneg, Partial* __restrict__ part) {
+    pdl_enter();
     __shared__ double sl[MT / 32];
     __shared__ long long sc[MT / 32];
     double loss = 0.0;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(MT) metrics_prepare_kernel(const float* __rest
 __global__ void __launch_bounds__(MT) metrics_pairs_kernel(const uint32_t* __restrict__ key, const uint8_t* __restrict__ isneg,
                                                            const int* __restrict__ negpre, long long n,
                                                            unsigned long long* __restrict__ twice_pairs) {
+    pdl_enter();
     unsigned long long acc = 0;
     for (long long i = (long long)blockIdx.x * MT + threadIdx.x; i < n; i += (long long)gridDim.x * MT) {
         if (isneg[i]) continue;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(MT) metrics_pairs_kernel(const uint32_t* __res
 __global__ void metrics_final_kernel(const Partial* __restrict__ part, int nparts, const int* __restrict__ negpre,
                                      long long n, const unsigned long long* __restrict__ twice_pairs,
                                      double* __restrict__ out) {
+    pdl_enter();
     double l = 0.0; long long c = 0;
     for (int b = 0; b < nparts; ++b) { l += part[b].loss; c += part[b].correct; }
     const double N = (double)negpre[n], P = (double)n - N;
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(256) input_transform_kernel(const float* __res
                                                               const int64_t* __restrict__ num_rows, long long B,
                                                               float* __restrict__ int_x, int64_t* __restrict__ cat_x,
                                                               int* __restrict__ err_flag) {
+    pdl_enter();
     const long long per = (long long)nd + F;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < B * per; t += (long long)gridDim.x * blockDim.x) {
         const long long b = t / per;
@@ -174,13 +178,13 @@ extern "C" int nasrec_binary_metrics(const float* logits, const float* y, int64_
     unsigned long long* pairs = (unsigned long long*)(base + w.pairs);
     cudaMemsetAsync(pairs, 0, sizeof(unsigned long long), st);
     // the scan runs over n+1 items so that negpre[n] = N; item n's own value is never summed (exclusive)
-    metrics_prepare_kernel<<<MB, MT, 0, st>>>(logits, y, n, key_in, neg_in, part);
+    nasrec_launch(metrics_prepare_kernel, MB, MT, 0, st, logits, y, n, key_in, neg_in, part);
     size_t cb = w.cub_bytes;
     cub::DeviceRadixSort::SortPairs(base + w.cub, cb, key_in, key_out, neg_in, neg_out, (int)n, 0, 32, st);
     cb = w.cub_bytes;
     cub::DeviceScan::ExclusiveSum(base + w.cub, cb, neg_out, negpre, (int)n + 1, st);
-    metrics_pairs_kernel<<<MB, MT, 0, st>>>(key_out, neg_out, negpre, n, pairs);
-    metrics_final_kernel<<<1, 1, 0, st>>>(part, MB, negpre, n, pairs, out3);
+    nasrec_launch(metrics_pairs_kernel, MB, MT, 0, st, key_out, neg_out, negpre, n, pairs);
+    nasrec_launch(metrics_final_kernel, 1, 1, 0, st, part, MB, negpre, n, pairs, out3);
     return nasrec_launch_status();
 }
 
@@ -193,7 +197,7 @@ extern "C" int nasrec_input_transform(const float* dense_raw, int64_t dense_stri
     CHECK_ARG((nd == 0 || (dense_raw && int_x)) && (F == 0 || (hex && num_rows && cat_x)));
     const long long total = B * ((long long)nd + F);
     const int blocks = (int)((total + 255) / 256 < 148LL * 8 ? (total + 255) / 256 : 148 * 8);
-    input_transform_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dense_raw, dense_stride_b, dense_stride_c, nd, hex, hex_stride_b,
+    nasrec_launch(input_transform_kernel, blocks, 256, 0, as_stream(stream), dense_raw, dense_stride_b, dense_stride_c, nd, hex, hex_stride_b,
                                                                   hex_stride_f, width, F, num_rows, B, int_x, cat_x,
                                                                   err_flag);
     return nasrec_launch_status();

@@ -12,6 +12,7 @@ namespace {
 __global__ void __launch_bounds__(1024) bce_kernel(const float* __restrict__ z, const float* __restrict__ y, int B,
                                                    float grad_scale, float* __restrict__ loss,
                                                    float* __restrict__ dz) {
+    pdl_enter();
     __shared__ float red[34];
     float acc = 0.f;
     const float invB = 1.f / (float)B;
@@ -37,6 +38,7 @@ struct SumsqPack {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const __grid_constant__ SumsqPack pk, float* __restrict__ partial,
                                                     int partial_off) {
+    pdl_enter();
     __shared__ float red[34];
     const int c = blockIdx.x;
     int t = 0;
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const __grid_constant__ Sums
 __global__ void __launch_bounds__(1024) clip_finalize_kernel(const float* __restrict__ partial, int n_partial,
                                                              const float* __restrict__ extra, int n_extra,
                                                              float max_norm, float* __restrict__ out) {
+    pdl_enter();
     __shared__ float red[34];
     float acc = 0.f;
     for (int i = threadIdx.x; i < n_partial; i += blockDim.x) acc += partial[i];
@@ -80,6 +83,7 @@ struct AdagradPack {
 
 __global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ AdagradPack pk, float lr, float eps,
                                                       const float* __restrict__ clip_coef) {
+    pdl_enter();
     const int c = blockIdx.x;
     int t = 0;
     while (t + 1 < pk.n && pk.chunk0[t + 1] <= c) ++t;
@@ -104,7 +108,7 @@ extern "C" {
 int nasrec_bce_fwd_bwd(const float* logits, const float* y, int B, float grad_scale, float* loss, float* dlogits,
                        void* stream) {
     CHECK_ARG(logits && y && B > 0);
-    bce_kernel<<<1, 1024, 0, as_stream(stream)>>>(logits, y, B, grad_scale, loss, dlogits);
+    nasrec_launch(bce_kernel, 1, 1024, 0, as_stream(stream), logits, y, B, grad_scale, loss, dlogits);
     return nasrec_launch_status();
 }
 
@@ -131,14 +135,14 @@ int nasrec_grad_norm_clip(const float* const* grads, const int64_t* sizes, int n
         pk.chunk0[m] = chunks;
         pk.n = m;
         if (chunks > 0) {
-            sumsq_kernel<<<chunks, 256, 0, st>>>(pk, partial, poff);
+            nasrec_launch(sumsq_kernel, chunks, 256, 0, st, pk, partial, poff);
             int rc = nasrec_launch_status();
             if (rc) return rc;
         }
         poff += chunks;
         done += m;
     }
-    clip_finalize_kernel<<<1, 1024, 0, st>>>(partial, poff, extra_sumsq, n_extra, max_norm, out);
+    nasrec_launch(clip_finalize_kernel, 1, 1024, 0, st, partial, poff, extra_sumsq, n_extra, max_norm, out);
     return nasrec_launch_status();
 }
 
@@ -161,7 +165,7 @@ int nasrec_adagrad_multi(float* const* w, const float* const* grads, float* cons
         pk.chunk0[m] = chunks;
         pk.n = m;
         if (chunks > 0) {
-            adagrad_kernel<<<chunks, 256, 0, st>>>(pk, lr, eps, clip_coef);
+            nasrec_launch(adagrad_kernel, chunks, 256, 0, st, pk, lr, eps, clip_coef);
             int rc = nasrec_launch_status();
             if (rc) return rc;
         }
