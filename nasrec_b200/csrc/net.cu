@@ -123,6 +123,17 @@ struct Net {
         if (ref_stamp[pi] != step_id) { ref_stamp[pi] = step_id; ref_order.push_back(pi); }
     }
     void zero(float* p, int64_t n) { cudaMemsetAsync(p, 0, (size_t)n * 4, st); }
+    // events for forking a block's sparse node onto the library's side stream during forward
+    cudaEvent_t ev[32];
+    int ev_made = 0, ev_next = 0;
+    cudaEvent_t event() {
+        if (ev_made < 32) {
+            cudaEventCreateWithFlags(&ev[ev_made], cudaEventDisableTiming);
+            return ev[ev_made++];
+        }
+        ev_next = (ev_next + 1) % 32;
+        return ev[ev_next];
+    }
     void record(std::function<void()> fn) { if (tape_on) tape.push_back(std::move(fn)); }
 };
 
@@ -612,9 +623,28 @@ void run_block(Net& n, int bi, const BlockChoice& ch, const std::vector<DSrc>& d
     const int rows = s + g;
     Var* sparse_out = n.var((int64_t)B * rows * E);
     int nd_w = 0, ns_w = 0;
+    // The dense node and the sparse node of a block are independent until the merger: with a side stream attached
+    // the sparse node's forward kernels (sparse-axis GEMM, LayerNorm, attention) run there, concurrently with the
+    // dense node's, and are joined before the merger / FM read sparse_out.
+    cudaStream_t main_st = n.st;
+    cudaStream_t side = n.overlap ? nasrec_internal_side_stream() : nullptr;
+    if (side == main_st) side = nullptr;
+    bool forked = false;
+    auto on_side = [&]() {
+        if (!side) return;
+        if (!forked) {
+            cudaEvent_t e = n.event();
+            cudaEventRecord(e, main_st);
+            cudaStreamWaitEvent(side, e, 0);
+            forked = true;
+        }
+        n.st = side;
+    };
     for (int ai : ch.active) {
         const NodeDesc& nd = bd.nodes[ai];
         const int* p = nd.p;
+        n.st = main_st;
+        if (nd.type == N_EFC || nd.type == N_TRANS) on_side();
         switch (nd.type) {
         case N_FC: {
             LinArgs a; a.W = p[0]; a.b = p[1]; a.lng = p[2]; a.lnb = p[3]; a.relu = true; a.d_out = d;
@@ -679,6 +709,12 @@ void run_block(Net& n, int bi, const BlockChoice& ch, const std::vector<DSrc>& d
         case N_ZERO2: case N_ZERO3: break;
         default: throw CallFailed(NASREC_EINVAL);
         }
+    }
+    n.st = main_st;
+    if (forked) {
+        cudaEvent_t e = n.event();
+        cudaEventRecord(e, side);
+        cudaStreamWaitEvent(main_st, e, 0);
     }
     if (nd_w == 0) n.zero(dense_out->t, dense_out->n);
     if (ns_w == 0) n.zero(sparse_out->t, sparse_out->n);

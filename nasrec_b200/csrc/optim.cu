@@ -47,9 +47,22 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const __grid_constant__ Sums
     const long long end = min(pk.size[t], beg + MT_CHUNK);
     const float* g = pk.g[t];
     float acc = 0.f;
-    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
-        const float v = g[i];
-        acc = fmaf(v, v, acc);
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {          // chunk starts are multiples of 4: 16-byte loads
+        const long long n4 = (end - beg) >> 2;
+        const float4* g4 = reinterpret_cast<const float4*>(g + beg);
+        for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 v = __ldg(g4 + i);
+            acc = fmaf(v.x, v.x, acc);
+            acc = fmaf(v.y, v.y, acc);
+            acc = fmaf(v.z, v.z, acc);
+            acc = fmaf(v.w, v.w, acc);
+        }
+        for (long long i = beg + (n4 << 2) + threadIdx.x; i < end; i += blockDim.x) acc = fmaf(g[i], g[i], acc);
+    } else {
+        for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+            const float v = g[i];
+            acc = fmaf(v, v, acc);
+        }
     }
     const float tot = block_sum(acc, red);
     if (threadIdx.x == 0) partial[partial_off + c] = tot;
@@ -93,11 +106,31 @@ __global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ Ad
     float* w = pk.w[t];
     const float* g = pk.g[t];
     float* s = pk.s[t];
-    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
-        const float gv = g[i] * coef;
-        const float sv = fmaf(gv, gv, s[i]);
-        s[i] = sv;
-        w[i] = w[i] - lr * (gv / (sqrtf(sv) + eps));
+    auto upd = [&](float gi, float& si, float& wi) {
+        const float gv = gi * coef;
+        const float sv = fmaf(gv, gv, si);
+        si = sv;
+        wi = wi - lr * (gv / (sqrtf(sv) + eps));
+    };
+    if (((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0) {
+        // three streams in, two out, 16 bytes per access (chunk starts are multiples of 4 elements)
+        const long long n4 = (end - beg) >> 2;
+        const float4* g4 = reinterpret_cast<const float4*>(g + beg);
+        float4* s4 = reinterpret_cast<float4*>(s + beg);
+        float4* w4 = reinterpret_cast<float4*>(w + beg);
+        for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 gv = __ldg(g4 + i);
+            float4 sv = s4[i], wv = w4[i];
+            upd(gv.x, sv.x, wv.x);
+            upd(gv.y, sv.y, wv.y);
+            upd(gv.z, sv.z, wv.z);
+            upd(gv.w, sv.w, wv.w);
+            s4[i] = sv;
+            w4[i] = wv;
+        }
+        for (long long i = beg + (n4 << 2) + threadIdx.x; i < end; i += blockDim.x) upd(g[i], s[i], w[i]);
+    } else {
+        for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) upd(g[i], s[i], w[i]);
     }
 }
 

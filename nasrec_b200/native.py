@@ -163,7 +163,8 @@ class NativeNet:
         self._numel = np.asarray([p.numel() for p in self.params], dtype=np.int64)
         self._rows = np.asarray([p.shape[0] if p.dim() >= 1 else 1 for p in self.params], dtype=np.int32)
         self._cols = np.asarray([p.shape[1] if p.dim() == 2 else 1 for p in self.params], dtype=np.int32)
-        self._req = np.asarray([int(p.requires_grad) for p in self.params], dtype=np.int32)
+        self._req_list = [p.requires_grad for p in self.params]
+        self._req = np.asarray(self._req_list, dtype=np.int32)
         m._tables.refresh([e.weight.detach() for e in m._embedding])
         tb = m._tables
         emb_states = [self.states[self._pi(e.weight)] for e in m._embedding] if self.states is not None else None
@@ -213,8 +214,9 @@ class NativeNet:
             self._build()
             _check(_fn("nasrec_net_set_arenas")(self.handle, self.act.data_ptr(), self.act.numel(), self.pg.data_ptr(),
                                                 self.pg.numel()), "nasrec_net_set_arenas")
-        req = [int(p.requires_grad) for p in self.params]
-        if req != self._req.tolist():
+        req = [p.requires_grad for p in self.params]
+        if req != self._req_list:
+            self._req_list = req
             self._req = np.asarray(req, dtype=np.int32)
             _check(_fn("nasrec_net_set_requires_grad")(self.handle, self._req.ctypes.data, len(req)), "set_requires_grad")
 
@@ -232,16 +234,25 @@ class NativeNet:
         flat: List[int] = []
         for mac, mic in zip(macro, micro):
             for key in ("dense_idx", "sparse_idx", "dense_left_idx", "dense_right_idx"):
-                v = _ints(mac[key])
-                if len(v) > 8:
+                v = mac[key]
+                if type(v) is not list:
+                    v = _ints(v)
+                n = len(v)
+                if n > 8:
                     raise ValueError("more than 8 sources in '%s'" % key)
-                flat.append(len(v))
-                flat += v + [0] * (8 - len(v))
-            act = _ints(mic["active_nodes"])
-            flat.append(len(act))
-            flat += act + [0] * (8 - len(act))
-            flat += [int(mic["dense_in_dims"]), int(mic["sparse_in_dims"]), int(mic["dense_sparse_interact"]),
-                     int(mic["deep_fm"])]
+                flat.append(n)
+                flat += v
+                flat += (0,) * (8 - n)
+            act = mic["active_nodes"]
+            if type(act) is not list:
+                act = _ints(act)
+            n = len(act)
+            if n > 8:
+                raise ValueError("more than 8 active nodes")
+            flat.append(n)
+            flat += act
+            flat += (0,) * (8 - n)
+            flat += (mic["dense_in_dims"], mic["sparse_in_dims"], mic["dense_sparse_interact"], mic["deep_fm"])
         return np.asarray(flat, dtype=np.int32)
 
     def _count(self):

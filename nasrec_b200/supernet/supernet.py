@@ -29,7 +29,8 @@ from ..utils.config import NUM_EMBEDDINGS_CRITEO
 from .modules import (CleverMaskGenerator, CleverZeroTensorGenerator, DotProduct, ElasticLinear, ElasticLinear3D,
                       FactorizationMachine3D, Run, SigmoidGating, Sum, Transformer, Zeros2D, Zeros3D, _materialize,
                       run_with_autograd)
-from .utils import anypath_choice_fn, assert_valid_ops_config
+from .utils import (anypath_choice_fn, assert_valid_ops_config, pick, pick_index, pick_with_replacement,
+                    pick_without_replacement)
 
 EMB = 16
 
@@ -291,18 +292,18 @@ class SuperNet(nn.Module):
 
     # ------------------------------------------------------------------ macro samplers (RNG-order exact)
     def _get_single_path_choice(self, n: int):           # supernet.py:723-736
-        bi = np.random.choice(n, 1 * 2)
-        return {"dense_idx": [int(np.random.choice(n))], "sparse_idx": [int(np.random.choice(n))],
+        bi = pick_with_replacement(n, 1 * 2)
+        return {"dense_idx": [pick_index(n)], "sparse_idx": [pick_index(n)],
                 "dense_left_idx": [int(bi[0])], "dense_right_idx": [int(bi[1])]}
 
     def _draw_multi(self, n: int, count_fn):
         nd_ = count_fn(n)
         ns_ = count_fn(n)
-        bi = np.random.choice(n, 1 * 2)
-        dense = np.random.choice(n, nd_, replace=False).reshape(-1).tolist()
-        sparse = np.random.choice(n, ns_, replace=False).reshape(-1).tolist()
-        return {"dense_idx": dense, "sparse_idx": sparse, "dense_left_idx": bi[:1].reshape(-1).tolist(),
-                "dense_right_idx": bi[1:].reshape(-1).tolist()}
+        bi = pick_with_replacement(n, 1 * 2)
+        dense = pick_without_replacement(n, nd_)
+        sparse = pick_without_replacement(n, ns_)
+        return {"dense_idx": dense, "sparse_idx": sparse, "dense_left_idx": [int(bi[0])],
+                "dense_right_idx": [int(bi[1])]}
 
     def _get_any_path_choice(self, n: int):              # supernet.py:738-770
         return self._draw_multi(n, self._anypath_choice_fn)
@@ -344,7 +345,7 @@ class SuperNet(nn.Module):
         else:
             raise NotImplementedError("Path strategy {} is not supported!".format(strat))
         if strat != "full-path":
-            self.macro_last_choice = choice
+            self.__dict__["macro_last_choice"] = choice
         return choice
 
     # ------------------------------------------------------------------ lazy life cycle
@@ -405,9 +406,10 @@ class SuperNet(nn.Module):
     def _sample(self, choices=None) -> Tuple[List[Dict], List[Dict]]:
         """Host side of forward (supernet.py:513-529, 574-585): counters, macro then
         per-block micro draws in block order, self.choice bookkeeping."""
+        d = self.__dict__
         if not self._fixed:
-            self._supernet_train_steps_counter += 1
-        self.choice = {"micro": [], "macro": []}
+            d["_supernet_train_steps_counter"] = self._supernet_train_steps_counter + 1
+        d["choice"] = {"micro": [], "macro": []}
         macro = self._get_choice() if choices is None else choices["macro"]
         self.choice["macro"] = macro
         micro = []
@@ -568,14 +570,14 @@ class SuperNetBlock(nn.Module):
     # ------------------------------------------------------------------ micro samplers (RNG-order exact)
     def _draw_tail(self, active):
         return {"active_nodes": active,
-                "dense_in_dims": np.random.choice(self._dense_node_dims),
-                "sparse_in_dims": np.random.choice(self._sparse_node_dims),
-                "dense_sparse_interact": np.random.choice([0, 1]),
-                "deep_fm": np.random.choice([0, 1])}
+                "dense_in_dims": pick(self._dense_node_dims),
+                "sparse_in_dims": pick(self._sparse_node_dims),
+                "dense_sparse_interact": pick_index(2),
+                "deep_fm": pick_index(2)}
 
     def _get_single_path_choice(self):                   # supernet.py:1244-1263
         while True:
-            active = sorted([np.random.choice(self._dense_nodes)] + [np.random.choice(self._sparse_nodes)])
+            active = sorted([pick(self._dense_nodes)] + [pick(self._sparse_nodes)])
             choice = self._draw_tail(active)
             if choice["active_nodes"] != self._zero_nodes:
                 return choice
@@ -588,8 +590,8 @@ class SuperNetBlock(nn.Module):
         while True:
             n_d = self._anypath_choice_fn(len(self._dense_nodes))
             n_s = self._anypath_choice_fn(len(self._sparse_nodes))
-            dense = np.random.choice(self._dense_nodes, n_d, replace=False).tolist()
-            sparse = np.random.choice(self._sparse_nodes, n_s, replace=False).tolist()
+            dense = pick_without_replacement(self._dense_nodes, n_d)
+            sparse = pick_without_replacement(self._sparse_nodes, n_s)
             choice = self._draw_tail(sorted(dense + sparse))
             if choice["active_nodes"] != self._zero_nodes:
                 return choice
@@ -616,15 +618,16 @@ class SuperNetBlock(nn.Module):
         else:
             raise NotImplementedError("Path strategy {} is not supported!".format(strat))
         if strat != "full-path":
-            self.micro_last_choice = choice
+            self.__dict__["micro_last_choice"] = choice      # (plain attribute: skip nn.Module.__setattr__, hot path)
         return choice
 
     def _sample(self, choices=None):
         """Host side of SuperNetBlock.forward (supernet.py:1067-1076)."""
         choice = self._get_choice() if choices is None else choices
-        self.choice = choice
+        d = self.__dict__
+        d["choice"] = choice
         if not self._fixed:
-            self._supernet_train_steps_counter += 1
+            d["_supernet_train_steps_counter"] = self._supernet_train_steps_counter + 1
         return choice
 
     def configure_choice(self, choice):                  # supernet.py:1316-1318
