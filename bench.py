@@ -241,8 +241,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created (the box exports NCCL_DEBUG);
+        # stdout must carry exactly one JSON line, so fd 1 points at stderr until the communicator exists.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            probe = torch.zeros(1, device=dev)
+            dist.all_reduce(probe)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     K, W = args.steps, args.warmup
     assert W >= 3, "timing rules: at least 3 warm-up steps"
 
