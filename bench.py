@@ -230,7 +230,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from nasrec_b200 import SuperNet, ops_config_lib, _lib
-    from nasrec_b200.parallel import DataParallelTrainer, shard_range, gather_results
+    from nasrec_b200.parallel import DataParallelTrainer
     from nasrec_b200.utils.train_utils import FusedTrainer, init_weights
     from nasrec_b200.search import SubnetEvaluator, generate_random_choice
 

@@ -222,8 +222,12 @@ struct Stager {
 
 template <int BN>
 struct TcCfg {
-    static constexpr int STAGES = BN == 128 ? 3 : 4;     // 192 KB / 192 KB / 160 KB / 144 KB of shared memory
-    static constexpr int PREFETCH = BN == 128 ? 2 : (BN == 64 ? 3 : 4);   // k-tiles of global loads kept in registers
+    // BN <= 64: few stages and 256 TMEM columns, so that two CTAs -- of the same launch, or of the main-stream and
+    // side-stream GEMMs that run concurrently -- share an SM and hide each other's prologue/epilogue.  Measured
+    // (profiles/r01_native_gemm_full.md): isolated launches get slower (K=1037 fwd 35 -> 50 us with two stages), the
+    // training pipelines get faster (fixed-model graph +8 %, KDD B=2048 +7 %) because the GEMMs of the two streams overlap.
+    static constexpr int STAGES = BN >= 64 ? 3 : 2;      // 192 KB (BN=128, one CTA per SM) / 144 KB / 81 KB / 73 KB
+    static constexpr int PREFETCH = 2;   // k-tiles of global loads kept in registers
     static constexpr int A_BYTES = TC_BM * TC_BK * 4;      // 16 KB
     static constexpr int B_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -233,12 +237,13 @@ struct TcCfg {
     // fp32 accumulation truncates, so its error grows linearly with the number of MMAs chained
     // into one accumulator; spreading K over up to 8 accumulators brings it back to FFMA level.
     static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;
-    static constexpr int NACC_MAX = 512 / ACC_STRIDE < 8 ? 512 / ACC_STRIDE : 8;
-    static constexpr int TMEM_COLS = 512;
+    static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;
+    static constexpr int NACC_MAX = TMEM_COLS / ACC_STRIDE < 8 ? TMEM_COLS / ACC_STRIDE : 8;
+    static constexpr int CTAS_PER_SM = BN == 128 ? 1 : 2;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Batch bt, int nprod) {
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) gemm_tc_kernel(const __grid_constant__ Batch bt, int nprod) {
     pdl_trigger();
     using Cfg = TcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];

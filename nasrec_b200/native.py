@@ -11,14 +11,13 @@ two caller-owned arenas.  Fixed (standalone) models and unusual corners stay on 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Dict, List, Optional, Sequence
 
 import numpy as np
 import torch
-import torch.nn as nn
 
 from . import _lib
-from .supernet.supernet import DS_INTERACT_NUM_SPLITS, EMB, SuperNet, _ints
+from .supernet.supernet import EMB, SuperNet, _ints
 from .utils.train_utils import FusedTrainer
 
 _NODE_TYPES = {"linear-2d": 0, "dot-product": 1, "sum": 2, "sigmoid-gating": 3, "linear-3d": 4, "transformer": 5,

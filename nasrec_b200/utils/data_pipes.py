@@ -8,7 +8,7 @@ turned into ``(int_x [B,nd] f32, cat_x [B,F] i64, y [B,1] f32)`` by ONE kernel
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence
 
 import numpy as np
 import torch

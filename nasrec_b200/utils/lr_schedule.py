@@ -8,13 +8,13 @@ entry scripts keep working, restated around two pure functions of the step index
 
 The pure functions are what ``FusedTrainer``/``SubnetEvaluator`` use (they take ``lr`` per
 step and own no torch optimizer); the classes wrap a ``torch.optim.Optimizer`` for the
-drop-in path.  tests/test_host_parity.py checks both against sequences generated from
+drop-in path.  tests/test_search_cpu.py checks both against sequences generated from
 the reference classes (tests/golden/lr_schedules.json).
 """
 from __future__ import annotations
 
 import math
-from typing import List, Tuple
+from typing import List
 
 import torch
 from torch.optim.lr_scheduler import _LRScheduler

@@ -169,7 +169,7 @@ def train_and_test_one_epoch(model, epoch: int, optimizer, lr_scheduler, train_l
                 train_auroc = 1.0
             else:
                 train_acc, train_auroc, _ = binary_metrics_device(res.detach(), yv)
-            logs["train_loss"].append(float(loss))
+            logs["train_loss"].append(float(loss.detach()))
             logs["train_AUROC"].append(train_auroc)
             logs["train_Accuracy"].append(train_acc)
             logs["epoch"].append(epoch)
