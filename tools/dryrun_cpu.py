@@ -71,7 +71,7 @@ m.materialize(13)
 tr = [orc.synth_batch(16, 13, G["num_embeddings"], seed=500 + b) for b in range(5)]
 ev = [orc.synth_batch(32, 13, G["num_embeddings"], seed=900 + b) for b in range(2)]
 srch.binary_metrics_device = lambda z, y: (0.5, 0.5, 0.7)
-se = srch.SubnetEvaluator(m)
+se = srch.SubnetEvaluator(m, use_native=False)
 for ts in (8192, 40, 1):
     r = se.finetune_and_score(G["cands"][0]["choice"], tr, ev, lr=0.04, trunk_samples=ts)
 S = srch.Searcher(se, srch.Tokenizer(7, sn.ops_config_lib["xlarge"]), tr, ev)
