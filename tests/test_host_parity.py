@@ -217,3 +217,45 @@ def test_checkpoint_bridge_round_trip(tmp_path):
     with open(tmp_path / "results.pickle", "rb") as fh:
         assert pickle.load(fh) == rec
     assert io_utils.load_pickle_data(str(tmp_path / "results.pickle")) == rec
+
+
+def test_fast_draws_consume_the_rng_like_np_random_choice():
+    """supernet/utils.pick* replace np.random.choice in the samplers: same values AND same RNG position
+    afterwards, for every call shape the samplers use (a16; the legacy global RandomState)."""
+    from nasrec_b200.supernet.utils import pick, pick_index, pick_with_replacement, pick_without_replacement
+    dims = [16, 32, 64, 128, 256, 512, 768, 1024]
+    for seed in range(300):
+        np.random.seed(seed)
+        a = [int(np.random.choice(n)) for n in (1, 2, 3, 4, 5, 6, 7)]
+        b = np.random.choice(7, 2).tolist()
+        c = [np.random.choice(n, k, replace=False).tolist() for n, k in ((1, 1), (4, 2), (7, 4), (7, 7))]
+        d = [int(np.random.choice(dims)), int(np.random.choice([0, 1])), int(np.random.choice([4, 5]))]
+        e = np.random.choice([0, 1, 2, 3], 2, replace=False).tolist()
+        tail = np.random.random()
+        np.random.seed(seed)
+        a2 = [pick_index(n) for n in (1, 2, 3, 4, 5, 6, 7)]
+        b2 = pick_with_replacement(7, 2).tolist()
+        c2 = [pick_without_replacement(n, k) for n, k in ((1, 1), (4, 2), (7, 4), (7, 7))]
+        d2 = [pick(dims), pick_index(2), pick([4, 5])]
+        e2 = pick_without_replacement([0, 1, 2, 3], 2)
+        assert (a, b, c, d, e) == (a2, b2, c2, d2, e2), seed
+        assert np.random.random() == tail, seed              # the stream is at the same position
+
+
+def test_native_choice_encoding_layout():
+    """The flat int layout the C++ executor decodes (include/nasrec_b200.h: 49 ints per block)."""
+    from nasrec_b200.native import NativeNet
+    macro = [{"dense_idx": [0], "sparse_idx": np.asarray([0]), "dense_left_idx": [0], "dense_right_idx": [0]},
+             {"dense_idx": [1, 0], "sparse_idx": [1], "dense_left_idx": np.arange(2), "dense_right_idx": [0]}]
+    micro = [{"active_nodes": [0, 5], "dense_in_dims": 64, "sparse_in_dims": 48, "dense_sparse_interact": 1, "deep_fm": 0},
+             {"active_nodes": np.asarray([1, 2, 4]), "dense_in_dims": np.int64(1024), "sparse_in_dims": 16,
+              "dense_sparse_interact": 0, "deep_fm": 1}]
+    enc = NativeNet.encode_choice(macro, micro)
+    assert enc.dtype == np.int32 and enc.shape == (2 * 49,)
+    b0, b1 = enc[:49], enc[49:]
+    assert b0[0] == 1 and b0[1] == 0 and b0[9] == 1 and b0[36] == 2 and list(b0[37:39]) == [0, 5]
+    assert list(b0[45:]) == [64, 48, 1, 0]
+    assert b1[0] == 2 and list(b1[1:3]) == [1, 0] and b1[18] == 2 and list(b1[19:21]) == [0, 1]
+    assert b1[36] == 3 and list(b1[37:40]) == [1, 2, 4] and list(b1[45:]) == [1024, 16, 0, 1]
+    with pytest.raises(ValueError):
+        NativeNet.encode_choice([{**macro[0], "dense_idx": list(range(9))}], micro[:1])
