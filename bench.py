@@ -301,7 +301,8 @@ def run_ours(args):
 
     # ---- value: inputs resident in HBM, per-step CUDA events, L2 flushed between steps ----
     clocks = ClockSampler(local)
-    clocks.start()
+    if rank == 0:                      # one sampler per job: rank 0's GPU stands for the box (same clocks policy)
+        clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     l0 = _lib.LIB.launches
     barrier()
