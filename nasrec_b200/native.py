@@ -363,7 +363,10 @@ class NativeTrainer(FusedTrainer):
                 m.materialize(int_x.shape[1])
             self.fallback_reason = NativeNet.unsupported_reason(m)
             if self.fallback_reason is None:
-                self.net = NativeNet(m, state_of=self._state_of)
+                try:
+                    self.net = NativeNet(m, state_of=self._state_of)
+                except (NotImplementedError, ValueError) as e:      # a model shape the executor does not describe
+                    self.fallback_reason = str(e)
         return self.net
 
     def _choice(self) -> np.ndarray:
