@@ -394,7 +394,7 @@ def sampler_fixture():
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps", "lr", "finetune", "tokenizer", "transform"]
+    which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps", "lr", "finetune", "tokenizer", "transform", "avazu"]
     if "samplers" in which:
         sampler_fixture()
     if "fixed" in which:
@@ -405,6 +405,8 @@ if __name__ == "__main__":
         supernet_fixture("supernet_xlarge_criteo", "criteo", "xlarge", nchoices=3)
     if "kdd" in which:
         supernet_fixture("supernet_xlarge_kdd", "kdd", "xlarge", nchoices=2)
+    if "avazu" in which:
+        supernet_fixture("supernet_xlarge_avazu", "avazu", "xlarge", nchoices=1)
     if "steps" in which:
         step_fixture()
     if "lr" in which:

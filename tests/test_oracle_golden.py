@@ -33,7 +33,8 @@ def _check_case(cfg, sd, ne, nd, ds, choice, B, seed, logits_ref, loss_ref, gn_r
         assert set(rows) <= set(sets[int(f)].tolist())
 
 
-@pytest.mark.parametrize("name", ["supernet_autoctr_criteo", "supernet_xlarge_criteo", "supernet_xlarge_kdd"])
+@pytest.mark.parametrize("name", ["supernet_autoctr_criteo", "supernet_xlarge_criteo", "supernet_xlarge_kdd",
+                                  "supernet_xlarge_avazu"])
 def test_oracle_matches_reference_supernet(name):
     meta, arr = load_golden(name)
     sd = orc.fill_state_dict(meta["shapes"], meta["state_seed"])
