@@ -259,3 +259,18 @@ def test_native_choice_encoding_layout():
     assert b1[36] == 3 and list(b1[37:40]) == [1, 2, 4] and list(b1[45:]) == [1024, 16, 0, 1]
     with pytest.raises(ValueError):
         NativeNet.encode_choice([{**macro[0], "dense_idx": list(range(9))}], micro[:1])
+
+
+def test_public_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/nasrec_b200.h must compile as C99 on its own
+    (no C++ or torch types in any signature)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "nasrec_b200.h")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)          # declarations only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "std::" not in code and "Tensor" not in code
