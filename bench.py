@@ -255,8 +255,7 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-    K, W = args.steps, args.warmup
-    assert W >= 3, "timing rules: at least 3 warm-up steps"
+    K, W = max(1, args.steps), max(3, args.warmup)      # timing rules: at least 3 warm-up steps (the line reports W)
 
     def barrier():
         if world > 1:
