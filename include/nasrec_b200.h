@@ -71,6 +71,25 @@ int nasrec_set_workspace(float* ws, int64_t nfloats);
  * stream == NULL detaches.  The split-K workspace is halved between the two streams while attached. */
 int nasrec_set_side_stream(void* stream);
 int nasrec_side_join(void* stream);
+/* TMA-fed operand path of the tensor-core GEMM (default on).  A launch takes it when every operand is
+ * 16-byte aligned with row strides that are multiples of 4 floats and -- for forward / dgrad -- the weight's
+ * pre-split planes have been announced with nasrec_set_weight_planes; anything else takes the LDG-producer
+ * kernel.  Both paths use the same arithmetic and agree to the last bit. */
+int nasrec_set_gemm_tma(int on);
+/* Pre-split copies of a [rows, cols] weight W (modules.py nn.LazyLinear weights keep the reference layout, whose
+ * row stride such as 1037 floats no tensor map can describe, and whose second concat source starts at column
+ * nd = 13 or F = 26, which no TMA box can start at): hi = rn_tf32(W), lo = W - hi, both [rows, ldp] with
+ * ldp % 4 == 0; W column c lives in plane column c + (c >= first ? shift : 0), shift = (4 - first % 4) % 4, all other
+ * plane columns zero (pass first = the width of the first concat source, or 0).  The announcement is a one-entry
+ * hint consumed by the GEMM entry points called next with the same W pointer (ldw == cols); W == NULL clears it.
+ * Keep the planes (zero-initialised by the caller) in step with W through nasrec_planes_refresh or
+ * nasrec_adagrad_multi_planes. */
+int nasrec_set_weight_planes(const float* W, const float* hi, const float* lo, int64_t ldp, int rows, int cols,
+                             int first);
+int nasrec_planes_refresh(const float* W, int64_t ldw, int rows, int cols, int first, float* hi, float* lo,
+                          int64_t ldp, void* stream);
+/* which = 0: tensor-map cache hits, 1: tensor maps encoded, 2: GEMM launches that took the TMA path */
+int64_t nasrec_tensor_map_stats(int which);
 
 /* ------------------------------------------------------------------ embedding
  * a1  SuperNet._input_stem_layers_bi_output, supernet.py:404-430:
@@ -266,6 +285,12 @@ int nasrec_grad_norm_clip(const float* const* grads, const int64_t* sizes, int n
 int nasrec_adagrad_multi(float* const* w, const float* const* grads, float* const* state,
                          const int64_t* sizes, int n, float lr, float eps, const float* clip_coef,
                          void* stream);
+/* Same, and rewrites the hi/lo planes (nasrec_set_weight_planes) of every tensor i with hi[i] != NULL from the
+ * updated weights in the same pass (cols[i] = row length of w[i], first[i] / ldp[i] as for nasrec_set_weight_planes). */
+int nasrec_adagrad_multi_planes(float* const* w, const float* const* grads, float* const* state,
+                                const int64_t* sizes, int n, float lr, float eps, const float* clip_coef,
+                                float* const* hi, float* const* lo, const int* cols, const int* first,
+                                const int64_t* ldp, void* stream);
 
 /* ---------------------------------------------------------------- step executor
  * The whole hot path behind one handle: SuperNet.forward (supernet.py:513-603), SuperNetBlock.forward
@@ -292,6 +317,10 @@ void* nasrec_net_create(const int* desc_i, int desc_len, int n_params, float* co
 void nasrec_net_destroy(void* net);
 int nasrec_net_set_arenas(void* net, void* act, int64_t act_bytes, void* pgrad, int64_t pgrad_bytes);
 int nasrec_net_set_requires_grad(void* net, const int* req, int n_params);
+/* hi/lo planes per parameter (HOST arrays of n_params device pointers, NULL entries = none; ldp in floats, first as above): the
+ * executor announces them to the GEMM entry points and keeps them in step inside nasrec_net_apply. */
+int nasrec_net_set_planes(void* net, float* const* hi, float* const* lo, const int64_t* ldp, const int* first,
+                          int n_params);
 int nasrec_net_set_overlap(void* net, int on);      /* join the side stream (nasrec_set_side_stream) after backward */
 /* Data-parallel overlap: during nasrec_net_forward_backward, cb(offset_bytes, nbytes) is called on the host each
  * time a block's parameter gradients are final -- the byte range of the gradient bucket sealed since the last call,

@@ -61,6 +61,8 @@ _SIGS = {
     "nasrec_bce_fwd_bwd": ([_f, _f, _i, _fl, _f, _f, _f], 1),
     "nasrec_grad_norm_clip": ([_f, _f, _i, _f, _i, _fl, _f, _f, _f], 2),
     "nasrec_adagrad_multi": ([_f, _f, _f, _f, _i, _fl, _fl, _f, _f], 1),
+    "nasrec_adagrad_multi_planes": ([_f, _f, _f, _f, _i, _fl, _fl, _f, _f, _f, _f, _f, _f, _f], 1),
+    "nasrec_planes_refresh": ([_f, _l, _i, _i, _i, _f, _f, _l, _f], 1),
     "nasrec_binary_metrics": ([_f, _f, _l, _f, _l, _f, _f], 6),     # prepare, sort (3 passes), scan, pairs, final
     "nasrec_input_transform": ([_f, _l, _l, _i, _f, _l, _l, _i, _i, _f, _l, _f, _f, _f, _f], 1),
 }
@@ -70,8 +72,10 @@ _SIGS_I64 = {
     "nasrec_sumsq_ws_floats": [_f, _i],
     "nasrec_binary_metrics_ws_bytes": [_l],
 }
+_SIGS_I64["nasrec_tensor_map_stats"] = [_i]
 EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace",
-           "nasrec_set_side_stream", "nasrec_side_join"] + list(_SIGS) + list(_SIGS_I64)
+           "nasrec_set_side_stream", "nasrec_side_join", "nasrec_set_gemm_tma",
+           "nasrec_set_weight_planes"] + list(_SIGS) + list(_SIGS_I64)
 
 
 class _Lib:
@@ -80,6 +84,9 @@ class _Lib:
         self.launches = 0          # kernels launched through this binding (bench.py's gpu_launches)
         self.workspace = None
         self.fn = {}
+        # bumped whenever dense weights are rewritten through raw pointers by a call that does NOT keep the
+        # pre-split weight planes in step (nasrec_b200/planes.py refreshes them on a mismatch)
+        self.weights_epoch = 0
 
     def load(self):
         if self.cdll is not None:
@@ -105,6 +112,13 @@ class _Lib:
         self.cdll.nasrec_set_workspace.restype = C.c_int
         self.cdll.nasrec_get_gemm_mode.argtypes = []
         self.cdll.nasrec_get_gemm_mode.restype = C.c_int
+        self.cdll.nasrec_set_gemm_tma.argtypes = [C.c_int]
+        self.cdll.nasrec_set_gemm_tma.restype = C.c_int
+        self.cdll.nasrec_set_weight_planes.argtypes = [_f, _f, _f, _l, _i, _i, _i]
+        self.cdll.nasrec_set_weight_planes.restype = C.c_int
+        tma = os.environ.get("NASREC_GEMM_TMA")
+        if tma is not None:
+            self.cdll.nasrec_set_gemm_tma(int(tma))
         mode = os.environ.get("NASREC_GEMM_MODE")
         if mode is not None:
             if self.cdll.nasrec_set_gemm_mode(int(mode)) != 0:
@@ -118,6 +132,16 @@ class _Lib:
         self.load()
         if self.cdll.nasrec_set_gemm_mode(int(mode)) != 0:
             raise ValueError("unsupported GEMM mode %r" % (mode,))
+
+    def set_gemm_tma(self, on: bool):
+        """TMA-fed operand path of the tensor-core GEMM on/off (both paths agree bit for bit)."""
+        self.load()
+        self.cdll.nasrec_set_gemm_tma(1 if on else 0)
+
+    def set_weight_planes(self, W: int, hi: int, lo: int, ldp: int, rows: int, cols: int, first: int = 0):
+        self.load()
+        if self.cdll.nasrec_set_weight_planes(W, hi, lo, ldp, rows, cols, first) != 0:
+            raise ValueError("nasrec_set_weight_planes rejected its arguments")
 
     def ensure_workspace(self, nfloats: int = 16 * 1024 * 1024):
         """Attach a split-K scratch buffer on the current CUDA device (kept alive here)."""
@@ -172,6 +196,8 @@ def call(name: str, *args):
             raise RuntimeError("%s failed: CUDA error %d" % (name, rc))
         raise ValueError("%s rejected its arguments (code %d)" % (name, rc))
     lib.launches += _SIGS[name][1]
+    if name == "nasrec_adagrad_multi":
+        lib.weights_epoch += 1
 
 
 def query(name: str, *args) -> int:

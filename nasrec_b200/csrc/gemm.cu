@@ -12,6 +12,9 @@
 // (:171,:223,:340,:359,:385,:489,:578,:584,:648,:740) and supernet.py:598,1140.
 #include "gemm_common.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
+#include <cstring>
+#include <cstddef>
 
 namespace {
 using namespace nasrec_gemm;
@@ -194,6 +197,46 @@ void mark_vec16(View& v) {
     v.vec16 = v.contig_j && jplain && iok && ((reinterpret_cast<uintptr_t>(v.p) & 15) == 0);
 }
 
+// Skinny launches (few output tiles, long K) leave most SMs idle: split K over several CTAs, partials into the
+// library workspace, fixed-order reduction (deterministic).  Shared by both tensor-core paths.
+template <class KTiles>
+void plan_split(Prob* prob, int nprob, KTiles ktiles_of, int maxN, cudaStream_t st, RedBatch& rb, int& totz) {
+    const long long ctas = nasrec_gemm::tc_cta_count(prob, nprob, nasrec_gemm::tc_pick_bn(prob, nprob, maxN));
+    float* wsb = nullptr;
+    long long wsn = 0;
+    ws_region(st, &wsb, &wsn);
+    if (!(wsb && ctas < 64)) return;
+    long long off = 0;
+    const int want = (int)(128 / (ctas > 0 ? ctas : 1));
+    for (int p = 0; p < nprob; ++p) {
+        Prob& pr = prob[p];
+        if (pr.nsplit != 1 || pr.c_sh_i != 0 || pr.c_hi_j != 1) continue;
+        if (pr.addend && pr.addend != pr.c) continue;
+        const int ktiles = ktiles_of(p);
+        int ns = want < ktiles / 4 ? want : ktiles / 4;
+        if (ns > 16) ns = 16;
+        const long long need = (long long)ns * pr.M * pr.N;
+        if (ns < 2 || off + need > wsn) continue;
+        RedSeg& rs = rb.seg[rb.nseg++];
+        rs.ws = wsb + off;
+        rs.c = pr.c;
+        rs.bias = pr.bias;
+        rs.ldc = pr.c_hi_i;
+        rs.M = pr.M;
+        rs.N = pr.N;
+        rs.nsplit = ns;
+        rs.accumulate = pr.addend != nullptr;
+        pr.c = wsb + off;
+        pr.c_hi_i = pr.N;
+        pr.bias = nullptr;
+        pr.addend = nullptr;
+        pr.nsplit = ns;
+        pr.split_stride = (long long)pr.M * pr.N;
+        off += need;
+        totz += ns - 1;
+    }
+}
+
 int launch(Batch& bt, cudaStream_t st) {
     for (int p = 0; p < bt.nprob; ++p)
         for (int t = 0; t < bt.prob[p].nterm; ++t) {
@@ -208,45 +251,12 @@ int launch(Batch& bt, cudaStream_t st) {
     }
     if (maxM <= 0 || maxN <= 0 || totz <= 0) return 0;
     if (g_gemm_mode != 0) {
-        // Skinny launches (few output tiles, long K) leave most SMs idle: split K over several CTAs,
-        // partials into the library workspace, fixed-order reduction (deterministic).
         RedBatch rb{};
-        const long long ctas = nasrec_gemm::tc_cta_count(bt, nasrec_gemm::tc_pick_bn(bt, maxN));
-        float* wsb = nullptr;
-        long long wsn = 0;
-        ws_region(st, &wsb, &wsn);
-        if (wsb && ctas < 64) {
-            long long off = 0;
-            const int want = (int)(128 / (ctas > 0 ? ctas : 1));
-            for (int p = 0; p < bt.nprob; ++p) {
-                Prob& pr = bt.prob[p];
-                if (pr.nsplit != 1 || pr.c_sh_i != 0 || pr.c_hi_j != 1) continue;
-                if (pr.addend && pr.addend != pr.c) continue;
-                int ktiles = 0;
-                for (int t = 0; t < pr.nterm; ++t) ktiles += (bt.term[pr.term0 + t].K + 31) / 32;
-                int ns = want < ktiles / 4 ? want : ktiles / 4;
-                if (ns > 16) ns = 16;
-                const long long need = (long long)ns * pr.M * pr.N;
-                if (ns < 2 || off + need > wsn) continue;
-                RedSeg& rs = rb.seg[rb.nseg++];
-                rs.ws = wsb + off;
-                rs.c = pr.c;
-                rs.bias = pr.bias;
-                rs.ldc = pr.c_hi_i;
-                rs.M = pr.M;
-                rs.N = pr.N;
-                rs.nsplit = ns;
-                rs.accumulate = pr.addend != nullptr;
-                pr.c = wsb + off;
-                pr.c_hi_i = pr.N;
-                pr.bias = nullptr;
-                pr.addend = nullptr;
-                pr.nsplit = ns;
-                pr.split_stride = (long long)pr.M * pr.N;
-                off += need;
-                totz += ns - 1;
-            }
-        }
+        plan_split(bt.prob, bt.nprob, [&](int p) {
+            int kt = 0;
+            for (int t = 0; t < bt.prob[p].nterm; ++t) kt += (bt.term[bt.prob[p].term0 + t].K + 31) / 32;
+            return kt;
+        }, maxN, st, rb, totz);
         int rc = nasrec_gemm::launch_tc(bt, maxM, maxN, totz, g_gemm_mode, st);
         if (rc || rb.nseg == 0) return rc;
         return launch_reduce(rb, st);
@@ -255,6 +265,403 @@ int launch(Batch& bt, cudaStream_t st) {
     if (grid.y > 65535 || grid.z > 65535) return NASREC_ETOOBIG;
     nasrec_launch(gemm64_kernel, grid, 256, 0, st, bt);
     return nasrec_launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------- TMA path
+// Host side of gemm_tma.cuh: which launches qualify, the tensor maps, and the per-launch operand layouts.
+int g_use_tma = 1;
+
+// Pre-split weight planes (nasrec_set_weight_planes): hi = rn_tf32(W), lo = W - hi, rows 16-byte aligned.
+// The reference's state-dict layout keeps row strides such as 1037 floats, which a tensor map cannot describe;
+// the planes are what forward and dgrad fetch by TMA instead (and they need no conversion in the kernel).
+struct Planes {
+    const float* W = nullptr;
+    const float* hi = nullptr;
+    const float* lo = nullptr;
+    long long ldp = 0;
+    int rows = 0, cols = 0;
+    int first = 0, shift = 0;      // plane column of W column c: c + (c >= first ? shift : 0)
+} g_pl;
+
+// A TMA box must start on a 16-byte boundary of the innermost dimension, and the reference layout puts the second
+// source of a concat at column nd (13) or F (26): the planes therefore shift every column >= `first` right by
+// `shift` (zero pad columns in between) so that all segment starts are multiples of 4 floats.
+inline long long plane_col(long long w_off) { return w_off + (w_off >= g_pl.first ? g_pl.shift : 0); }
+inline bool plane_seg_ok(long long w_off, long long width) {
+    if (width == 0) return true;
+    if (w_off < g_pl.first && w_off + width > g_pl.first) return false;
+    return (plane_col(w_off) & 3) == 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_encode_tried = false;
+
+bool have_encoder() {
+    if (!g_encode_tried) {
+        g_encode_tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode = (EncodeTiledFn)fn;
+        cudaGetLastError();
+    }
+    return g_encode != nullptr;
+}
+
+struct MapSpec {
+    const float* base;
+    uint64_t dim[4];
+    uint64_t stride[3];     // bytes, dims 1..rank-1
+    uint32_t box[4];
+    uint32_t rank;
+    uint32_t swz;           // 0: SWIZZLE_128B, 1: SWIZZLE_64B, 2: SWIZZLE_128B_ATOM_32B, 3: none
+};
+struct MapEnt {
+    MapSpec key;
+    CUtensorMap map;
+    bool valid;
+};
+constexpr int MAP_CACHE = 4096;
+MapEnt* g_map_cache = nullptr;
+long long g_map_hits = 0, g_map_misses = 0, g_tma_launches = 0;
+
+bool get_map(CUtensorMap* out, const MapSpec& sp) {
+    if (!g_map_cache) g_map_cache = new MapEnt[MAP_CACHE]();
+    uint64_t h = (uint64_t)(uintptr_t)sp.base * 0x9E3779B97F4A7C15ull;
+    h ^= (sp.dim[0] * 31 + sp.dim[1]) * 0xC2B2AE3D27D4EB4Full + sp.dim[2] * 0x165667B19E3779F9ull + sp.stride[0] * 13 + sp.box[1] * 7 +
+         sp.box[0] + sp.swz;
+    MapEnt& e = g_map_cache[(h >> 20) & (MAP_CACHE - 1)];
+    if (e.valid && std::memcmp(&e.key, &sp, sizeof(MapSpec)) == 0) {
+        *out = e.map;
+        ++g_map_hits;
+        return true;
+    }
+    ++g_map_misses;
+    cuuint64_t gdim[4] = {sp.dim[0], sp.dim[1], sp.dim[2], sp.dim[3]};
+    cuuint64_t gstr[3] = {sp.stride[0], sp.stride[1], sp.stride[2]};
+    cuuint32_t box[4] = {sp.box[0], sp.box[1], sp.box[2], sp.box[3]};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap m;
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)sp.rank, (void*)sp.base, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          sp.swz == 0 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                      : (sp.swz == 1 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                     : (sp.swz == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE)),
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    e.key = sp;
+    e.map = m;
+    e.valid = true;
+    *out = m;
+    return true;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+using nasrec_gemm::OpLayout;
+using nasrec_gemm::TBatch;
+using nasrec_gemm::TTerm;
+using nasrec_gemm::OP_KM128;
+using nasrec_gemm::OP_MN128;
+using nasrec_gemm::OP_MN3R;
+using nasrec_gemm::OP_KM64;
+
+OpLayout make_layout(int kind, int rows, int convert) {
+    OpLayout L{};
+    L.convert = convert;
+    const uint32_t ver = 1u << 14;
+    switch (kind) {
+    case OP_KM128:
+        L.rank = 2; L.nbox = 1; L.box_dim = 0; L.box_bytes = rows * 128;
+        L.rdim = 1; L.rsh = 0; L.kdim = 0; L.ksh = 0;
+        L.desc_hi32 = (1024u >> 4) | ver | (2u << 29); L.desc_lbo = 1;
+        for (int j = 0; j < 4; ++j) L.koff[j] = 32 * j;
+        L.tile_bytes = rows * 128; L.mn_major = 0;
+        break;
+    case OP_MN128:      // kind::tf32 accepts MN-major operands only in the 128-byte swizzle with 32-byte atoms: K atom = 4 rows
+        L.rank = 2; L.nbox = rows >= 32 ? rows / 32 : 1; L.box_dim = 0; L.box_bytes = 4096;
+        L.rdim = 0; L.rsh = 0; L.kdim = 1; L.ksh = 0;
+        L.desc_hi32 = (512u >> 4) | ver | (1u << 29); L.desc_lbo = 4096u >> 4;
+        for (int j = 0; j < 4; ++j) L.koff[j] = 1024 * j;
+        L.tile_bytes = L.nbox * 4096; L.mn_major = 1;
+        break;
+    case OP_MN3R:       // rows = (b, e): one plain box {16 e, 32 k, 8 b} lands in the lo plane; converters repack it to MN128
+        L.rank = 3; L.nbox = 1; L.box_dim = 0; L.box_bytes = 16384;
+        L.rdim = 2; L.rsh = 4; L.kdim = 1; L.ksh = 0;
+        L.desc_hi32 = (512u >> 4) | ver | (1u << 29); L.desc_lbo = 4096u >> 4;
+        for (int j = 0; j < 4; ++j) L.koff[j] = 1024 * j;
+        L.tile_bytes = 16384; L.mn_major = 1;
+        L.convert = 2;
+        break;
+    default:            // OP_KM64: k = (b, e): a 32-wide k-tile is 2 samples; one box {16 e, rows, 2 b}
+        L.rank = 3; L.nbox = 1; L.box_dim = 0; L.box_bytes = rows * 128;
+        L.rdim = 1; L.rsh = 0; L.kdim = 2; L.ksh = 4;
+        L.desc_hi32 = (512u >> 4) | ver | (4u << 29); L.desc_lbo = 1;
+        L.koff[0] = 0; L.koff[1] = 32; L.koff[2] = rows * 64; L.koff[3] = rows * 64 + 32;
+        L.tile_bytes = rows * 128; L.mn_major = 0;
+        break;
+    }
+    return L;
+}
+
+void set_box(MapSpec& sp, int kind, int rows) {
+    sp.swz = kind == OP_KM128 ? 0 : (kind == OP_KM64 ? 1 : (kind == OP_MN128 ? 2 : 3));
+    sp.box[3] = 1;
+    switch (kind) {
+    case OP_KM128: sp.box[0] = 32; sp.box[1] = (uint32_t)rows; sp.box[2] = 1; break;
+    case OP_MN128: sp.box[0] = 32; sp.box[1] = 32; sp.box[2] = 1; break;
+    case OP_MN3R: sp.box[0] = 16; sp.box[1] = 32; sp.box[2] = 8; break;
+    default: sp.box[0] = 16; sp.box[1] = (uint32_t)rows; sp.box[2] = 2; break;
+    }
+}
+
+MapSpec spec2d(const float* base, uint64_t inner, uint64_t outer, long long ld) {
+    MapSpec sp{};
+    sp.base = base; sp.rank = 2;
+    sp.dim[0] = inner; sp.dim[1] = outer; sp.dim[2] = 1; sp.dim[3] = 1;
+    sp.stride[0] = (uint64_t)ld * 4;
+    return sp;
+}
+MapSpec spec3d(const float* base, uint64_t rows, uint64_t B, long long bstride) {      // [B, rows, 16] tensor as (e, row, b)
+    MapSpec sp{};
+    sp.base = base; sp.rank = 3;
+    sp.dim[0] = NASREC_EMB_DIM; sp.dim[1] = rows; sp.dim[2] = B; sp.dim[3] = 1;
+    sp.stride[0] = NASREC_EMB_DIM * 4; sp.stride[1] = (uint64_t)bstride * 4;
+    return sp;
+}
+// Work description filled by the entry points before the tile width is known.
+struct TmaJob {
+    TBatch tb;
+    MapSpec spec[nasrec_gemm::TM_MAXMAPS];
+    int side[nasrec_gemm::TM_MAXMAPS];     // 0: A operand map, 1: B operand map
+    int nmap = 0;
+    int a_kind = 0, b_kind = 0, a_conv = 1, b_conv = 0;
+    int add(const MapSpec& sp, int which) {
+        spec[nmap] = sp;
+        side[nmap] = which;
+        return nmap++;
+    }
+};
+TmaJob* g_job = nullptr;       // one reusable job (host-side scratch; the library is single-threaded per process)
+
+TmaJob& fresh_job() {
+    if (!g_job) g_job = new TmaJob();
+    g_job->nmap = 0;
+    std::memset(&g_job->tb.nprob, 0, sizeof(TBatch) - offsetof(TBatch, nprob));
+    return *g_job;
+}
+
+template <int BNv>
+int launch_tma_job(TmaJob& job, int maxM, int maxN, int totz, cudaStream_t st) {
+    return nasrec_gemm::launch_tma_bn<BNv>(job.tb, maxM, maxN, totz, st);
+}
+
+int run_tma(TmaJob& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
+    TBatch& tb = job.tb;
+    int maxM = 0, maxN = 0, totz = 0;
+    for (int i = 0; i < tb.nprob; ++i) {
+        maxM = tb.prob[i].M > maxM ? tb.prob[i].M : maxM;
+        maxN = tb.prob[i].N > maxN ? tb.prob[i].N : maxN;
+        totz += tb.prob[i].nsplit;
+    }
+    if (maxM <= 0 || maxN <= 0 || totz <= 0) return 0;
+    RedBatch rb{};
+    plan_split(tb.prob, tb.nprob, [&](int p) {
+        int kt = 0;
+        for (int t = 0; t < tb.prob[p].nterm; ++t) kt += (tb.term[tb.prob[p].term0 + t].K + 31) / 32;
+        return kt;
+    }, maxN, st, rb, totz);
+    const int bn = nasrec_gemm::tc_pick_bn(tb.prob, tb.nprob, maxN);
+    tb.nprod = g_gemm_mode;
+    tb.la = make_layout(job.a_kind, nasrec_gemm::TC_BM, job.a_conv);
+    tb.lb = make_layout(job.b_kind, bn, job.b_conv);
+    for (int i = 0; i < job.nmap; ++i) {
+        set_box(job.spec[i], job.side[i] ? job.b_kind : job.a_kind, job.side[i] ? bn : nasrec_gemm::TC_BM);
+        if (!get_map(&tb.maps[i], job.spec[i])) return NASREC_EINVAL;
+    }
+    int rc;
+    switch (bn) {
+        case 16: rc = launch_tma_job<16>(job, maxM, maxN, totz, st); break;
+        case 32: rc = launch_tma_job<32>(job, maxM, maxN, totz, st); break;
+        case 64: rc = launch_tma_job<64>(job, maxM, maxN, totz, st); break;
+        default: rc = launch_tma_job<128>(job, maxM, maxN, totz, st); break;
+    }
+    if (rc) return rc;
+    ++g_tma_launches;
+    if (rb.nseg) rc = launch_reduce(rb, st);
+    if (rc) return rc;
+    if (extra_rb && extra_rb->nseg) rc = launch_reduce(*extra_rb, st);
+    return rc;
+}
+
+inline bool tma_on() { return g_use_tma && g_gemm_mode != 0 && have_encoder(); }
+inline bool planes_for(const float* W, long long ldw) {
+    return g_pl.W == W && g_pl.hi && (g_gemm_mode == 1 || g_pl.lo) && g_pl.cols == (int)ldw;
+}
+
+constexpr int NOT_TMA = -1000;     // "this launch does not qualify": the caller takes the LDG-producer kernel
+
+int tma_seg_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off, int N, const float* bias,
+                float* C, int64_t ldc, int M, cudaStream_t st) {
+    if (!tma_on() || !planes_for(W, ldw)) return NOT_TMA;
+    int live = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        if (!al16(segs[s].ptr) || (segs[s].ld & 3) || !plane_seg_ok(segs[s].w_off, segs[s].width)) return NOT_TMA;
+        ++live;
+    }
+    if (live + 2 > nasrec_gemm::TM_MAXMAPS || live > MAXT) return NOT_TMA;
+    TmaJob& job = fresh_job();
+    job.a_kind = OP_KM128; job.a_conv = 1; job.b_kind = OP_KM128; job.b_conv = 0;
+    const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
+    const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
+    TBatch& tb = job.tb;
+    tb.nprob = 1;
+    Prob& p = tb.prob[0];
+    p.M = M; p.N = N; p.term0 = 0;
+    p.c = C; p.c_hi_i = ldc; p.c_hi_j = 1;
+    p.bias = bias ? bias + n_off : nullptr;
+    p.nsplit = 1;
+    int nt = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        TTerm& t = tb.term[nt++];
+        t.K = (int)segs[s].width;
+        t.a_hi = t.a_lo = (short)job.add(spec2d(segs[s].ptr, segs[s].width, M, segs[s].ld), 0);
+        t.b_hi = (short)bh; t.b_lo = (short)bl;
+        t.b_base[0] = (int)plane_col(segs[s].w_off); t.b_base[1] = n_off;
+    }
+    p.nterm = nt;
+    return run_tma(job, st);
+}
+
+int tma_seg_dgrad(const float* dC, int64_t ldc, int N, const float* W, int64_t ldw, int n_off, const nasrec_seg_t* dsegs,
+                  int nseg, int M, int accumulate, cudaStream_t st) {
+    if (!tma_on() || !planes_for(W, ldw) || !al16(dC) || (ldc & 3)) return NOT_TMA;
+    TmaJob& job = fresh_job();
+    job.a_kind = OP_KM128; job.a_conv = 1; job.b_kind = OP_MN128; job.b_conv = 0;
+    const int ah = job.add(spec2d(dC, N, M, ldc), 0);
+    const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
+    const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
+    TBatch& tb = job.tb;
+    int np = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (dsegs[s].width == 0) continue;
+        if (np >= MAXP || !plane_seg_ok(dsegs[s].w_off, dsegs[s].width)) return NOT_TMA;
+        Prob& p = tb.prob[np];
+        TTerm& t = tb.term[np];
+        p.M = M; p.N = (int)dsegs[s].width; p.term0 = np; p.nterm = 1;
+        p.c = const_cast<float*>(dsegs[s].ptr); p.c_hi_i = dsegs[s].ld; p.c_hi_j = 1;
+        p.addend = accumulate ? dsegs[s].ptr : nullptr;
+        p.nsplit = 1;
+        t.K = N;
+        t.a_hi = t.a_lo = (short)ah;
+        t.b_hi = (short)bh; t.b_lo = (short)bl;
+        t.b_base[0] = (int)plane_col(dsegs[s].w_off); t.b_base[1] = n_off;     // B(n = column of the segment, k = output row)
+        ++np;
+    }
+    tb.nprob = np;
+    return run_tma(job, st);
+}
+
+int tma_seg_wgrad(const float* dC, int64_t ldc, int N, const nasrec_seg_t* segs, int nseg, float* dW, int64_t ldw, int n_off,
+                  int M, int accumulate, cudaStream_t st) {
+    if (!tma_on() || !al16(dC) || (ldc & 3)) return NOT_TMA;
+    int live = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        if (!al16(segs[s].ptr) || (segs[s].ld & 3)) return NOT_TMA;
+        ++live;
+    }
+    if (live + 1 > nasrec_gemm::TM_MAXMAPS || live > MAXP) return NOT_TMA;
+    TmaJob& job = fresh_job();
+    job.a_kind = OP_MN128; job.a_conv = 1; job.b_kind = OP_MN128; job.b_conv = 1;
+    const int ah = job.add(spec2d(dC, N, M, ldc), 0);          // A(i = output row, k = sample) = dC[k*ldc + i]
+    TBatch& tb = job.tb;
+    int np = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        Prob& p = tb.prob[np];
+        TTerm& t = tb.term[np];
+        p.M = N; p.N = (int)segs[s].width; p.term0 = np; p.nterm = 1;
+        p.c = dW + (long long)n_off * ldw + segs[s].w_off; p.c_hi_i = ldw; p.c_hi_j = 1;
+        p.addend = accumulate ? p.c : nullptr;
+        p.nsplit = 1;
+        t.K = M;
+        t.a_hi = t.a_lo = (short)ah;
+        t.b_hi = t.b_lo = (short)job.add(spec2d(segs[s].ptr, segs[s].width, M, segs[s].ld), 1);
+        ++np;
+    }
+    tb.nprob = np;
+    return run_tma(job, st);
+}
+
+int tma_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int P, const float* bias, float* Z,
+                  int64_t z_bstride, int B, cudaStream_t st) {
+    if (!tma_on() || !planes_for(W, ldw)) return NOT_TMA;
+    int live = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        if (!al16(segs[s].ptr) || (segs[s].ld & 3) || !plane_seg_ok(segs[s].w_off, segs[s].width)) return NOT_TMA;
+        ++live;
+    }
+    if (live + 2 > nasrec_gemm::TM_MAXMAPS || live > MAXT) return NOT_TMA;
+    TmaJob& job = fresh_job();
+    job.a_kind = OP_MN3R; job.a_conv = 1; job.b_kind = OP_KM128; job.b_conv = 0;
+    const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
+    const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
+    TBatch& tb = job.tb;
+    tb.nprob = 1;
+    Prob& p = tb.prob[0];
+    p.M = B * NASREC_EMB_DIM; p.N = P; p.term0 = 0;
+    p.c = Z; p.c_hi_i = z_bstride; p.c_lo_i = 1; p.c_sh_i = 4; p.c_hi_j = NASREC_EMB_DIM;
+    p.bias = bias;
+    p.nsplit = 1;
+    int nt = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        TTerm& t = tb.term[nt++];
+        t.K = (int)segs[s].width;
+        t.a_hi = t.a_lo = (short)job.add(spec3d(segs[s].ptr, segs[s].width, B, segs[s].ld), 0);
+        t.b_hi = (short)bh; t.b_lo = (short)bl;
+        t.b_base[0] = (int)plane_col(segs[s].w_off); t.b_base[1] = 0;
+    }
+    p.nterm = nt;
+    return run_tma(job, st);
+}
+
+int tma_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* W, int64_t ldw, const nasrec_seg_t* dsegs,
+                    int nseg, int B, int accumulate, cudaStream_t st) {
+    if (!tma_on() || !planes_for(W, ldw) || !al16(dZ) || (dz_bstride & 3)) return NOT_TMA;
+    TmaJob& job = fresh_job();
+    job.a_kind = OP_MN3R; job.a_conv = 1; job.b_kind = OP_MN128; job.b_conv = 0;
+    const int ah = job.add(spec3d(dZ, P, B, dz_bstride), 0);
+    const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
+    const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
+    TBatch& tb = job.tb;
+    int np = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (dsegs[s].width == 0) continue;
+        if (np >= MAXP || !plane_seg_ok(dsegs[s].w_off, dsegs[s].width)) return NOT_TMA;
+        Prob& p = tb.prob[np];
+        TTerm& t = tb.term[np];
+        p.M = B * NASREC_EMB_DIM; p.N = (int)dsegs[s].width; p.term0 = np; p.nterm = 1;
+        p.c = const_cast<float*>(dsegs[s].ptr);
+        p.c_hi_i = dsegs[s].ld; p.c_lo_i = 1; p.c_sh_i = 4; p.c_hi_j = NASREC_EMB_DIM;
+        p.addend = accumulate ? dsegs[s].ptr : nullptr;
+        p.nsplit = 1;
+        t.K = P;
+        t.a_hi = t.a_lo = (short)ah;
+        t.b_hi = (short)bh; t.b_lo = (short)bl;
+        t.b_base[0] = (int)plane_col(dsegs[s].w_off); t.b_base[1] = 0;        // B(n = r, k = p) = W[p*ldw + w_off + r]
+        ++np;
+    }
+    tb.nprob = np;
+    return run_tma(job, st);
 }
 
 bool segs_ok(const nasrec_seg_t* segs, int nseg) {
@@ -293,6 +700,10 @@ int nasrec_set_workspace(float* ws, int64_t nfloats) {
 int nasrec_seg_linear_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off, int N,
                           const float* bias, float* C, int64_t ldc, int M, void* stream) {
     CHECK_ARG(segs_ok(segs, nseg) && W && C && M > 0 && N > 0 && n_off >= 0);
+    {
+        const int rc = tma_seg_fwd(segs, nseg, W, ldw, n_off, N, bias, C, ldc, M, as_stream(stream));
+        if (rc != NOT_TMA) return rc;
+    }
     Batch bt{};
     bt.nprob = 1;
     Prob& p = bt.prob[0];
@@ -319,6 +730,10 @@ int nasrec_seg_linear_fwd(const nasrec_seg_t* segs, int nseg, const float* W, in
 int nasrec_seg_linear_dgrad(const float* dC, int64_t ldc, int N, const float* W, int64_t ldw, int n_off,
                             const nasrec_seg_t* dsegs, int nseg, int M, int accumulate, void* stream) {
     CHECK_ARG(segs_ok(dsegs, nseg) && dC && W && M > 0 && N > 0);
+    {
+        const int rc = tma_seg_dgrad(dC, ldc, N, W, ldw, n_off, dsegs, nseg, M, accumulate, as_stream(stream));
+        if (rc != NOT_TMA) return rc;
+    }
     Batch bt{};
     int np = 0;
     for (int s = 0; s < nseg; ++s) {
@@ -347,6 +762,10 @@ int nasrec_seg_linear_dgrad(const float* dC, int64_t ldc, int N, const float* W,
 int nasrec_seg_linear_wgrad(const float* dC, int64_t ldc, int N, const nasrec_seg_t* segs, int nseg, float* dW,
                             int64_t ldw, int n_off, int M, int accumulate, void* stream) {
     CHECK_ARG(segs_ok(segs, nseg) && dC && dW && M > 0 && N > 0);
+    {
+        const int rc = tma_seg_wgrad(dC, ldc, N, segs, nseg, dW, ldw, n_off, M, accumulate, as_stream(stream));
+        if (rc != NOT_TMA) return rc;
+    }
     Batch bt{};
     int np = 0;
     for (int s = 0; s < nseg; ++s) {
@@ -375,6 +794,10 @@ int nasrec_seg_linear_wgrad(const float* dC, int64_t ldc, int N, const nasrec_se
 int nasrec_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int P, const float* bias,
                      float* Z, int64_t z_bstride, int B, void* stream) {
     CHECK_ARG(segs_ok(segs, nseg) && W && Z && B > 0 && P > 0);
+    {
+        const int rc = tma_sproj_fwd(segs, nseg, W, ldw, P, bias, Z, z_bstride, B, as_stream(stream));
+        if (rc != NOT_TMA) return rc;
+    }
     Batch bt{};
     bt.nprob = 1;
     Prob& p = bt.prob[0];
@@ -410,6 +833,10 @@ int nasrec_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t
 int nasrec_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* W, int64_t ldw,
                        const nasrec_seg_t* dsegs, int nseg, int B, int accumulate, void* stream) {
     CHECK_ARG(segs_ok(dsegs, nseg) && dZ && W && B > 0 && P > 0);
+    {
+        const int rc = tma_sproj_dgrad(dZ, dz_bstride, P, W, ldw, dsegs, nseg, B, accumulate, as_stream(stream));
+        if (rc != NOT_TMA) return rc;
+    }
     Batch bt{};
     int np = 0;
     for (int s = 0; s < nseg; ++s) {
@@ -507,9 +934,46 @@ int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_
     bt.nprob = np;
     rb.nseg = np;
     if (np == 0) return 0;
+    bool tma_ok = tma_on() && al16(dZ) && !(dz_bstride & 3) && np + 1 <= nasrec_gemm::TM_MAXMAPS;
+    for (int s = 0; s < nseg && tma_ok; ++s)
+        if (segs[s].width > 0 && (!al16(segs[s].ptr) || (segs[s].ld & 3))) tma_ok = false;
+    if (tma_ok) {
+        TmaJob& job = fresh_job();
+        job.a_kind = OP_KM64; job.a_conv = 1; job.b_kind = OP_KM64; job.b_conv = 1;
+        const int ah = job.add(spec3d(dZ, P, B, dz_bstride), 0);
+        int q = 0;
+        for (int s = 0; s < nseg; ++s) {
+            if (segs[s].width == 0) continue;
+            job.tb.prob[q] = bt.prob[q];
+            TTerm& t = job.tb.term[q];
+            t.K = B * NASREC_EMB_DIM;
+            t.a_hi = t.a_lo = (short)ah;
+            t.b_hi = t.b_lo = (short)job.add(spec3d(segs[s].ptr, segs[s].width, B, segs[s].ld), 1);
+            ++q;
+        }
+        job.tb.nprob = np;
+        return run_tma(job, as_stream(stream), &rb);
+    }
     int rc = launch(bt, as_stream(stream));
     if (rc) return rc;
     return launch_reduce(rb, as_stream(stream));
 }
+
+int nasrec_set_gemm_tma(int on) {
+    g_use_tma = on ? 1 : 0;
+    return 0;
+}
+
+int nasrec_set_weight_planes(const float* W, const float* hi, const float* lo, int64_t ldp, int rows, int cols, int first) {
+    const int shift = (4 - (first & 3)) & 3;
+    if (W && (!hi || !al16(hi) || (lo && !al16(lo)) || (ldp & 3) || ldp < cols + shift || rows <= 0 || cols <= 0 || first < 0 ||
+              first > cols))
+        return NASREC_EINVAL;
+    g_pl.W = W; g_pl.hi = hi; g_pl.lo = lo; g_pl.ldp = ldp; g_pl.rows = rows; g_pl.cols = cols;
+    g_pl.first = first; g_pl.shift = shift;
+    return 0;
+}
+
+int64_t nasrec_tensor_map_stats(int which) { return which == 0 ? g_map_hits : (which == 1 ? g_map_misses : g_tma_launches); }
 
 }  // extern "C"

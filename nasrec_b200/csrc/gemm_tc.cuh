@@ -484,20 +484,22 @@ inline int launch_tc_bn(const Batch& bt, int maxM, int maxN, int totz, int nprod
 }
 
 // CTAs a launch would use with N-tile width bn
-inline long long tc_cta_count(const Batch& bt, int bn) {
+inline long long tc_cta_count(const Prob* prob, int nprob, int bn) {
     long long c = 0;
-    for (int i = 0; i < bt.nprob; ++i)
-        c += (long long)((bt.prob[i].M + TC_BM - 1) / TC_BM) * ((bt.prob[i].N + bn - 1) / bn) * bt.prob[i].nsplit;
+    for (int i = 0; i < nprob; ++i)
+        c += (long long)((prob[i].M + TC_BM - 1) / TC_BM) * ((prob[i].N + bn - 1) / bn) * prob[i].nsplit;
     return c;
 }
+inline long long tc_cta_count(const Batch& bt, int bn) { return tc_cta_count(bt.prob, bt.nprob, bn); }
 
 // widest N tile that still spreads the launch over most of the 148 SMs (one CTA per SM)
-inline int tc_pick_bn(const Batch& bt, int maxN) {
+inline int tc_pick_bn(const Prob* prob, int nprob, int maxN) {
     if (maxN <= 16) return 16;
-    if (maxN > 64 && tc_cta_count(bt, 128) >= 120) return 128;
-    if (maxN > 32 && tc_cta_count(bt, 64) >= 120) return 64;
-    return maxN <= 32 ? 32 : (tc_cta_count(bt, 32) > 296 ? 64 : 32);
+    if (maxN > 64 && tc_cta_count(prob, nprob, 128) >= 120) return 128;
+    if (maxN > 32 && tc_cta_count(prob, nprob, 64) >= 120) return 64;
+    return maxN <= 32 ? 32 : (tc_cta_count(prob, nprob, 32) > 296 ? 64 : 32);
 }
+inline int tc_pick_bn(const Batch& bt, int maxN) { return tc_pick_bn(bt.prob, bt.nprob, maxN); }
 
 inline int launch_tc(const Batch& bt, int maxM, int maxN, int totz, int nprod, cudaStream_t st) {
     switch (tc_pick_bn(bt, maxN)) {

@@ -49,7 +49,7 @@ struct Arena {
 };
 
 struct Var { float* t = nullptr; float* g = nullptr; bool req = false; int64_t n = 0; };
-struct Par { float* w; float* st; float* g; int64_t n; int rows, cols; bool req; };
+struct Par { float* w; float* st; float* g; int64_t n; int rows, cols; bool req; float* hi = nullptr; float* lo = nullptr; int64_t ldp = 0; int first = 0; };
 struct Seg { Var* v; int64_t off; int64_t ld; int64_t width; int64_t w_off; };
 using Segs = std::vector<Seg>;
 
@@ -138,6 +138,11 @@ struct Net {
 };
 
 inline bool preq(Net& n, int pi) { return pi >= 0 && n.par[pi].req; }
+// announce the weight's pre-split planes to the GEMM entry points called next (no planes: clears the hint)
+inline void hint_planes(const Par& W) {
+    if (W.hi) nasrec_set_weight_planes(W.w, W.hi, W.lo, W.ldp, W.rows, W.cols, W.first);
+    else nasrec_set_weight_planes(nullptr, nullptr, nullptr, 0, 0, 0, 0);
+}
 inline float* pw(Net& n, int pi) { return pi >= 0 ? n.par[pi].w : nullptr; }
 
 inline bool any_req(const Segs& s) { for (auto& x : s) if (x.v->req) return true; return false; }
@@ -262,6 +267,7 @@ Var* linear_ln(Net& n, const Segs& segs, int M, LinArgs a) {
     if (!out) { out = n.var((int64_t)M * a.d_out); ldy = a.d_out; }
     float *mean = nullptr, *rstd = nullptr;
     if (has_ln) { mean = n.act.alloc(M); rstd = n.act.alloc(M); }
+    hint_planes(W);
     ck(nasrec_linear_ln_fwd(sp, ns, W.w, ldw, a.n_off, N, pw(n, a.b), pw(n, a.lng), pw(n, a.lnb), LN_EPS, a.relu, a.d_out, z,
                             out->t + a.out_off, ldy, mean, rstd, a.accumulate, M, n.st), 2);
     const bool req = any_req(segs) || W.req || preq(n, a.b) || preq(n, a.lng) || preq(n, a.lnb);
@@ -281,6 +287,7 @@ Var* linear_ln(Net& n, const Segs& segs, int M, LinArgs a) {
         nasrec_seg_t sp[NASREC_MAX_SEGS], dsp[NASREC_MAX_SEGS];
         int flags[NASREC_MAX_SEGS];
         pack(segs, sp);
+        hint_planes(W);
         if (distinct_woffs(segs) && grad_targets(n, segs, dsp, flags)) {
             ck(nasrec_linear_ln_bwd(out->g + a.out_off, ldy, a.d_out, z, M, N, pw(n, a.lng), pw(n, a.lnb), mean, rstd, a.relu,
                                     sp, dsp, flags, ns, W.w, ldw, a.n_off, gw, gb, want_ln ? n.pgrad(a.lng) : nullptr,
@@ -339,6 +346,7 @@ Var* sproj_ln(Net& n, const Segs& segs, int B, SprojArgs a) {
     if (!out) { out = n.var((int64_t)B * a.p_out * E); obs = (int64_t)a.p_out * E; }
     float *mean = nullptr, *rstd = nullptr;
     if (has_ln) { mean = n.act.alloc((int64_t)B * E); rstd = n.act.alloc((int64_t)B * E); }
+    hint_planes(W);
     ck(nasrec_sproj_ln_fwd(sp, ns, W.w, ldw, P, pw(n, a.b), pw(n, a.lng), pw(n, a.lnb), LN_EPS, a.relu, a.p_out, z,
                            out->t + a.out_off, obs, mean, rstd, a.accumulate, B, n.st), 2);
     const bool req = any_req(segs) || W.req || preq(n, a.b) || preq(n, a.lng) || preq(n, a.lnb);
@@ -358,6 +366,7 @@ Var* sproj_ln(Net& n, const Segs& segs, int B, SprojArgs a) {
         nasrec_seg_t sp[NASREC_MAX_SEGS], dsp[NASREC_MAX_SEGS];
         int flags[NASREC_MAX_SEGS];
         pack(segs, sp);
+        hint_planes(W);
         if (distinct_woffs(segs) && grad_targets(n, segs, dsp, flags)) {
             float* ws = nullptr;
             if (gw) {
@@ -401,17 +410,18 @@ Var* sproj_ln(Net& n, const Segs& segs, int B, SprojArgs a) {
 // ------------------------------------------------------------------------------------------- small operators
 Var* dot_tril(Net& n, Var* x, Var* y, int B, int P) {
     const int R = (P + 1) * P / 2;
-    Var* out = n.var((int64_t)B * R);
-    ck(nasrec_dot_tril_fwd(x->t, E, y->t, (int64_t)P * E, P, out->t, R, B, n.st));
+    const int ldr = (R + 3) & ~3;          // 16-byte aligned rows (the consumer GEMM fetches them by TMA)
+    Var* out = n.var((int64_t)B * ldr);
+    ck(nasrec_dot_tril_fwd(x->t, E, y->t, (int64_t)P * E, P, out->t, ldr, B, n.st));
     out->req = x->req || y->req;
     if (!(n.tape_on && out->req)) return out;
     Net* np = &n;
-    n.record([np, x, y, B, P, R, out]() {
+    n.record([np, x, y, B, P, ldr, out]() {
         Net& n = *np;
         if (!out->g) return;
         float* dx = x->req ? n.act.alloc((int64_t)B * E) : nullptr;
         float* dy = y->req ? n.act.alloc((int64_t)B * P * E) : nullptr;
-        ck(nasrec_dot_tril_bwd(out->g, R, x->t, E, y->t, (int64_t)P * E, P, dx, E, dy, (int64_t)P * E, B, n.st));
+        ck(nasrec_dot_tril_bwd(out->g, ldr, x->t, E, y->t, (int64_t)P * E, P, dx, E, dy, (int64_t)P * E, B, n.st));
         if (dx) accumulate_into(n, x, dx);
         if (dy) accumulate_into(n, y, dy);
     });
@@ -562,7 +572,7 @@ BlockChoice decode(const int* c) {
     return bc;
 }
 
-struct DSrc { Var* v; int w; };
+struct DSrc { Var* v; int w; int ld; };
 struct SSrc { Var* v; int s, g; };
 
 bool is_dense_binary(int t) { return t == N_SUM || t == N_GATE; }
@@ -596,7 +606,7 @@ void run_block(Net& n, int bi, const BlockChoice& ch, const std::vector<DSrc>& d
         for (int j : idx) {
             if (j < 0 || j >= n_src || !have[j]) throw CallFailed(NASREC_EINVAL);
             const int64_t w_off = j == 0 ? 0 : n.nd + (int64_t)maxd * (j - 1);
-            segs.push_back(Seg{dsrc[j].v, 0, dsrc[j].w, dsrc[j].w, w_off});
+            segs.push_back(Seg{dsrc[j].v, 0, dsrc[j].ld, dsrc[j].w, w_off});
         }
         total = n_src > 1 ? n.nd + maxd * (n_src - 1) : n.nd;
         return segs;
@@ -662,7 +672,7 @@ void run_block(Net& n, int bi, const BlockChoice& ch, const std::vector<DSrc>& d
             const int nR = (P + 1) * P / 2;
             LinArgs o; o.W = p[8]; o.b = p[9]; o.lng = p[10]; o.lnb = p[11]; o.d_out = d;
             o.out = dense_out; o.ldy = d; o.accumulate = nd_w > 0;
-            linear_ln(n, Segs{Seg{R, 0, nR, nR, 0}}, B, o);
+            linear_ln(n, Segs{Seg{R, 0, (nR + 3) & ~3, nR, 0}}, B, o);
             ++nd_w;
         } break;
         case N_SUM: {
@@ -739,7 +749,7 @@ void run_block(Net& n, int bi, const BlockChoice& ch, const std::vector<DSrc>& d
         linear_ln(n, Segs{Seg{ix, 0, E, E, 0}}, B, a);
     }
     if (ch.dsi == 1 && !project) copy2d(n, dense_out, 0, d, B, d, sparse_out, (int64_t)s * E, (int64_t)rows * E, 0);
-    d_out = DSrc{dense_out, d};
+    d_out = DSrc{dense_out, d, d};
     s_out = SSrc{sparse_out, s, g};
 }
 
@@ -786,8 +796,12 @@ Var* forward(Net& n, const int* choice, const float* int_x, const int64_t* cat_x
     n.B = B;
     n.cat_x = cat_x;
     // stem
-    Var* x0 = n.var((int64_t)B * n.nd, false);
-    x0->t = const_cast<float*>(int_x);
+    // the dense input keeps the caller's [B, nd] layout; a row stride that is not a multiple of 4 floats (nd = 13)
+    // cannot be described by a tensor map, so it is staged once into a padded copy that TMA can fetch
+    const int nd_ld = (n.nd + 3) & ~3;
+    Var* x0 = n.var((int64_t)B * nd_ld, nd_ld != n.nd);
+    if (nd_ld != n.nd) ck(nasrec_act_fwd(int_x, n.nd, B, n.nd, 0, x0->t, nd_ld, 0, n.st));
+    else x0->t = const_cast<float*>(int_x);
     bool emb_req = false;
     for (int pi : n.emb_par) emb_req = emb_req || n.par[pi].req;
     Var* sp0 = n.var((int64_t)B * n.F * E, emb_rows == nullptr);
@@ -799,13 +813,13 @@ Var* forward(Net& n, const int* choice, const float* int_x, const int64_t* cat_x
         Net* np = &n;
         n.record([np, stem]() { np->emb_gout = stem->g; });
     }
-    std::vector<DSrc> dsrc{DSrc{x0, n.nd}};
+    std::vector<DSrc> dsrc{DSrc{x0, n.nd, nd_ld}};
     std::vector<SSrc> ssrc{SSrc{sp0, n.F, 0}};
     std::vector<bool> have{true};
     const std::vector<bool> need = liveness(n, ch);
     for (int i = 0; i < n.num_blocks; ++i) {
         if (!need[i + 1]) {
-            dsrc.push_back(DSrc{nullptr, 0});
+            dsrc.push_back(DSrc{nullptr, 0, 0});
             ssrc.push_back(SSrc{nullptr, 0, 0});
             have.push_back(false);
             continue;
@@ -822,7 +836,7 @@ Var* forward(Net& n, const int* choice, const float* int_x, const int64_t* cat_x
     const SSrc& sl = ssrc.back();
     const BlockDesc& last = n.blocks[n.num_blocks - 1];
     const int64_t bs = (int64_t)(sl.s + sl.g) * E;
-    Segs segs{Seg{dl.v, 0, dl.w, dl.w, 0}, Seg{sl.v, 0, bs, (int64_t)sl.s * E, last.maxd}};
+    Segs segs{Seg{dl.v, 0, dl.ld, dl.w, 0}, Seg{sl.v, 0, bs, (int64_t)sl.s * E, last.maxd}};
     if (sl.g) segs.push_back(Seg{sl.v, (int64_t)sl.s * E, bs, (int64_t)sl.g * E, last.maxd + (int64_t)last.maxs * E});
     LinArgs a; a.W = n.final_w; a.b = n.final_b; a.d_out = 1;
     return linear_ln(n, segs, B, a);
@@ -865,7 +879,7 @@ void* nasrec_net_create(const int* desc_i, int desc_len, int n_params, float* co
         n->blocks.push_back(bd);
     }
     if (o != desc_len) { delete n; return nullptr; }
-    for (int i = 0; i < n_params; ++i) n->par.push_back(Par{w[i], state ? state[i] : nullptr, nullptr, numel[i], rows[i], cols[i], req[i] != 0});
+    for (int i = 0; i < n_params; ++i) { Par p{}; p.w = w[i]; p.st = state ? state[i] : nullptr; p.g = nullptr; p.n = numel[i]; p.rows = rows[i]; p.cols = cols[i]; p.req = req[i] != 0; n->par.push_back(p); }
     n->d_tables = d_tables; n->d_rows = d_rows; n->d_table_ptrs_rw = d_tables_rw; n->d_state_ptrs = d_states; n->d_err = d_err;
     return n;
 }
@@ -885,6 +899,21 @@ int nasrec_net_set_requires_grad(void* net, const int* req, int n_params) {
     Net* n = (Net*)net;
     CHECK_ARG(n && req && n_params == (int)n->par.size());
     for (int i = 0; i < n_params; ++i) n->par[i].req = req[i] != 0;
+    return 0;
+}
+
+int nasrec_net_set_planes(void* net, float* const* hi, float* const* lo, const int64_t* ldp, const int* first, int n_params) {
+    Net* n = (Net*)net;
+    CHECK_ARG(n && n_params == (int)n->par.size());
+    for (int i = 0; i < n_params; ++i) {
+        Par& p = n->par[i];
+        if (hi && lo && ldp && first && hi[i] && lo[i]) {
+            CHECK_ARG(ldp[i] >= p.cols && (ldp[i] & 3) == 0 && first[i] >= 0 && first[i] <= p.cols);
+            p.hi = hi[i]; p.lo = lo[i]; p.ldp = ldp[i]; p.first = first[i];
+        } else {
+            p.hi = p.lo = nullptr; p.ldp = 0; p.first = 0;
+        }
+    }
     return 0;
 }
 
@@ -997,13 +1026,15 @@ int nasrec_net_apply(void* net, float lr, float eps, float max_norm, float* norm
             for (int e : n->emb_par) if (e == pi) is_emb = true;
             if (!is_emb && n->par[pi].g) dense.push_back(pi);
         }
-        std::vector<float*> w, s;
+        std::vector<float*> w, s, hi, lo;
         std::vector<const float*> g;
-        std::vector<int64_t> sz;
+        std::vector<int64_t> sz, ldp;
+        std::vector<int> cols, first;
         for (int pi : dense) {
             Par& p = n->par[pi];
             if (!p.st) throw CallFailed(NASREC_EINVAL);
             w.push_back(p.w); s.push_back(p.st); g.push_back(p.g); sz.push_back(p.n);
+            hi.push_back(p.hi); lo.push_back(p.lo); ldp.push_back(p.ldp); cols.push_back(p.cols); first.push_back(p.first);
         }
         const float* coef = nullptr;
         if (max_norm > 0.f) {
@@ -1013,7 +1044,8 @@ int nasrec_net_apply(void* net, float lr, float eps, float max_norm, float* norm
             coef = norm_out + 1;
         }
         if (!dense.empty())
-            ck(nasrec_adagrad_multi(w.data(), g.data(), s.data(), sz.data(), (int)sz.size(), lr, eps, coef, st));
+            ck(nasrec_adagrad_multi_planes(w.data(), g.data(), s.data(), sz.data(), (int)sz.size(), lr, eps, coef, hi.data(),
+                                           lo.data(), cols.data(), first.data(), ldp.data(), st));
         if (n->have_sparse)
             ck(nasrec_emb_rowwise_adagrad(n->uniq, n->nuniq, n->row_grad, n->d_table_ptrs_rw, n->d_state_ptrs, n->sB, n->F, lr,
                                           eps, coef, st));

@@ -92,7 +92,18 @@ struct AdagradPack {
     float* s[MT_MAX];
     long long size[MT_MAX];
     int chunk0[MT_MAX + 1];
+    // optional pre-split copies of w for the TMA-fed GEMM (gemm_tma.cuh): hi = rn_tf32(w), lo = w - hi, row stride ldp
+    float* hi[MT_MAX];
+    float* lo[MT_MAX];
+    int cols[MT_MAX];
+    int ldp[MT_MAX];
+    int first[MT_MAX];      // plane column of w column c: c + (c >= first ? shift : 0), shift = (4 - first % 4) % 4
 };
+
+__device__ __forceinline__ void plane_split(float w, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
+    lo = w - hi;
+}
 
 __global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ AdagradPack pk, float lr, float eps,
                                                       const float* __restrict__ clip_coef) {
@@ -106,6 +117,19 @@ __global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ Ad
     float* w = pk.w[t];
     const float* g = pk.g[t];
     float* s = pk.s[t];
+    float* ph = pk.hi[t];
+    float* pl = pk.lo[t];
+    const unsigned cols = (unsigned)pk.cols[t];
+    const long long ldp = pk.ldp[t];
+    const unsigned first = (unsigned)pk.first[t], shift = (4u - (first & 3u)) & 3u;
+    auto plane = [&](long long i, float wi) {          // flat index of w -> (row, col) of the padded planes
+        const unsigned r = (unsigned)i / cols, c = (unsigned)i - r * cols;
+        const unsigned pc = c + (c >= first ? shift : 0u);
+        float h, l;
+        plane_split(wi, h, l);
+        ph[r * ldp + pc] = h;
+        pl[r * ldp + pc] = l;
+    };
     auto upd = [&](float gi, float& si, float& wi) {
         const float gv = gi * coef;
         const float sv = fmaf(gv, gv, si);
@@ -127,10 +151,51 @@ __global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ Ad
             upd(gv.w, sv.w, wv.w);
             s4[i] = sv;
             w4[i] = wv;
+            if (ph) {
+                const long long e = beg + (i << 2);
+                if (ldp == (long long)cols && shift == 0) {      // planes have w's own layout: 16-byte stores
+                    float4 h4, l4;
+                    plane_split(wv.x, h4.x, l4.x);
+                    plane_split(wv.y, h4.y, l4.y);
+                    plane_split(wv.z, h4.z, l4.z);
+                    plane_split(wv.w, h4.w, l4.w);
+                    *reinterpret_cast<float4*>(ph + e) = h4;
+                    *reinterpret_cast<float4*>(pl + e) = l4;
+                } else {
+                    plane(e, wv.x);
+                    plane(e + 1, wv.y);
+                    plane(e + 2, wv.z);
+                    plane(e + 3, wv.w);
+                }
+            }
         }
-        for (long long i = beg + (n4 << 2) + threadIdx.x; i < end; i += blockDim.x) upd(g[i], s[i], w[i]);
+        for (long long i = beg + (n4 << 2) + threadIdx.x; i < end; i += blockDim.x) {
+            upd(g[i], s[i], w[i]);
+            if (ph) plane(i, w[i]);
+        }
     } else {
-        for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) upd(g[i], s[i], w[i]);
+        for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+            upd(g[i], s[i], w[i]);
+            if (ph) plane(i, w[i]);
+        }
+    }
+}
+
+// hi/lo planes of a [rows, cols] weight (row stride ldw) with row stride ldp; pad columns are left alone (zero)
+__global__ void __launch_bounds__(256) planes_refresh_kernel(const float* __restrict__ w, long long ldw, int rows, int cols,
+                                                             int first, float* __restrict__ hi, float* __restrict__ lo,
+                                                             long long ldp) {
+    pdl_enter();
+    const int shift = (4 - (first & 3)) & 3;
+    const long long total = (long long)rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols;
+        const int c = (int)(i - r * cols);
+        float h, l;
+        plane_split(w[r * ldw + c], h, l);
+        const long long o = r * ldp + c + (c >= first ? shift : 0);
+        hi[o] = h;
+        lo[o] = l;
     }
 }
 
@@ -179,9 +244,27 @@ int nasrec_grad_norm_clip(const float* const* grads, const int64_t* sizes, int n
     return nasrec_launch_status();
 }
 
+int nasrec_planes_refresh(const float* W, int64_t ldw, int rows, int cols, int first, float* hi, float* lo, int64_t ldp,
+                          void* stream) {
+    CHECK_ARG(W && hi && lo && rows > 0 && cols > 0 && first >= 0 && first <= cols && ldw >= cols);
+    CHECK_ARG(ldp >= cols + ((4 - (first & 3)) & 3));
+    const long long total = (long long)rows * cols;
+    long long gx = (total + 255) / 256;
+    if (gx > 2368) gx = 2368;
+    nasrec_launch(planes_refresh_kernel, (unsigned)gx, 256, 0, as_stream(stream), W, (long long)ldw, rows, cols, first, hi, lo, (long long)ldp);
+    return nasrec_launch_status();
+}
+
 int nasrec_adagrad_multi(float* const* w, const float* const* grads, float* const* state, const int64_t* sizes,
                          int n, float lr, float eps, const float* clip_coef, void* stream) {
+    return nasrec_adagrad_multi_planes(w, grads, state, sizes, n, lr, eps, clip_coef, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int nasrec_adagrad_multi_planes(float* const* w, const float* const* grads, float* const* state, const int64_t* sizes,
+                                int n, float lr, float eps, const float* clip_coef, float* const* hi, float* const* lo,
+                                const int* cols, const int* first, const int64_t* ldp, void* stream) {
     CHECK_ARG(n >= 0 && (n == 0 || (w && grads && state && sizes)));
+    CHECK_ARG(!hi || (lo && cols && first && ldp));
     cudaStream_t st = as_stream(stream);
     int done = 0;
     while (done < n) {
@@ -194,6 +277,14 @@ int nasrec_adagrad_multi(float* const* w, const float* const* grads, float* cons
             pk.size[m] = sizes[done + m];
             pk.chunk0[m] = chunks;
             chunks += (int)((sizes[done + m] + MT_CHUNK - 1) / MT_CHUNK);
+            if (hi && hi[done + m]) {
+                if (sizes[done + m] >= (1ll << 31)) return NASREC_ETOOBIG;
+                pk.hi[m] = hi[done + m];
+                pk.lo[m] = lo[done + m];
+                pk.cols[m] = cols[done + m];
+                pk.ldp[m] = (int)ldp[done + m];
+                pk.first[m] = first[done + m];
+            }
         }
         pk.chunk0[m] = chunks;
         pk.n = m;

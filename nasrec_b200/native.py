@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .planes import PlaneCache
 from .supernet.supernet import EMB, SuperNet, _ints
 from .utils.train_utils import FusedTrainer
 
@@ -31,6 +32,7 @@ _PROTOS = {
     "nasrec_net_destroy": ([_vp], None),
     "nasrec_net_set_arenas": ([_vp, _vp, _l, _vp, _l], _i),
     "nasrec_net_set_requires_grad": ([_vp, _vp, _i], _i),
+    "nasrec_net_set_planes": ([_vp, _vp, _vp, _vp, _vp, _i], _i),
     "nasrec_net_set_overlap": ([_vp, _i], _i),
     "nasrec_net_set_seal_callback": ([_vp, _vp], _i),
     "nasrec_net_forward": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp], _i),
@@ -179,6 +181,38 @@ class NativeNet:
             tb.err.data_ptr())
         if not self.handle:
             raise RuntimeError("nasrec_net_create failed")
+        self._plane_gen = -1
+        self._sync_planes()
+
+    def _sync_planes(self):
+        """Weight planes for the TMA-fed GEMM (nasrec_b200/planes.py): rebuild what changed behind the executor's
+        back and (re)announce the pointers when plane storage was (re)allocated."""
+        cache = PlaneCache.of(self.model)
+        emb = {id(e.weight) for e in self.model._embedding}
+        if self._plane_gen < 0:
+            self._plane_params = [p for p in self.params if id(p) not in emb and PlaneCache.wanted(p)]
+            self._vsum = -1
+        vsum = 0
+        for p in self._plane_params:          # cheap per-step check; storage moves are caught by refresh()'s signature
+            vsum += p._version
+        if vsum == self._vsum and cache.epoch == _lib.LIB.weights_epoch and cache.generation == self._plane_gen:
+            return
+        cache.sync(self._plane_params)
+        self._vsum = vsum
+        if cache.generation != self._plane_gen:
+            n = len(self.params)
+            hi, lo, ld, first = [None] * n, [None] * n, [0] * n, [0] * n
+            for p in self._plane_params:
+                h, l, ldp, f = cache.planes(p)
+                i = self._index[id(p)]
+                hi[i], lo[i], ld[i], first[i] = h.data_ptr(), l.data_ptr(), ldp, f
+            self._ldp = np.asarray(ld, dtype=np.int64)
+            self._first = np.asarray(first, dtype=np.int32)
+            _check(_fn("nasrec_net_set_planes")(self.handle, C.cast((C.c_void_p * n)(*hi), C.c_void_p),
+                                                C.cast((C.c_void_p * n)(*lo), C.c_void_p), self._ldp.ctypes.data,
+                                                self._first.ctypes.data, n),
+                   "nasrec_net_set_planes")
+            self._plane_gen = cache.generation
 
     def _signature(self):
         return (self.params[0].data_ptr(), self.params[-1].data_ptr(), len(self.params))
@@ -213,6 +247,7 @@ class NativeNet:
             self._build()
             _check(_fn("nasrec_net_set_arenas")(self.handle, self.act.data_ptr(), self.act.numel(), self.pg.data_ptr(),
                                                 self.pg.numel()), "nasrec_net_set_arenas")
+        self._sync_planes()
         req = [p.requires_grad for p in self.params]
         if req != self._req_list:
             self._req_list = req
