@@ -197,26 +197,25 @@ void mark_vec16(View& v) {
     v.vec16 = v.contig_j && jplain && iok && ((reinterpret_cast<uintptr_t>(v.p) & 15) == 0);
 }
 
-// Skinny launches (few output tiles, long K) leave most SMs idle: split K over several CTAs, partials into the
-// library workspace, fixed-order reduction (deterministic).  Shared by both tensor-core paths.
+// Tile width + split-K plan of one launch, shared by both tensor-core paths (so that they sum in the same order and agree
+// bit for bit).  Skinny launches (few output tiles, long K) leave most SMs idle: their K range is split over several CTAs,
+// partials go to the library workspace and a fixed-order reduction follows (deterministic).
 template <class KTiles>
-void plan_split(Prob* prob, int nprob, KTiles ktiles_of, int maxN, cudaStream_t st, RedBatch& rb, int& totz) {
-    const long long ctas = nasrec_gemm::tc_cta_count(prob, nprob, nasrec_gemm::tc_pick_bn(prob, nprob, maxN));
+int plan_tiles(Prob* prob, int nprob, KTiles ktiles_of, int maxN, cudaStream_t st, RedBatch& rb, int& totz) {
     float* wsb = nullptr;
     long long wsn = 0;
     ws_region(st, &wsb, &wsn);
-    if (!(wsb && ctas < 64)) return;
+    const int bn = nasrec_gemm::tc_pick_bn(prob, nprob, maxN, ktiles_of, wsb != nullptr);
+    const long long ctas = nasrec_gemm::tc_cta_count(prob, nprob, bn);
+    if (!wsb || ctas > nasrec_gemm::TC_SM_COUNT / 2) return bn;
     long long off = 0;
-    const int want = (int)(128 / (ctas > 0 ? ctas : 1));
     for (int p = 0; p < nprob; ++p) {
         Prob& pr = prob[p];
         if (pr.nsplit != 1 || pr.c_sh_i != 0 || pr.c_hi_j != 1) continue;
         if (pr.addend && pr.addend != pr.c) continue;
-        const int ktiles = ktiles_of(p);
-        int ns = want < ktiles / 4 ? want : ktiles / 4;
-        if (ns > 16) ns = 16;
+        const int ns = nasrec_gemm::tc_split_for(ctas, ktiles_of(p));
         const long long need = (long long)ns * pr.M * pr.N;
-        if (ns < 2 || off + need > wsn) continue;
+        if (ns < 2 || off + need > wsn || rb.nseg >= NASREC_MAX_SEGS) continue;
         RedSeg& rs = rb.seg[rb.nseg++];
         rs.ws = wsb + off;
         rs.c = pr.c;
@@ -235,6 +234,7 @@ void plan_split(Prob* prob, int nprob, KTiles ktiles_of, int maxN, cudaStream_t 
         off += need;
         totz += ns - 1;
     }
+    return bn;
 }
 
 int launch(Batch& bt, cudaStream_t st) {
@@ -252,12 +252,12 @@ int launch(Batch& bt, cudaStream_t st) {
     if (maxM <= 0 || maxN <= 0 || totz <= 0) return 0;
     if (g_gemm_mode != 0) {
         RedBatch rb{};
-        plan_split(bt.prob, bt.nprob, [&](int p) {
+        const int bn = plan_tiles(bt.prob, bt.nprob, [&](int p) {
             int kt = 0;
             for (int t = 0; t < bt.prob[p].nterm; ++t) kt += (bt.term[bt.prob[p].term0 + t].K + 31) / 32;
             return kt;
         }, maxN, st, rb, totz);
-        int rc = nasrec_gemm::launch_tc(bt, maxM, maxN, totz, g_gemm_mode, st);
+        int rc = nasrec_gemm::launch_tc(bt, bn, maxM, maxN, totz, g_gemm_mode, st);
         if (rc || rb.nseg == 0) return rc;
         return launch_reduce(rb, st);
     }
@@ -367,39 +367,38 @@ using nasrec_gemm::TBatch;
 using nasrec_gemm::TTerm;
 using nasrec_gemm::OP_KM128;
 using nasrec_gemm::OP_MN128;
-using nasrec_gemm::OP_MN3R;
+using nasrec_gemm::OP_MN3;
 using nasrec_gemm::OP_KM64;
 
 OpLayout make_layout(int kind, int rows, int convert) {
     OpLayout L{};
+    L.kind = kind;
     L.convert = convert;
     const uint32_t ver = 1u << 14;
+    for (int d = 0; d < 4; ++d) L.rsh[d] = L.ksh[d] = 31;
     switch (kind) {
     case OP_KM128:
         L.rank = 2; L.nbox = 1; L.box_dim = 0; L.box_bytes = rows * 128;
-        L.rdim = 1; L.rsh = 0; L.kdim = 0; L.ksh = 0;
+        L.rsh[1] = 0; L.ksh[0] = 0;
         L.desc_hi32 = (1024u >> 4) | ver | (2u << 29); L.desc_lbo = 1;
         for (int j = 0; j < 4; ++j) L.koff[j] = 32 * j;
         L.tile_bytes = rows * 128; L.mn_major = 0;
         break;
     case OP_MN128:      // kind::tf32 accepts MN-major operands only in the 128-byte swizzle with 32-byte atoms: K atom = 4 rows
         L.rank = 2; L.nbox = rows >= 32 ? rows / 32 : 1; L.box_dim = 0; L.box_bytes = 4096;
-        L.rdim = 0; L.rsh = 0; L.kdim = 1; L.ksh = 0;
+        L.rsh[0] = 0; L.ksh[1] = 0;
         L.desc_hi32 = (512u >> 4) | ver | (1u << 29); L.desc_lbo = 4096u >> 4;
         for (int j = 0; j < 4; ++j) L.koff[j] = 1024 * j;
         L.tile_bytes = L.nbox * 4096; L.mn_major = 1;
         break;
-    case OP_MN3R:       // rows = (b, e): one plain box {16 e, 32 k, 8 b} lands in the lo plane; converters repack it to MN128
+    case OP_MN3:        // A only; rows = (b, e): one plain box {16 e, 32 k, 8 b}, read by the converters as it lands
         L.rank = 3; L.nbox = 1; L.box_dim = 0; L.box_bytes = 16384;
-        L.rdim = 2; L.rsh = 4; L.kdim = 1; L.ksh = 0;
-        L.desc_hi32 = (512u >> 4) | ver | (1u << 29); L.desc_lbo = 4096u >> 4;
-        for (int j = 0; j < 4; ++j) L.koff[j] = 1024 * j;
+        L.rsh[2] = 4; L.ksh[1] = 0;
         L.tile_bytes = 16384; L.mn_major = 1;
-        L.convert = 2;
         break;
     default:            // OP_KM64: k = (b, e): a 32-wide k-tile is 2 samples; one box {16 e, rows, 2 b}
         L.rank = 3; L.nbox = 1; L.box_dim = 0; L.box_bytes = rows * 128;
-        L.rdim = 1; L.rsh = 0; L.kdim = 2; L.ksh = 4;
+        L.rsh[1] = 0; L.ksh[2] = 4;
         L.desc_hi32 = (512u >> 4) | ver | (4u << 29); L.desc_lbo = 1;
         L.koff[0] = 0; L.koff[1] = 32; L.koff[2] = rows * 64; L.koff[3] = rows * 64 + 32;
         L.tile_bytes = rows * 128; L.mn_major = 0;
@@ -414,7 +413,7 @@ void set_box(MapSpec& sp, int kind, int rows) {
     switch (kind) {
     case OP_KM128: sp.box[0] = 32; sp.box[1] = (uint32_t)rows; sp.box[2] = 1; break;
     case OP_MN128: sp.box[0] = 32; sp.box[1] = 32; sp.box[2] = 1; break;
-    case OP_MN3R: sp.box[0] = 16; sp.box[1] = 32; sp.box[2] = 8; break;
+    case OP_MN3: sp.box[0] = 16; sp.box[1] = 32; sp.box[2] = 8; break;
     default: sp.box[0] = 16; sp.box[1] = (uint32_t)rows; sp.box[2] = 2; break;
     }
 }
@@ -470,12 +469,11 @@ int run_tma(TmaJob& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
     }
     if (maxM <= 0 || maxN <= 0 || totz <= 0) return 0;
     RedBatch rb{};
-    plan_split(tb.prob, tb.nprob, [&](int p) {
+    const int bn = plan_tiles(tb.prob, tb.nprob, [&](int p) {
         int kt = 0;
         for (int t = 0; t < tb.prob[p].nterm; ++t) kt += (tb.term[tb.prob[p].term0 + t].K + 31) / 32;
         return kt;
     }, maxN, st, rb, totz);
-    const int bn = nasrec_gemm::tc_pick_bn(tb.prob, tb.nprob, maxN);
     tb.nprod = g_gemm_mode;
     tb.la = make_layout(job.a_kind, nasrec_gemm::TC_BM, job.a_conv);
     tb.lb = make_layout(job.b_kind, bn, job.b_conv);
@@ -611,7 +609,7 @@ int tma_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ld
     }
     if (live + 2 > nasrec_gemm::TM_MAXMAPS || live > MAXT) return NOT_TMA;
     TmaJob& job = fresh_job();
-    job.a_kind = OP_MN3R; job.a_conv = 1; job.b_kind = OP_KM128; job.b_conv = 0;
+    job.a_kind = OP_MN3; job.a_conv = 1; job.b_kind = OP_KM128; job.b_conv = 0;
     const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
     const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
     TBatch& tb = job.tb;
@@ -638,7 +636,7 @@ int tma_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* W, 
                     int nseg, int B, int accumulate, cudaStream_t st) {
     if (!tma_on() || !planes_for(W, ldw) || !al16(dZ) || (dz_bstride & 3)) return NOT_TMA;
     TmaJob& job = fresh_job();
-    job.a_kind = OP_MN3R; job.a_conv = 1; job.b_kind = OP_MN128; job.b_conv = 0;
+    job.a_kind = OP_MN3; job.a_conv = 1; job.b_kind = OP_MN128; job.b_conv = 0;
     const int ah = job.add(spec3d(dZ, P, B, dz_bstride), 0);
     const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
     const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;

@@ -15,6 +15,7 @@
 // warp 8 = TMEM allocator + single-thread MMA issuer.  mbarrier pipeline: full[s] (256 producer
 // arrivals) / empty[s] (tcgen05.commit) / done (tcgen05.commit after the last k-tile).
 #pragma once
+#include <cstdlib>
 #include "gemm_common.cuh"
 
 namespace nasrec_gemm {
@@ -237,7 +238,9 @@ struct TcCfg {
     // fp32 accumulation truncates, so its error grows linearly with the number of MMAs chained
     // into one accumulator; spreading K over up to 8 accumulators brings it back to FFMA level.
     static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;
-    static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;
+    static constexpr int TMEM_COLS = 256;
+    // 128-wide tiles rotate over 2 accumulators only (the TMA kernel shares its 512 TMEM columns with the split A operand):
+    // they are chosen only together with split-K that leaves <= 16 k-tiles per CTA (tc_pick_bn), which bounds the chain
     static constexpr int NACC_MAX = TMEM_COLS / ACC_STRIDE < 8 ? TMEM_COLS / ACC_STRIDE : 8;
     static constexpr int CTAS_PER_SM = BN == 128 ? 1 : 2;
 };
@@ -492,17 +495,37 @@ inline long long tc_cta_count(const Prob* prob, int nprob, int bn) {
 }
 inline long long tc_cta_count(const Batch& bt, int bn) { return tc_cta_count(bt.prob, bt.nprob, bn); }
 
-// widest N tile that still spreads the launch over most of the 148 SMs (one CTA per SM)
-inline int tc_pick_bn(const Prob* prob, int nprob, int maxN) {
-    if (maxN <= 16) return 16;
-    if (maxN > 64 && tc_cta_count(prob, nprob, 128) >= 120) return 128;
-    if (maxN > 32 && tc_cta_count(prob, nprob, 64) >= 120) return 64;
-    return maxN <= 32 ? 32 : (tc_cta_count(prob, nprob, 32) > 296 ? 64 : 32);
+// Tile width.  One tcgen05.mma costs ~130 clk to issue whatever its N (measured, tools/mma_bench.cu), so the wider the
+// tile the fewer issue slots an output element costs; the SMs are filled by splitting K instead (plan_split, deterministic
+// fixed-order reduction).  128-wide tiles only when the split leaves each CTA <= 16 k-tiles (two accumulators).
+constexpr int TC_SM_COUNT = 148;
+inline int tc_split_for(long long ctas, int ktiles) {
+    if (ctas <= 0 || ctas > TC_SM_COUNT / 2) return 1;
+    int ns = (int)(TC_SM_COUNT / ctas);
+    if (ns > ktiles / 3) ns = ktiles / 3;
+    if (ns > 16) ns = 16;
+    return ns < 2 ? 1 : ns;
 }
-inline int tc_pick_bn(const Batch& bt, int maxN) { return tc_pick_bn(bt.prob, bt.nprob, maxN); }
+template <class KTiles>
+inline int tc_pick_bn(const Prob* prob, int nprob, int maxN, KTiles ktiles_of, bool can_split) {
+    static const int forced = getenv("NASREC_TC_BN") ? atoi(getenv("NASREC_TC_BN")) : 0;      // experiments only
+    if (forced) return forced;
+    if (maxN <= 16) return 16;
+    if (maxN <= 32) return 32;
+    if (maxN <= 64) return 64;
+    const long long c128 = tc_cta_count(prob, nprob, 128);
+    if (!can_split || c128 > TC_SM_COUNT / 2) return 64;
+    for (int p = 0; p < nprob; ++p) {
+        if (prob[p].N <= 64) continue;
+        const int kt = ktiles_of(p);
+        const int ns = prob[p].nsplit > 1 ? prob[p].nsplit : tc_split_for(c128, kt);
+        if ((kt + ns - 1) / ns > 16) return 64;
+    }
+    return 128;
+}
 
-inline int launch_tc(const Batch& bt, int maxM, int maxN, int totz, int nprod, cudaStream_t st) {
-    switch (tc_pick_bn(bt, maxN)) {
+inline int launch_tc(const Batch& bt, int bn, int maxM, int maxN, int totz, int nprod, cudaStream_t st) {
+    switch (bn) {
         case 16: return launch_tc_bn<16>(bt, maxM, maxN, totz, nprod, st);
         case 32: return launch_tc_bn<32>(bt, maxM, maxN, totz, nprod, st);
         case 64: return launch_tc_bn<64>(bt, maxM, maxN, totz, nprod, st);

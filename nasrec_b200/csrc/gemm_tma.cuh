@@ -1,21 +1,25 @@
-// TMA-fed tcgen05 path of the segment-list GEMM (sm_100a): no operand passes through registers on its way
-// from global memory to the tensor core.
+// TMA-fed tcgen05 path of the segment-list GEMM (sm_100a).
 //
-//   warp 9 (one lane)  producer: cp.async.bulk.tensor (TMA) of the raw fp32 operand tiles into the swizzled
-//                      shared-memory layouts the UMMA descriptors name; full[s] counts the landed bytes
-//   warps 0-7          converters: fp32 -> (hi = rn_tf32(x), lo = x - hi) in place, shared memory only
-//                      (weights arrive pre-split from their hi/lo planes and skip this step)
-//   warp 8 (one lane)  tcgen05.mma.kind::tf32 issuer, accumulators in TMEM, tcgen05.commit frees the stage
-//   warps 0-3          epilogue (same as gemm_tc.cuh: round-robin accumulators summed in fp32 registers)
+//   warp 9 (3 lanes)   producers: cp.async.bulk.tensor (TMA) of the raw fp32 A tile and of the B tile(s) into shared
+//                      memory, one lane per stream (A, B hi, B lo); full[s] counts the landed bytes
+//   warps 0-7          converters: A tile shared memory -> registers -> (hi = rn_tf32(x), lo = x - hi) -> TENSOR MEMORY
+//                      (tcgen05.st); a B tile that is an activation (weight gradients) is split in place in shared memory
+//   warp 8 (one lane)  tcgen05.mma.kind::tf32 issuer: A operand from TMEM, B operand from shared memory
+//                      (descriptor), accumulators in TMEM, tcgen05.commit frees the stage
+//   warps 0-3          epilogue (as gemm_tc.cuh: round-robin accumulators summed in fp32 registers)
 //
-// Arithmetic (split, product order, accumulator rotation, k-tile partition) is the one of gemm_tc.cuh, so the
-// two kernels agree to the last bit; what changes is how the bytes travel.  Operand layouts:
-//   KM128  K-major, SWIZZLE_128B: 2-D tensor (k, rows); activations / dY in forward and dgrad, weights forward
-//   MN128  MN-major, 128-byte swizzle of 32-byte chunks (the only MN-major layout kind::tf32 accepts): 2-D tensor
-//          (rows, k); weights in dgrad, both operands of wgrad
-//   MN3R   same shared-memory layout for the rows m = (b, e) of a [B, rows, 16] sparse tensor, whose contiguous runs
-//          are only 16 floats: TMA lands the plain 3-D box (e=16, k=r, b) in the lo plane and the converter warps
-//          repack it (two samples' lanes per 128-byte row) while they split it
+// Why A lives in TMEM: the 3xTF32 scheme issues three MMAs per k-step that re-read both operands.  With both in shared
+// memory a 128 x 32 x 32 k-tile costs ~60 KB of operand reads + 48 KB of converter traffic + 24 KB of TMA writes against
+// the SM's 128 B/clk shared-memory port: ~1000 clk per k-tile where the tensor core needs ~200 (ncu: profiles/r02_gemm.md).
+// Writing the split A planes to TMEM removes the converter stores and every A read from that port (B is the small
+// operand: BN x 32).
+//
+// Arithmetic (split, product order, accumulator rotation, k-tile partition) is the one of gemm_tc.cuh, so the two
+// kernels agree to the last bit; what changes is how the bytes travel.  Landing layouts of the raw tiles:
+//   KM128  K-major, SWIZZLE_128B: 2-D tensor (k, rows); activations / dY in forward and dgrad (A), weight planes (B)
+//   MN128  MN-major, 128-byte swizzle with 32-byte atoms (the only MN-major layout kind::tf32 accepts from shared
+//          memory): 2-D tensor (rows, k); weight planes in dgrad (B), both operands of wgrad
+//   MN3    plain 3-D box (e=16, k=r, b) of a [B, rows, 16] sparse tensor whose rows are m = (b, e) (A only)
 //   KM64   K-major, SWIZZLE_64B: 3-D tensor (e=16, rows, b): sparse-axis weight gradient (k = (b, e))
 // TMA zero-fills everything outside a tensor's extent, which is what the partial last k-tile of a segment needs.
 #pragma once
@@ -28,28 +32,30 @@ constexpr int TM_MAXMAPS = 20;
 constexpr int TM_CONV_WARPS = 8;
 constexpr int TM_CONV_THREADS = TM_CONV_WARPS * 32;
 constexpr int TM_THREADS = TM_CONV_THREADS + 64;       // + MMA warp + TMA warp
+constexpr int TM_SLOTS = 4;                            // TMEM slots of the split A tile (64 columns each)
+constexpr int TM_ACC_COLS = 256;                       // TMEM columns [0, 256): accumulators; [256, 512): A slots (hi 32 + lo 32 each)
 
-enum OpKind { OP_KM128 = 0, OP_MN128 = 1, OP_MN3R = 2, OP_KM64 = 3 };
+enum OpKind { OP_KM128 = 0, OP_MN128 = 1, OP_MN3 = 2, OP_KM64 = 3 };
 
 struct OpLayout {
-    int rank;               // tensor-map rank (2, 3 or 4)
+    int kind;               // OpKind (selects the converters' read pattern for A)
+    int rank;               // tensor-map rank
     int nbox;               // TMA boxes per tile; box i: coordinate[box_dim] += 32 * i, shared offset i * box_bytes
     int box_dim;
     int box_bytes;
-    int rdim, rsh;          // coordinate[rdim] += row0 >> rsh
-    int kdim, ksh;          // coordinate[kdim] += k0 >> ksh
-    uint32_t desc_hi32;     // constant upper word of the shared-memory descriptor (SBO, version, swizzle mode)
-    uint32_t desc_lbo;      // LBO >> 4
-    int koff[4];            // byte offset of each UMMA_K (8) step of a 32-wide k-tile
-    int tile_bytes;         // bytes of one plane of the tile (= what the converters walk and TMA delivers)
-    int mn_major;           // instruction-descriptor transpose bit
-    int convert;            // 0: lo plane fetched by TMA; 1: lo plane derived in the kernel from the raw tile;
-                            // 2: raw tile lands in the lo plane and is repacked into the MN128 layout while it is split
+    int rsh[4];             // coordinate[d] = base[d] + (row0 >> rsh[d]) + (k0 >> ksh[d]); shift 31 = no contribution
+    int ksh[4];
+    uint32_t desc_hi32;     // B only: constant upper word of the shared-memory descriptor (SBO, version, swizzle mode)
+    uint32_t desc_lbo;      // B only: LBO >> 4
+    int koff[4];            // B only: byte offset of each UMMA_K (8) step of a 32-wide k-tile
+    int tile_bytes;         // bytes of one plane of the tile
+    int mn_major;           // B only: instruction-descriptor transpose bit
+    int convert;            // B only: 1 = lo plane derived in the kernel from the raw tile; 0 = lo plane fetched by TMA
 };
 
 struct TTerm {
     int K;
-    short a_hi, a_lo, b_hi, b_lo;     // tensor-map indices (lo unused when the operand is converted in the kernel)
+    short a_hi, a_lo, b_hi, b_lo;     // tensor-map indices (a_lo unused: A is always split in the kernel)
     int a_base[4], b_base[4];         // coordinates of (row 0, k 0)
 };
 
@@ -77,74 +83,58 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-
-__device__ __forceinline__ void tma_tile(const OpLayout& L, const CUtensorMap* map, uint32_t dst, uint32_t bar, const int* base,
-                                         int row0, int k0) {
-    int c[4] = {base[0], base[1], base[2], base[3]};
-    c[L.rdim] += row0 >> L.rsh;
-    c[L.kdim] += k0 >> L.ksh;
-    for (int i = 0; i < L.nbox; ++i) {
-        if (L.rank == 2) tma_load_2d(dst, map, bar, c[0], c[1]);
-        else if (L.rank == 3) tma_load_3d(dst, map, bar, c[0], c[1], c[2]);
-        else tma_load_4d(dst, map, bar, c[0], c[1], c[2], c[3]);
-        dst += L.box_bytes;
-        c[L.box_dim] += 32;
-    }
-}
-
 __device__ __forceinline__ uint64_t tm_desc(const OpLayout& L, uint32_t saddr) {
     return (uint64_t)(((saddr >> 4) & 0x3FFFu) | (L.desc_lbo << 16)) | ((uint64_t)L.desc_hi32 << 32);
 }
 
-// hi = rn_tf32(x) written back in place, lo = x - hi into the lo plane at the same (swizzled) offset
-template <int NV>
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+
+// hi = rn_tf32(x) written back in place, lo = x - hi into the lo plane at the same (swizzled) offset (B tiles of wgrad)
+template <int NV, int NT>
 __device__ __forceinline__ void convert_tile(uint8_t* hi, uint8_t* lo, int nchunk, int tid) {
     float4 v[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        const int c = tid + q * TM_CONV_THREADS;
+        const int c = tid + q * NT;
         if (c < nchunk) v[q] = *reinterpret_cast<const float4*>(hi + (size_t)c * 16);
     }
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        const int c = tid + q * TM_CONV_THREADS;
+        const int c = tid + q * NT;
         if (c < nchunk) store_split4(hi, lo, (uint32_t)c * 16u, v[q], true);
-    }
-}
-
-// MN3R: the landed box is [b (8)][r (32)][16 floats]; chunk c = 4 floats.  Destination: sample pair b>>1 is a 4 KB MN atom,
-// k-row r a 128-byte row, (b&1, e>>3) its 32-byte chunk, XOR-swizzled with r&3 (SWIZZLE_128B_BASE32B).
-__device__ __forceinline__ void repack_tile(uint8_t* hi, uint8_t* lo, int tid, bool split) {
-    constexpr int NV = TC_BM * TC_BK * 4 / 16 / TM_CONV_THREADS;
-    float4 v[NV];
-#pragma unroll
-    for (int q = 0; q < NV; ++q) v[q] = *reinterpret_cast<const float4*>(lo + (size_t)(tid + q * TM_CONV_THREADS) * 16);
-    asm volatile("bar.sync 1, %0;" ::"n"(TM_CONV_THREADS) : "memory");       // everyone has read the landing zone
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        const int c = tid + q * TM_CONV_THREADS;
-        const int e4 = c & 3, r = (c >> 2) & 31, b = c >> 7;
-        const uint32_t dst = (uint32_t)((b >> 1) * 4096 + r * 128 + (((((b & 1) << 1) | (e4 >> 1)) ^ (r & 3)) << 5) + ((e4 & 1) << 4));
-        store_split4(hi, lo, dst, v[q], split);
     }
 }
 
 template <int BN>
 struct TmCfg {
-    static constexpr int A_BYTES = TC_BM * TC_BK * 4;                         // 16 KB per plane
+    static constexpr int A_BYTES = TC_BM * TC_BK * 4;                         // 16 KB raw landing zone
     static constexpr int B_BYTES = (BN < 32 ? 32 : BN) * TC_BK * 4;           // MN-major boxes are 32 wide
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = BN <= 32 ? 4 : (BN == 64 ? 4 : 3);          // 160 / 192 / 192 KB
+    static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = BN <= 32 ? 8 : (BN == 64 ? 6 : 4);          // 192 KB each: deep TMA prefetch, one CTA per SM
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
     static constexpr int ACC_STRIDE = TcCfg<BN>::ACC_STRIDE;
-    static constexpr int TMEM_COLS = TcCfg<BN>::TMEM_COLS;
     static constexpr int NACC_MAX = TcCfg<BN>::NACC_MAX;
+    static_assert(BN <= 128 && NACC_MAX * ACC_STRIDE <= TM_ACC_COLS, "accumulators and A slots share the 512 TMEM columns");
 };
 
 template <int BN>
@@ -184,20 +174,19 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const int ntiles = max(0, kt_end - kt_begin);
     const int nacc = min(Cfg::NACC_MAX, ntiles);
     const int nprod = tb.nprod;
-    const bool conv_a = (nprod > 1 && tb.la.convert) || tb.la.convert == 2, conv_b = nprod > 1 && tb.lb.convert;
+    const bool conv_b = nprod > 1 && tb.lb.convert;
 
     if (tid == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, TM_CONV_WARPS);
+            mbar_init(bar_conv + 8 * s, TM_CONV_WARPS / 2);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                     "r"((uint32_t)Cfg::TMEM_COLS)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -208,8 +197,20 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     pdl_wait();
 
     if (warp == 9) {
-        // ------------------------------------------------------------ TMA producer (one thread)
-        if (lane == 0 && ntiles > 0) {
+        // ------------------------------------------------------------ TMA producers: lane 0 A (raw), lane 1 B (hi / raw),
+        // lane 2 B lo -- one lane per stream so that the issue sequences run side by side
+        if (lane < 3 && ntiles > 0) {
+            const bool is_b = lane >= 1, is_lo = lane == 2;
+            const OpLayout& L = is_b ? tb.lb : tb.la;
+            const int rank = L.rank, nbox = L.nbox, box_bytes = L.box_bytes, box_dim = L.box_dim;
+            const bool b_lo = nprod > 1 && !tb.lb.convert;                     // the weight's lo plane is fetched, not derived
+            const bool active = !is_lo || b_lo;
+            const int row0 = is_b ? n0 : m0;
+            const int rp0 = row0 >> L.rsh[0], rp1 = row0 >> L.rsh[1], rp2 = row0 >> L.rsh[2];
+            const int ks0 = L.ksh[0], ks1 = L.ksh[1], ks2 = L.ksh[2];
+            const int bd0 = box_dim == 0 ? 32 : 0, bd1 = box_dim == 1 ? 32 : 0, bd2 = box_dim == 2 ? 32 : 0;
+            const uint32_t soff = is_b ? (uint32_t)(Cfg::A_BYTES + (is_lo ? Cfg::B_BYTES : 0)) : 0u;
+            const uint32_t tx = (uint32_t)(tb.la.nbox * tb.la.box_bytes + tb.lb.nbox * tb.lb.box_bytes * (b_lo ? 2 : 1));
             int t_cur = 0, kk = 0;
             {
                 int kt = 0;
@@ -222,52 +223,72 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     kt += nk;
                 }
             }
-            const bool a_lo = nprod > 1 && !tb.la.convert, b_lo = nprod > 1 && !tb.lb.convert;
-            const uint32_t tx = (uint32_t)(tb.la.nbox * tb.la.box_bytes * (a_lo ? 2 : 1) + tb.lb.nbox * tb.lb.box_bytes * (b_lo ? 2 : 1));
+            int K = 0, b0 = 0, b1 = 0, b2 = 0;
+            const CUtensorMap* map = nullptr;
+            auto load_term = [&](int t) {
+                const TTerm& tm = tb.term[pr.term0 + t];
+                K = tm.K;
+                const int mi = is_b ? (is_lo ? tm.b_lo : tm.b_hi) : tm.a_hi;
+                map = &tb.maps[mi];
+                const int* base = is_b ? tm.b_base : tm.a_base;
+                b0 = base[0] + rp0; b1 = base[1] + rp1; b2 = base[2] + rp2;
+            };
+            for (int t = 0; t < pr.nterm; ++t) {       // warm the descriptor cache for every map this lane will name
+                const TTerm& tm = tb.term[pr.term0 + t];
+                const int mi = is_b ? (is_lo ? tm.b_lo : tm.b_hi) : tm.a_hi;
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&tb.maps[mi]) : "memory");
+            }
+            load_term(t_cur);
+            const uint32_t tiles_u32 = smem_u32(tiles);
+#pragma unroll 1
             for (int it = 0; it < ntiles; ++it) {
-                while (kk * TC_BK >= tb.term[pr.term0 + t_cur].K) { ++t_cur; kk = 0; }
-                const TTerm& tm = tb.term[pr.term0 + t_cur];
+                while (kk * TC_BK >= K) { load_term(++t_cur); kk = 0; }
                 const int s = it % Cfg::STAGES;
                 const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                 const uint32_t full = bar_full + 8 * s;
-                mbar_expect_tx(full, tx);
-                const uint32_t st = smem_u32(tiles + s * Cfg::STAGE_BYTES);
-                const int k0 = kk * TC_BK;
-                tma_tile(tb.la, &tb.maps[tm.a_hi], st + (tb.la.convert == 2 ? Cfg::A_BYTES : 0), full, tm.a_base, m0, k0);
-                if (a_lo) tma_tile(tb.la, &tb.maps[tm.a_lo], st + Cfg::A_BYTES, full, tm.a_base, m0, k0);
-                tma_tile(tb.lb, &tb.maps[tm.b_hi], st + 2 * Cfg::A_BYTES, full, tm.b_base, n0, k0);
-                if (b_lo) tma_tile(tb.lb, &tb.maps[tm.b_lo], st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, full, tm.b_base, n0, k0);
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                if (lane == 0) mbar_expect_tx(full, tx);
+                __syncwarp(0x7u);
+                if (active) {
+                    const int k0 = kk * TC_BK;
+                    int c0 = b0 + (k0 >> ks0), c1 = b1 + (k0 >> ks1), c2 = b2 + (k0 >> ks2);
+                    uint32_t dst = tiles_u32 + (uint32_t)(s * Cfg::STAGE_BYTES) + soff;
+                    for (int i = 0; i < nbox; ++i) {
+                        if (rank == 2) tma_load_2d(dst, map, full, c0, c1);
+                        else tma_load_3d(dst, map, full, c0, c1, c2);
+                        dst += box_bytes;
+                        c0 += bd0; c1 += bd1; c2 += bd2;
+                    }
+                }
                 ++kk;
             }
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0 && ntiles > 0) {
-            const uint32_t idesc = umma_idesc_tf32(BN) | ((uint32_t)tb.la.mn_major << 15) | ((uint32_t)tb.lb.mn_major << 16);
+            const uint32_t idesc = umma_idesc_tf32(BN) | ((uint32_t)tb.lb.mn_major << 16);       // A from TMEM is K-major
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % Cfg::STAGES;
                 const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
                 mbar_wait(bar_full + 8 * s, ph);
-                if (conv_a || conv_b) mbar_wait(bar_conv + 8 * s, ph);
+                mbar_wait(bar_conv + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(tiles + s * Cfg::STAGE_BYTES);
-                const uint32_t sb = sa + 2 * Cfg::A_BYTES;
+                const uint32_t sb = smem_u32(tiles + s * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
+                const uint32_t ta = tmem + (uint32_t)(TM_ACC_COLS + (it % TM_SLOTS) * 64);
                 const uint32_t tacc = tmem + (uint32_t)((it % nacc) * Cfg::ACC_STRIDE);
 #pragma unroll
                 for (int k = 0; k < TC_BK / TC_UK; ++k) {
-                    const uint64_t a_hi = tm_desc(tb.la, sa + tb.la.koff[k]);
-                    const uint64_t a_lo = tm_desc(tb.la, sa + Cfg::A_BYTES + tb.la.koff[k]);
+                    const uint32_t a_hi = ta + (uint32_t)(k * TC_UK), a_lo = a_hi + 32u;
                     const uint64_t b_hi = tm_desc(tb.lb, sb + tb.lb.koff[k]);
                     const uint64_t b_lo = tm_desc(tb.lb, sb + Cfg::B_BYTES + tb.lb.koff[k]);
                     const uint32_t first = (it >= nacc || k > 0) ? 1u : 0u;
                     if (nprod > 1) {
-                        umma_tf32(tacc, a_lo, b_hi, idesc, first);
-                        umma_tf32(tacc, a_hi, b_lo, idesc, 1u);
-                        if (nprod > 3) umma_tf32(tacc, a_lo, b_lo, idesc, 1u);
-                        umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
+                        umma_tf32_ts(tacc, a_lo, b_hi, idesc, first);
+                        umma_tf32_ts(tacc, a_hi, b_lo, idesc, 1u);
+                        if (nprod > 3) umma_tf32_ts(tacc, a_lo, b_lo, idesc, 1u);
+                        umma_tf32_ts(tacc, a_hi, b_hi, idesc, 1u);
                     } else {
-                        umma_tf32(tacc, a_hi, b_hi, idesc, first);
+                        umma_tf32_ts(tacc, a_hi, b_hi, idesc, first);
                     }
                 }
                 umma_commit(bar_empty + 8 * s);
@@ -278,20 +299,80 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         tc_fence_before();
     } else {
         // ------------------------------------------------------------ converters (warps 0-7)
-        if (conv_a || conv_b) {
-            const int na = tb.la.tile_bytes >> 4, nb = tb.lb.tile_bytes >> 4;
+        // thread = one A row (TMEM lane 32 * (warp & 3) + lane); warps 0-3 convert the even k-tiles, warps 4-7 the odd ones,
+        // so that two tiles' load -> split -> TMEM-store latency chains are in flight at a time
+        {
+            const int q = warp & 3, g = warp >> 2;
+            const int m = q * 32 + lane;
+            const int akind = tb.la.kind;
+            const int nb = tb.lb.tile_bytes >> 4;
+            const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)TM_ACC_COLS;
+            const int ctid = tid & 127;
 #pragma unroll 1
-            for (int it = 0; it < ntiles; ++it) {
+            for (int it = g; it < ntiles; it += 2) {
                 const int s = it % Cfg::STAGES;
                 const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
                 mbar_wait(bar_full + 8 * s, ph);
-                uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
-                if (tb.la.convert == 2) repack_tile(st, st + Cfg::A_BYTES, tid, nprod > 1);
-                else if (conv_a) convert_tile<Cfg::A_BYTES / 16 / TM_CONV_THREADS>(st, st + Cfg::A_BYTES, na, tid);
-                if (conv_b)
-                    convert_tile<(Cfg::B_BYTES / 16 + TM_CONV_THREADS - 1) / TM_CONV_THREADS>(st + 2 * Cfg::A_BYTES,
-                                                                                             st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, nb, tid);
-                fence_proxy_async_smem();
+                const uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
+                if (it >= TM_SLOTS) {
+                    // the TMEM slot is free once the MMAs of k-tile it - TM_SLOTS have retired: their commit arrived on that
+                    // tile's empty barrier (which cannot complete again before this tile has been converted)
+                    const int jt = it - TM_SLOTS;
+                    mbar_wait(bar_empty + 8 * (jt % Cfg::STAGES), (uint32_t)(jt / Cfg::STAGES) & 1u);
+                    tc_fence_after();
+                }
+                const uint32_t ta = lane_base + (uint32_t)((it % TM_SLOTS) * 64);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float x[16];
+                    if (akind == OP_KM128) {
+                        // [128 rows][128 B], 16-byte chunks XOR-swizzled with row & 7: 4 chunks of this thread's row
+                        const uint8_t* rowp = st + m * 128;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 v = *reinterpret_cast<const float4*>(rowp + ((((h << 2) + c) ^ (m & 7)) << 4));
+                            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                        }
+                    } else if (akind == OP_MN128) {
+                        // 4 boxes of [32 k rows][32 rows x 4 B], 32-byte chunks XOR-swizzled with k & 3
+                        const uint8_t* boxp = st + (m >> 5) * 4096 + (m & 7) * 4;
+                        const int ch = (m & 31) >> 3;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int k = (h << 4) + j;
+                            x[j] = *reinterpret_cast<const float*>(boxp + k * 128 + ((ch ^ (k & 3)) << 5));
+                        }
+                    } else if (akind == OP_MN3) {
+                        // plain [8 samples][32 k rows][16 floats]; row m = (sample m >> 4, lane m & 15)
+                        const uint8_t* bp = st + (m >> 4) * 2048 + (m & 15) * 4;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) x[j] = *reinterpret_cast<const float*>(bp + ((h << 4) + j) * 64);
+                    } else {
+                        // OP_KM64: [2 samples][128 rows][64 B], 16-byte chunks XOR-swizzled with (row >> 1) & 3; k = (sample h, e)
+                        const uint8_t* rowp = st + h * 8192 + m * 64;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ ((m >> 1) & 3)) << 4));
+                            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                        }
+                    }
+                    if (nprod > 1) {
+                        float hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) split_tf32(x[j], hi[j], lo[j]);
+                        tmem_st16(ta + (uint32_t)(h * 16), hi);
+                        tmem_st16(ta + 32u + (uint32_t)(h * 16), lo);
+                    } else {
+                        tmem_st16(ta + (uint32_t)(h * 16), x);
+                    }
+                }
+                if (conv_b) {
+                    uint8_t* bh = const_cast<uint8_t*>(st) + Cfg::A_BYTES;
+                    convert_tile<(Cfg::B_BYTES / 16 + 127) / 128, 128>(bh, bh + Cfg::B_BYTES, nb, ctid);
+                    fence_proxy_async_smem();
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_conv + 8 * s);
             }
@@ -339,9 +420,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     const int n = n0 + c0 + lane;
                     const float bias = (pr.bias && n < pr.N) ? __ldg(pr.bias + n) : 0.f;
                     for (int rr = 0; rr < 32; ++rr) {
-                        const int m = m0 + warp * 32 + rr;
-                        if (m >= pr.M || n >= pr.N) continue;
-                        const long long o = (long long)(m >> pr.c_sh_i) * pr.c_hi_i + (long long)(m & cmask) * pr.c_lo_i + n;
+                        const int mm = m0 + warp * 32 + rr;
+                        if (mm >= pr.M || n >= pr.N) continue;
+                        const long long o = (long long)(mm >> pr.c_sh_i) * pr.c_hi_i + (long long)(mm & cmask) * pr.c_lo_i + n;
                         float v = scratch[rr * 33 + lane] + bias;
                         if (pr.addend) v += pr.addend[o];
                         pr.c[o + (long long)split * pr.split_stride] = v;
@@ -366,8 +447,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Cfg::TMEM_COLS)
-                     : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
