@@ -108,6 +108,11 @@ int nasrec_emb_gather_fwd(const float* const* tables, const int64_t* num_rows, c
 int nasrec_emb_grad_sort_reduce(const int64_t* idx, const float* gout, int B, int F,
                                 int64_t* uniq, int* nuniq, float* row_grad, float* sumsq,
                                 int* seg_scratch, void* stream);
+/* Same with the forward gather's bounds check: ids outside [0, num_rows[f]) are dropped from the reduction (they
+ * would address rows that do not exist) and err_flag (device int, may be null) is OR-ed with 1. */
+int nasrec_emb_grad_sort_reduce_checked(const int64_t* idx, const int64_t* num_rows, int* err_flag,
+                                        const float* gout, int B, int F, int64_t* uniq, int* nuniq,
+                                        float* row_grad, float* sumsq, int* seg_scratch, void* stream);
 
 /* Scatter the reduced rows into dense zero-initialised [N_f,16] gradients (what
  * nn.Embedding.weight.grad holds in the reference). */
@@ -315,12 +320,18 @@ void* nasrec_net_create(const int* desc_i, int desc_len, int n_params, float* co
                         const float* const* d_tables, const int64_t* d_rows, float* const* d_tables_rw,
                         float* const* d_states, int* d_err);
 void nasrec_net_destroy(void* net);
+/* (Re)attaching arenas discards the current step: nasrec_net_sparse_reduce / nasrec_net_apply then return NASREC_EINVAL
+ * until the next nasrec_net_forward_backward. */
 int nasrec_net_set_arenas(void* net, void* act, int64_t act_bytes, void* pgrad, int64_t pgrad_bytes);
 int nasrec_net_set_requires_grad(void* net, const int* req, int n_params);
 /* hi/lo planes per parameter (HOST arrays of n_params device pointers, NULL entries = none; ldp in floats, first as above): the
  * executor announces them to the GEMM entry points and keeps them in step inside nasrec_net_apply. */
 int nasrec_net_set_planes(void* net, float* const* hi, float* const* lo, const int64_t* ldp, const int* first,
                           int n_params);
+/* Rows of the batch nasrec_net_sparse_reduce will be given (the all-gathered global batch under data parallelism; default:
+ * the step's own B).  forward_backward reserves the reduction's and the clip's scratch for that many rows up front, so the
+ * two later calls never run out of arena after the step's gradients exist. */
+int nasrec_net_set_reserve(void* net, int rows);
 int nasrec_net_set_overlap(void* net, int on);      /* join the side stream (nasrec_set_side_stream) after backward */
 /* Data-parallel overlap: during nasrec_net_forward_backward, cb(offset_bytes, nbytes) is called on the host each
  * time a block's parameter gradients are final -- the byte range of the gradient bucket sealed since the last call,

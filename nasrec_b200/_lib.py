@@ -27,6 +27,7 @@ _fl = C.c_float
 _SIGS = {
     "nasrec_emb_gather_fwd": ([_f, _f, _f, _f, _i, _i, _f, _f], 1),
     "nasrec_emb_grad_sort_reduce": ([_f, _f, _i, _i, _f, _f, _f, _f, _f, _f], 1),
+    "nasrec_emb_grad_sort_reduce_checked": ([_f, _f, _f, _f, _i, _i, _f, _f, _f, _f, _f, _f], 1),
     "nasrec_emb_grad_to_dense": ([_f, _f, _f, _f, _i, _i, _f], 1),
     "nasrec_emb_rowwise_adagrad": ([_f, _f, _f, _f, _f, _i, _i, _fl, _fl, _f, _f], 1),
     "nasrec_seg_linear_fwd": ([_f, _i, _f, _l, _i, _i, _f, _f, _l, _i, _f], 1),

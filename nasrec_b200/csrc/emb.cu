@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(256) emb_gather_kernel(const float* const* __r
 // head flags + block scan -> unique rows, then 16 lanes per unique row sum the
 // duplicates in ascending sample order.
 __global__ void __launch_bounds__(1024) emb_sort_reduce_kernel(const int64_t* __restrict__ idx,
-                                                               const float* __restrict__ gout, int B, int Bpad,
+                                                               const int64_t* __restrict__ num_rows, int* err_flag,
+                                                               const float* __restrict__ gout, int Bin, int Bpad,
                                                                int F, int64_t* __restrict__ uniq,
                                                                int* __restrict__ nuniq,
                                                                float* __restrict__ row_grad,
@@ -45,12 +46,27 @@ __global__ void __launch_bounds__(1024) emb_sort_reduce_kernel(const int64_t* __
     extern __shared__ unsigned long long keys[];
     __shared__ int wsum[32];
     __shared__ float red[34];
-    __shared__ int s_total;
+    __shared__ int s_total, s_valid;
     const int f = blockIdx.x;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < Bpad; i += nt)
-        keys[i] = i < B ? (((unsigned long long)idx[(long long)i * F + f] << 32) | (unsigned)i) : ~0ull;
+    if (tid == 0) s_valid = 0;
     __syncthreads();
+    // ids outside [0, num_rows[f]) would address rows that do not exist (the reference's nn.Embedding asserts): they are
+    // dropped here -- their key sorts behind every valid one -- and reported through err_flag, as the forward gather does
+    const unsigned long long nrows = num_rows ? (unsigned long long)num_rows[f] : (1ull << 31);
+    int nvalid = 0;
+    for (int i = tid; i < Bpad; i += nt) {
+        unsigned long long key = ~0ull;
+        if (i < Bin) {
+            const unsigned long long row = (unsigned long long)idx[(long long)i * F + f];
+            if (row < nrows) { key = (row << 32) | (unsigned)i; ++nvalid; }
+        }
+        keys[i] = key;
+    }
+    if (nvalid) atomicAdd(&s_valid, nvalid);
+    __syncthreads();
+    const int B = s_valid;                    // valid keys; the scratch / output strides stay Bin
+    if (tid == 0 && B != Bin && err_flag) atomicOr(err_flag, 1);
     for (int k = 2; k <= Bpad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < Bpad; i += nt) {
@@ -96,7 +112,7 @@ __global__ void __launch_bounds__(1024) emb_sort_reduce_kernel(const int64_t* __
     }
     __syncthreads();
     int pos = wsum[wid] + inc - cnt;
-    int* seg = seg_scratch + (long long)f * (B + 1);
+    int* seg = seg_scratch + (long long)f * (Bin + 1);
     for (int i = beg; i < end; ++i)
         if (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) seg[pos++] = i;
     const int U = s_total;
@@ -128,8 +144,8 @@ __global__ void __launch_bounds__(1024) emb_sort_reduce_kernel(const int64_t* __
             const unsigned b = (unsigned)(keys[i] & 0xffffffffu);
             acc += __ldg(gout + ((long long)b * F + f) * NASREC_EMB_DIM + e);
         }
-        row_grad[((long long)f * B + u) * NASREC_EMB_DIM + e] = acc;
-        if (e == 0) uniq[(long long)f * B + u] = (int64_t)(keys[s0] >> 32);
+        row_grad[((long long)f * Bin + u) * NASREC_EMB_DIM + e] = acc;
+        if (e == 0) uniq[(long long)f * Bin + u] = (int64_t)(keys[s0] >> 32);
         sq += acc * acc;
     }
     const float tot = block_sum(sq, red);
@@ -190,6 +206,12 @@ int nasrec_emb_gather_fwd(const float* const* tables, const int64_t* num_rows, c
 
 int nasrec_emb_grad_sort_reduce(const int64_t* idx, const float* gout, int B, int F, int64_t* uniq, int* nuniq,
                                 float* row_grad, float* sumsq, int* seg_scratch, void* stream) {
+    return nasrec_emb_grad_sort_reduce_checked(idx, nullptr, nullptr, gout, B, F, uniq, nuniq, row_grad, sumsq, seg_scratch, stream);
+}
+
+int nasrec_emb_grad_sort_reduce_checked(const int64_t* idx, const int64_t* num_rows, int* err_flag, const float* gout, int B,
+                                        int F, int64_t* uniq, int* nuniq, float* row_grad, float* sumsq, int* seg_scratch,
+                                        void* stream) {
     CHECK_ARG(idx && gout && uniq && nuniq && row_grad && sumsq && seg_scratch && B > 0 && F > 0);
     if (B > 16384) return NASREC_ETOOBIG;
     int Bpad = 32;
@@ -203,8 +225,8 @@ int nasrec_emb_grad_sort_reduce(const int64_t* idx, const float* gout, int B, in
         attr_set = true;
     }
     const int threads = Bpad >= 1024 ? 1024 : (Bpad < 64 ? 64 : Bpad);
-    nasrec_launch(emb_sort_reduce_kernel, F, threads, smem, as_stream(stream), idx, gout, B, Bpad, F, uniq, nuniq, row_grad,
-                                                                    sumsq, seg_scratch);
+    nasrec_launch(emb_sort_reduce_kernel, F, threads, smem, as_stream(stream), idx, num_rows, err_flag, gout, B, Bpad, F, uniq,
+                  nuniq, row_grad, sumsq, seg_scratch);
     return nasrec_launch_status();
 }
 

@@ -83,6 +83,38 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// Warp-uniform issue: the WHOLE warp executes these on warp-uniform operands and one lane is elected inside the asm block.
+// Measured (tools/mma_bench.cu): a tcgen05.mma issued from an `if (lane == 0)` branch costs ~130 clk whatever its size --
+// the compiler cannot prove the operands uniform and wraps every instruction of the uniform datapath in a
+// lane-uniformisation loop -- against 26 clk (N = 32) / 65 clk (N = 128) when issued this way.
+__device__ __forceinline__ void mbar_expect_tx_w(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_w(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, pe;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ uint64_t tm_desc(const OpLayout& L, uint32_t saddr) {
     return (uint64_t)(((saddr >> 4) & 0x3FFFu) | (L.desc_lbo << 16)) | ((uint64_t)L.desc_hi32 << 32);
 }
@@ -197,20 +229,19 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     pdl_wait();
 
     if (warp == 9) {
-        // ------------------------------------------------------------ TMA producers: lane 0 A (raw), lane 1 B (hi / raw),
-        // lane 2 B lo -- one lane per stream so that the issue sequences run side by side
-        if (lane < 3 && ntiles > 0) {
-            const bool is_b = lane >= 1, is_lo = lane == 2;
-            const OpLayout& L = is_b ? tb.lb : tb.la;
-            const int rank = L.rank, nbox = L.nbox, box_bytes = L.box_bytes, box_dim = L.box_dim;
-            const bool b_lo = nprod > 1 && !tb.lb.convert;                     // the weight's lo plane is fetched, not derived
-            const bool active = !is_lo || b_lo;
-            const int row0 = is_b ? n0 : m0;
-            const int rp0 = row0 >> L.rsh[0], rp1 = row0 >> L.rsh[1], rp2 = row0 >> L.rsh[2];
-            const int ks0 = L.ksh[0], ks1 = L.ksh[1], ks2 = L.ksh[2];
-            const int bd0 = box_dim == 0 ? 32 : 0, bd1 = box_dim == 1 ? 32 : 0, bd2 = box_dim == 2 ? 32 : 0;
-            const uint32_t soff = is_b ? (uint32_t)(Cfg::A_BYTES + (is_lo ? Cfg::B_BYTES : 0)) : 0u;
-            const uint32_t tx = (uint32_t)(tb.la.nbox * tb.la.box_bytes + tb.lb.nbox * tb.lb.box_bytes * (b_lo ? 2 : 1));
+        // ------------------------------------------------------------ TMA producer: the whole warp runs warp-uniform code,
+        // one elected lane issues; per k-tile: A (raw), B (hi / raw) and, for weights, B lo
+        if (ntiles > 0) {
+            const OpLayout& LA = tb.la;
+            const OpLayout& LB = tb.lb;
+            const bool b_lo = nprod > 1 && !LB.convert;                        // the weight's lo plane is fetched, not derived
+            const uint32_t tx = (uint32_t)(LA.nbox * LA.box_bytes + LB.nbox * LB.box_bytes * (b_lo ? 2 : 1));
+            const int a_rank = LA.rank, a_nbox = LA.nbox, a_bb = LA.box_bytes, b_rank = LB.rank, b_nbox = LB.nbox, b_bb = LB.box_bytes;
+            const int ar0 = m0 >> LA.rsh[0], ar1 = m0 >> LA.rsh[1], ar2 = m0 >> LA.rsh[2];
+            const int br0 = n0 >> LB.rsh[0], br1 = n0 >> LB.rsh[1], br2 = n0 >> LB.rsh[2];
+            const int ak0 = LA.ksh[0], ak1 = LA.ksh[1], ak2 = LA.ksh[2], bk0 = LB.ksh[0], bk1 = LB.ksh[1], bk2 = LB.ksh[2];
+            const int ad0 = LA.box_dim == 0 ? 32 : 0, ad1 = LA.box_dim == 1 ? 32 : 0;
+            const int bd0 = LB.box_dim == 0 ? 32 : 0, bd1 = LB.box_dim == 1 ? 32 : 0;
             int t_cur = 0, kk = 0;
             {
                 int kt = 0;
@@ -223,21 +254,23 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     kt += nk;
                 }
             }
-            int K = 0, b0 = 0, b1 = 0, b2 = 0;
-            const CUtensorMap* map = nullptr;
+            int K = 0, a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+            const CUtensorMap *map_a = nullptr, *map_bh = nullptr, *map_bl = nullptr;
             auto load_term = [&](int t) {
                 const TTerm& tm = tb.term[pr.term0 + t];
                 K = tm.K;
-                const int mi = is_b ? (is_lo ? tm.b_lo : tm.b_hi) : tm.a_hi;
-                map = &tb.maps[mi];
-                const int* base = is_b ? tm.b_base : tm.a_base;
-                b0 = base[0] + rp0; b1 = base[1] + rp1; b2 = base[2] + rp2;
+                map_a = &tb.maps[tm.a_hi]; map_bh = &tb.maps[tm.b_hi]; map_bl = &tb.maps[tm.b_lo];
+                a0 = tm.a_base[0] + ar0; a1 = tm.a_base[1] + ar1; a2 = tm.a_base[2] + ar2;
+                b0 = tm.b_base[0] + br0; b1 = tm.b_base[1] + br1; b2 = tm.b_base[2] + br2;
             };
-            for (int t = 0; t < pr.nterm; ++t) {       // warm the descriptor cache for every map this lane will name
-                const TTerm& tm = tb.term[pr.term0 + t];
-                const int mi = is_b ? (is_lo ? tm.b_lo : tm.b_hi) : tm.a_hi;
-                asm volatile("prefetch.tensormap [%0];" ::"l"(&tb.maps[mi]) : "memory");
-            }
+            if (lane == 0)
+                for (int t = 0; t < pr.nterm; ++t) {       // warm the descriptor cache
+                    const TTerm& tm = tb.term[pr.term0 + t];
+                    asm volatile("prefetch.tensormap [%0];" ::"l"(&tb.maps[tm.a_hi]) : "memory");
+                    asm volatile("prefetch.tensormap [%0];" ::"l"(&tb.maps[tm.b_hi]) : "memory");
+                    if (b_lo) asm volatile("prefetch.tensormap [%0];" ::"l"(&tb.maps[tm.b_lo]) : "memory");
+                }
+            __syncwarp();
             load_term(t_cur);
             const uint32_t tiles_u32 = smem_u32(tiles);
 #pragma unroll 1
@@ -247,53 +280,74 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
                 const uint32_t full = bar_full + 8 * s;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                if (lane == 0) mbar_expect_tx(full, tx);
-                __syncwarp(0x7u);
-                if (active) {
-                    const int k0 = kk * TC_BK;
-                    int c0 = b0 + (k0 >> ks0), c1 = b1 + (k0 >> ks1), c2 = b2 + (k0 >> ks2);
-                    uint32_t dst = tiles_u32 + (uint32_t)(s * Cfg::STAGE_BYTES) + soff;
-                    for (int i = 0; i < nbox; ++i) {
-                        if (rank == 2) tma_load_2d(dst, map, full, c0, c1);
-                        else tma_load_3d(dst, map, full, c0, c1, c2);
-                        dst += box_bytes;
-                        c0 += bd0; c1 += bd1; c2 += bd2;
+                mbar_expect_tx_w(full, tx);
+                const int k0 = kk * TC_BK;
+                uint32_t dst = tiles_u32 + (uint32_t)(s * Cfg::STAGE_BYTES);
+                {
+                    int c0 = a0 + (k0 >> ak0), c1 = a1 + (k0 >> ak1);
+                    const int c2 = a2 + (k0 >> ak2);
+                    uint32_t d = dst;
+                    for (int i = 0; i < a_nbox; ++i) {
+                        if (a_rank == 2) tma_load_2d_w(d, map_a, full, c0, c1);
+                        else tma_load_3d_w(d, map_a, full, c0, c1, c2);
+                        d += a_bb; c0 += ad0; c1 += ad1;
+                    }
+                }
+                {
+                    int c0 = b0 + (k0 >> bk0), c1 = b1 + (k0 >> bk1);
+                    const int c2 = b2 + (k0 >> bk2);
+                    uint32_t d = dst + Cfg::A_BYTES;
+                    for (int i = 0; i < b_nbox; ++i) {
+                        if (b_rank == 2) tma_load_2d_w(d, map_bh, full, c0, c1);
+                        else tma_load_3d_w(d, map_bh, full, c0, c1, c2);
+                        if (b_lo) {
+                            if (b_rank == 2) tma_load_2d_w(d + Cfg::B_BYTES, map_bl, full, c0, c1);
+                            else tma_load_3d_w(d + Cfg::B_BYTES, map_bl, full, c0, c1, c2);
+                        }
+                        d += b_bb; c0 += bd0; c1 += bd1;
                     }
                 }
                 ++kk;
             }
         }
     } else if (warp == 8) {
-        // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0 && ntiles > 0) {
+        // ------------------------------------------------------------ MMA issuer: whole warp, warp-uniform operands, elected lane
+        if (ntiles > 0) {
+            const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem, 0);
             const uint32_t idesc = umma_idesc_tf32(BN) | ((uint32_t)tb.lb.mn_major << 16);       // A from TMEM is K-major
+            const uint32_t dlo = tb.lb.desc_lbo << 16;
+            const uint64_t dhi = (uint64_t)tb.lb.desc_hi32 << 32;
+            const int ko0 = tb.lb.koff[0], ko1 = tb.lb.koff[1], ko2 = tb.lb.koff[2], ko3 = tb.lb.koff[3];
+            const uint32_t tiles_u32 = smem_u32(tiles);
+#pragma unroll 1
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % Cfg::STAGES;
                 const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
                 mbar_wait(bar_full + 8 * s, ph);
                 mbar_wait(bar_conv + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t sb = smem_u32(tiles + s * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
-                const uint32_t ta = tmem + (uint32_t)(TM_ACC_COLS + (it % TM_SLOTS) * 64);
-                const uint32_t tacc = tmem + (uint32_t)((it % nacc) * Cfg::ACC_STRIDE);
+                const uint32_t sb = tiles_u32 + (uint32_t)(s * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
+                const uint32_t ta = tm_u + (uint32_t)(TM_ACC_COLS + (it % TM_SLOTS) * 64);
+                const uint32_t tacc = tm_u + (uint32_t)((it % nacc) * Cfg::ACC_STRIDE);
 #pragma unroll
                 for (int k = 0; k < TC_BK / TC_UK; ++k) {
+                    const int ko = k == 0 ? ko0 : (k == 1 ? ko1 : (k == 2 ? ko2 : ko3));
                     const uint32_t a_hi = ta + (uint32_t)(k * TC_UK), a_lo = a_hi + 32u;
-                    const uint64_t b_hi = tm_desc(tb.lb, sb + tb.lb.koff[k]);
-                    const uint64_t b_lo = tm_desc(tb.lb, sb + Cfg::B_BYTES + tb.lb.koff[k]);
+                    const uint64_t b_hi = (uint64_t)((((sb + ko) >> 4) & 0x3FFFu) | dlo) | dhi;
+                    const uint64_t b_lo = (uint64_t)((((sb + Cfg::B_BYTES + ko) >> 4) & 0x3FFFu) | dlo) | dhi;
                     const uint32_t first = (it >= nacc || k > 0) ? 1u : 0u;
                     if (nprod > 1) {
-                        umma_tf32_ts(tacc, a_lo, b_hi, idesc, first);
-                        umma_tf32_ts(tacc, a_hi, b_lo, idesc, 1u);
-                        if (nprod > 3) umma_tf32_ts(tacc, a_lo, b_lo, idesc, 1u);
-                        umma_tf32_ts(tacc, a_hi, b_hi, idesc, 1u);
+                        umma_tf32_ts_w(tacc, a_lo, b_hi, idesc, first);
+                        umma_tf32_ts_w(tacc, a_hi, b_lo, idesc, 1u);
+                        if (nprod > 3) umma_tf32_ts_w(tacc, a_lo, b_lo, idesc, 1u);
+                        umma_tf32_ts_w(tacc, a_hi, b_hi, idesc, 1u);
                     } else {
-                        umma_tf32_ts(tacc, a_hi, b_hi, idesc, first);
+                        umma_tf32_ts_w(tacc, a_hi, b_hi, idesc, first);
                     }
                 }
-                umma_commit(bar_empty + 8 * s);
+                umma_commit_w(bar_empty + 8 * s);
             }
-            umma_commit(bar_done);
+            umma_commit_w(bar_done);
         }
         __syncwarp();
         tc_fence_before();

@@ -92,6 +92,13 @@ struct Net {
     int64_t* uniq = nullptr; int* nuniq = nullptr; float* row_grad = nullptr; float* sumsq = nullptr; int sB = 0;
     bool have_sparse = false;
     bool overlap = false;
+    // scratch of nasrec_net_sparse_reduce / nasrec_net_apply, reserved by forward_backward so that those two calls cannot
+    // overflow an arena after the step's gradients exist (growing the arenas then would leave them pointing at freed memory)
+    int reserve_rows = 0;                     // rows of the (all-gathered) batch the sparse reduction will see
+    int res_rows = 0;
+    int64_t* res_uniq = nullptr; int* res_nuniq = nullptr; float* res_row_grad = nullptr; float* res_sumsq = nullptr; int* res_scratch = nullptr;
+    float* res_partial = nullptr; int64_t res_partial_n = 0;
+    bool step_valid = false;                  // false after nasrec_net_set_arenas: gradients of an earlier step are gone
     // data-parallel overlap: called during backward whenever a block's parameter gradients are final, with the
     // byte range of the gradient bucket that was sealed (the caller all-reduces it while backward continues)
     void (*seal_cb)(int64_t offset_bytes, int64_t nbytes) = nullptr;
@@ -892,6 +899,14 @@ int nasrec_net_set_arenas(void* net, void* act, int64_t act_bytes, void* pgrad, 
     n->act = Arena{(char*)act, (size_t)act_bytes, 0, 0};
     n->pg = Arena{(char*)pgrad, (size_t)pgrad_bytes, 0, 0};
     n->pg_dirty = (size_t)pgrad_bytes;       // unknown contents: clear everything once
+    // whatever an earlier step left in the old arenas is gone: make reduce / apply refuse instead of reading freed memory
+    for (int pi : n->touched) n->par[pi].g = nullptr;
+    n->touched.clear();
+    n->emb_gout = nullptr;
+    n->have_sparse = false;
+    n->step_valid = false;
+    n->res_rows = 0;
+    n->res_partial = nullptr;
     return 0;
 }
 
@@ -918,6 +933,12 @@ int nasrec_net_set_planes(void* net, float* const* hi, float* const* lo, const i
 }
 
 int nasrec_net_set_overlap(void* net, int on) { ((Net*)net)->overlap = on != 0; return 0; }
+
+int nasrec_net_set_reserve(void* net, int rows) {
+    CHECK_ARG(net && rows >= 0);
+    ((Net*)net)->reserve_rows = rows;
+    return 0;
+}
 
 int nasrec_net_set_seal_callback(void* net, nasrec_seal_cb_t cb) {
     CHECK_ARG(net);
@@ -946,6 +967,21 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
     const int rc = guarded([&] {
         cudaStream_t st = as_stream(stream);
         reset_step(*n, st);
+        n->step_valid = false;
+        {   // reserve what sparse_reduce / apply will need, before any work is queued
+            const int rows = n->reserve_rows > B ? n->reserve_rows : B;
+            const int F = n->F;
+            n->res_uniq = (int64_t*)n->act.alloc_bytes((size_t)F * rows * 8);
+            n->res_nuniq = (int*)n->act.alloc_bytes((size_t)F * 4);
+            n->res_row_grad = n->act.alloc((int64_t)F * rows * E);
+            n->res_sumsq = n->act.alloc(F);
+            n->res_scratch = (int*)n->act.alloc_bytes((size_t)F * (rows + 1) * 4);
+            n->res_rows = rows;
+            int64_t chunks = 0;
+            for (const Par& p : n->par) chunks += (p.n + 16383) / 16384;      // >= nasrec_sumsq_ws_floats of any subset
+            n->res_partial = n->act.alloc(chunks);
+            n->res_partial_n = chunks;
+        }
         if (n->pg_dirty) ck((int)cudaMemsetAsync(n->pg.base, 0, n->pg_dirty, st));
         Var* out = forward(*n, choice, int_x, cat_x, nullptr, B, true);
         out->g = n->act.alloc(B);
@@ -970,6 +1006,7 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
         if (n->overlap) ck(nasrec_side_join(st), 0);
         if (n->seal_cb && n->pg.off > sealed) n->seal_cb((int64_t)sealed, (int64_t)(n->pg.off - sealed));
         n->pg_dirty = n->pg.off;
+        n->step_valid = true;
     });
     if (rc) n->pg_dirty = n->pg.cap;       // a failed step may have scribbled anywhere in the bucket: clear all of it next time
     return rc;
@@ -1000,14 +1037,22 @@ int nasrec_net_sparse_reduce(void* net, const int64_t* cat_all, const float* gou
         const int64_t* cat = cat_all ? cat_all : n->cat_x;
         const float* go = gout_all ? gout_all : n->emb_gout;
         const int Bs = cat_all ? B_all : n->B;
+        if (!n->step_valid) throw CallFailed(NASREC_EINVAL);      // no step, or its arenas were replaced
         if (!go) { n->have_sparse = false; return; }
         const int F = n->F;
-        n->uniq = (int64_t*)n->act.alloc_bytes((size_t)F * Bs * 8);
-        n->nuniq = (int*)n->act.alloc_bytes((size_t)F * 4);
-        n->row_grad = n->act.alloc((int64_t)F * Bs * E);
-        n->sumsq = n->act.alloc(F);
-        int* scratch = (int*)n->act.alloc_bytes((size_t)F * (Bs + 1) * 4);
-        ck(nasrec_emb_grad_sort_reduce(cat, go, Bs, F, n->uniq, n->nuniq, n->row_grad, n->sumsq, scratch, as_stream(stream)));
+        int* scratch;
+        if (Bs <= n->res_rows) {
+            n->uniq = n->res_uniq; n->nuniq = n->res_nuniq; n->row_grad = n->res_row_grad; n->sumsq = n->res_sumsq;
+            scratch = n->res_scratch;
+        } else {                                                  // the caller did not announce this many rows (nasrec_net_set_reserve)
+            n->uniq = (int64_t*)n->act.alloc_bytes((size_t)F * Bs * 8);
+            n->nuniq = (int*)n->act.alloc_bytes((size_t)F * 4);
+            n->row_grad = n->act.alloc((int64_t)F * Bs * E);
+            n->sumsq = n->act.alloc(F);
+            scratch = (int*)n->act.alloc_bytes((size_t)F * (Bs + 1) * 4);
+        }
+        ck(nasrec_emb_grad_sort_reduce_checked(cat, n->d_rows, n->d_err, go, Bs, F, n->uniq, n->nuniq, n->row_grad, n->sumsq, scratch,
+                                               as_stream(stream)));
         n->sB = Bs;
         n->have_sparse = true;
     });
@@ -1020,6 +1065,7 @@ int nasrec_net_apply(void* net, float lr, float eps, float max_norm, float* norm
     CHECK_ARG(n && norm_out);
     return guarded([&] {
         cudaStream_t st = as_stream(stream);
+        if (!n->step_valid) throw CallFailed(NASREC_EINVAL);
         std::vector<int> dense;
         for (int pi : n->ref_order) {
             bool is_emb = false;
@@ -1038,7 +1084,8 @@ int nasrec_net_apply(void* net, float lr, float eps, float max_norm, float* norm
         }
         const float* coef = nullptr;
         if (max_norm > 0.f) {
-            float* partial = n->act.alloc(nasrec_sumsq_ws_floats(sz.data(), (int)sz.size()));
+            const int64_t need = nasrec_sumsq_ws_floats(sz.data(), (int)sz.size());
+            float* partial = (n->res_partial && need <= n->res_partial_n) ? n->res_partial : n->act.alloc(need);
             ck(nasrec_grad_norm_clip(g.data(), sz.data(), (int)sz.size(), n->have_sparse ? n->sumsq : nullptr,
                                      n->have_sparse ? n->F : 0, max_norm, partial, norm_out, st), 2);
             coef = norm_out + 1;

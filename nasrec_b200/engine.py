@@ -614,6 +614,13 @@ class EmbeddingTables:
             self.key = key
         return self
 
+    def check(self):
+        """Raise IndexError if any embedding id seen so far was outside its table (synchronises; call it where the
+        caller synchronises anyway).  The reference fails through nn.Embedding's index assert (supernet.py:407)."""
+        if self.err is not None and int(self.err.item()) != 0:
+            self.err.zero_()
+            raise IndexError("embedding index out of range (cat_feats must lie in [0, num_embeddings[f]))")
+
 
 class SparseEmbGrad:
     """Result of the deterministic sorted-row reduction for one step."""
@@ -627,8 +634,9 @@ class SparseSink(list):
     defer = False
 
 
-def reduce_sparse(cat_x: torch.Tensor, gout: torch.Tensor) -> SparseEmbGrad:
-    """Deterministic sorted-row reduction of d(sparse)[B,F,16] (nasrec_emb_grad_sort_reduce)."""
+def reduce_sparse(cat_x: torch.Tensor, gout: torch.Tensor, tables: Optional["EmbeddingTables"] = None) -> SparseEmbGrad:
+    """Deterministic sorted-row reduction of d(sparse)[B,F,16] (nasrec_emb_grad_sort_reduce).  With ``tables`` the ids are
+    bounds-checked as in the forward gather: out-of-range ids are dropped and ``tables.err`` is raised."""
     B, F = cat_x.shape
     dev = cat_x.device
     sg = SparseEmbGrad()
@@ -638,8 +646,12 @@ def reduce_sparse(cat_x: torch.Tensor, gout: torch.Tensor) -> SparseEmbGrad:
     sg.row_grad = torch.empty(F, B, E, dtype=torch.float32, device=dev)
     sg.sumsq = torch.empty(F, dtype=torch.float32, device=dev)
     scratch = torch.empty(F, B + 1, dtype=torch.int32, device=dev)
-    call("nasrec_emb_grad_sort_reduce", cat_x.data_ptr(), _p(gout), B, F, sg.uniq.data_ptr(), sg.nuniq.data_ptr(),
-         _p(sg.row_grad), _p(sg.sumsq), scratch.data_ptr())
+    if tables is not None and tables.rows is not None:
+        call("nasrec_emb_grad_sort_reduce_checked", cat_x.data_ptr(), _p_i(tables.rows), _p_i(tables.err), _p(gout), B, F,
+             sg.uniq.data_ptr(), sg.nuniq.data_ptr(), _p(sg.row_grad), _p(sg.sumsq), scratch.data_ptr())
+    else:
+        call("nasrec_emb_grad_sort_reduce", cat_x.data_ptr(), _p(gout), B, F, sg.uniq.data_ptr(), sg.nuniq.data_ptr(),
+             _p(sg.row_grad), _p(sg.sumsq), scratch.data_ptr())
     return sg
 
 
@@ -672,7 +684,7 @@ def embedding(tape: Tape, tables: EmbeddingTables, weights: Sequence[PVar], cat_
         if sparse_sink is not None and getattr(sparse_sink, "defer", False):
             sparse_sink.append((cat_x, out.g))
             return
-        sg = reduce_sparse(cat_x, out.g)
+        sg = reduce_sparse(cat_x, out.g, tables)
         if sparse_sink is not None:
             sparse_sink.append(sg)
             return

@@ -34,6 +34,7 @@ _PROTOS = {
     "nasrec_net_set_requires_grad": ([_vp, _vp, _i], _i),
     "nasrec_net_set_planes": ([_vp, _vp, _vp, _vp, _vp, _i], _i),
     "nasrec_net_set_overlap": ([_vp, _i], _i),
+    "nasrec_net_set_reserve": ([_vp, _i], _i),
     "nasrec_net_set_seal_callback": ([_vp, _vp], _i),
     "nasrec_net_forward": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp], _i),
     "nasrec_net_forward_backward": ([_vp, _vp, _vp, _vp, _vp, _i, _fl, _vp, _vp, _vp], _i),
@@ -352,15 +353,31 @@ class NativeNet:
         off = gp.value - self.act.data_ptr()
         return self.act[off: off + B * F * EMB * 4].view(torch.float32).view(B, F, EMB)
 
+    def reserve(self, rows: int):
+        """Rows the sparse reduction will see (world_size x B under data parallelism): forward_backward reserves the
+        reduction's and the clip's scratch for them, so reduce / apply cannot overflow an arena afterwards."""
+        if rows != getattr(self, "_reserved", None):
+            _check(_fn("nasrec_net_set_reserve")(self.handle, int(rows)), "nasrec_net_set_reserve")
+            self._reserved = rows
+
+    def _after_step(self, what: str, rc: int):
+        # These two run on the gradients forward_backward left in the arenas: growing the arenas here would free them.
+        # forward_backward reserved their scratch, so an overflow means the caller under-announced the batch (reserve()).
+        if rc == _ENOSPACE:
+            raise MemoryError("%s ran out of arena after the step's gradients were produced; call NativeNet.reserve(rows) "
+                              "with the size of the all-gathered batch before forward_backward" % what)
+        _check(rc, what)
+        self._count()
+
     def sparse_reduce(self, cat_all: Optional[torch.Tensor] = None, gout_all: Optional[torch.Tensor] = None):
         B_all = cat_all.shape[0] if cat_all is not None else 0
-        self._retrying("nasrec_net_sparse_reduce", lambda: _fn("nasrec_net_sparse_reduce")(
+        self._after_step("nasrec_net_sparse_reduce", _fn("nasrec_net_sparse_reduce")(
             self.handle, cat_all.data_ptr() if cat_all is not None else None,
             gout_all.data_ptr() if gout_all is not None else None, B_all, _lib.stream_ptr()))
 
     def apply(self, lr: float, eps: float, clip: Optional[float]) -> torch.Tensor:
         norm = torch.empty(2, dtype=torch.float32, device=self.dev)
-        self._retrying("nasrec_net_apply", lambda: _fn("nasrec_net_apply")(
+        self._after_step("nasrec_net_apply", _fn("nasrec_net_apply")(
             self.handle, float(lr), float(eps), float(clip) if clip is not None else 0.0, norm.data_ptr(),
             _lib.stream_ptr()))
         return norm

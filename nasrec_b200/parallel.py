@@ -118,7 +118,8 @@ class DataParallelTrainer(FusedTrainer):
         sparse = None
         if raw is not None:
             cat_l, gout_l = raw
-            sparse = eng.reduce_sparse(allgather_cat(cat_l, self.group), allgather_cat(gout_l, self.group))
+            sparse = eng.reduce_sparse(allgather_cat(cat_l, self.group), allgather_cat(gout_l, self.group),
+                                       getattr(self.model, "_tables", None))
         self.apply(run, sparse, lr)
         return logits, loss
 
@@ -155,6 +156,7 @@ class NativeDataParallelTrainer(DataParallelTrainer):
         from . import _lib
         net.refresh()
         cat = (cat_x if cat_x.dtype == torch.int64 else cat_x.long()).contiguous()
+        net.reserve(self.world * cat.shape[0])       # the sparse reduction will see the all-gathered batch
         with _lib.pin_stream():
             # Sealed ranges of the gradient bucket are all-reduced while backward is still running: NCCL works on
             # its own stream, ordered after the kernels already queued here (late blocks hold the widest weights and

@@ -113,7 +113,11 @@ def test_one_epoch(model, test_loader, loss_fn=None, gpu=None, max_steps: int = 
             if max_steps != -1 and counter >= max_steps:
                 break
     model.train(was_training)
-    return binary_metrics_device(torch.cat(preds), torch.cat(labels))
+    res = binary_metrics_device(torch.cat(preds), torch.cat(labels))       # synchronises (three scalars reach the host)
+    tables = getattr(model, "_tables", None)
+    if tables is not None:
+        tables.check()             # an out-of-range id raises IndexError, as nn.Embedding does in the reference
+    return res
 
 
 def train_and_test_one_epoch(model, epoch: int, optimizer, lr_scheduler, train_loader, test_loader, loss_fn,

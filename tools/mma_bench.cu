@@ -22,6 +22,12 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint3
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void mma_ts_w(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p, pe;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void commit_w(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
 
 __global__ void __launch_bounds__(128, 1) k(int N, int ts, int rot, int group, int n, long long* out, int use_elect) {
@@ -41,9 +47,35 @@ __global__ void __launch_bounds__(128, 1) k(int N, int ts, int rot, int group, i
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
+    if (use_elect == 2 && warp == 0) {
+        // every lane of warp 0 runs the issue loop on warp-uniform operands; the election happens inside the asm block
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint32_t bs = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t db = desc128(bs + 16384);
+        const uint32_t a0 = tm + 256;
+        const uint32_t bar0 = __shfl_sync(0xffffffffu, smem_u32(&bar[0]), 0);
+        int nc = 0;
+        const long long t0 = clock64();
+        for (int i = 0; i < n; i += 12) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                mma_ts_w(tm, a0 + 32 + kk * 8, db + adv, idesc, 1u);
+                mma_ts_w(tm, a0 + kk * 8, db + 256 + adv, idesc, 1u);
+                mma_ts_w(tm, a0 + kk * 8, db + adv, idesc, 1u);
+            }
+            if (nc >= 16) mbar_wait(bar0 + 8 * (nc % 16), (uint32_t)((nc - 16) / 16) & 1u);
+            commit_w(bar0 + 8 * (nc % 16));
+            ++nc;
+        }
+        for (int c = (nc > 16 ? nc - 16 : 0); c < nc; ++c) mbar_wait(bar0 + 8 * (c % 16), (uint32_t)(c / 16) & 1u);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+    }
     uint32_t elected = 0;
     if (warp == 0) asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}\n" : "=r"(elected));
-    if (use_elect ? (warp == 0 && elected) : (threadIdx.x == 0)) {
+    if (use_elect == 2 ? false : (use_elect ? (warp == 0 && elected) : (threadIdx.x == 0))) {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t da = desc128(base), db = desc128(base + 16384);
         int nc = 0;        // commits issued so far; commit c goes to bar[c % 16], reused only after its previous phase completed
