@@ -88,6 +88,9 @@ int nasrec_set_weight_planes(const float* W, const float* hi, const float* lo, i
                              int first);
 int nasrec_planes_refresh(const float* W, int64_t ldw, int rows, int cols, int first, float* hi, float* lo,
                           int64_t ldp, void* stream);
+/* Host-side launch accounting: what = 1 starts (and clears), 0 stops, 2 returns the nanoseconds spent inside
+ * cudaLaunchKernelEx since the start, 3 the number of launches. */
+int64_t nasrec_host_prof(int what);
 /* which = 0: tensor-map cache hits, 1: tensor maps encoded, 2: GEMM launches that took the TMA path */
 int64_t nasrec_tensor_map_stats(int which);
 

@@ -74,6 +74,7 @@ _SIGS_I64 = {
     "nasrec_binary_metrics_ws_bytes": [_l],
 }
 _SIGS_I64["nasrec_tensor_map_stats"] = [_i]
+_SIGS_I64["nasrec_host_prof"] = [_i]
 EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace",
            "nasrec_set_side_stream", "nasrec_side_join", "nasrec_set_gemm_tma",
            "nasrec_set_weight_planes"] + list(_SIGS) + list(_SIGS_I64)

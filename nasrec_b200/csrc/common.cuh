@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <time.h>
 #include "../../include/nasrec_b200.h"
 
 #define NASREC_VERSION 100
@@ -83,6 +84,15 @@ __device__ __forceinline__ void pdl_enter() {
     pdl_wait();
 }
 
+// host-side launch accounting (nasrec_host_prof): nanoseconds spent inside cudaLaunchKernelEx and the number of launches
+extern long long g_nasrec_launch_ns, g_nasrec_launch_count;
+extern int g_nasrec_host_prof;
+static inline long long nasrec_now_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t nasrec_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                         Args&&... args) {
@@ -96,6 +106,13 @@ static inline cudaError_t nasrec_launch(void (*kernel)(KArgs...), dim3 grid, dim
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (g_nasrec_host_prof) {
+        const long long t0 = nasrec_now_ns();
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+        g_nasrec_launch_ns += nasrec_now_ns() - t0;
+        ++g_nasrec_launch_count;
+        return e;
+    }
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

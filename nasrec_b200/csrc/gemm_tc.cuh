@@ -495,9 +495,10 @@ inline long long tc_cta_count(const Prob* prob, int nprob, int bn) {
 }
 inline long long tc_cta_count(const Batch& bt, int bn) { return tc_cta_count(bt.prob, bt.nprob, bn); }
 
-// Tile width.  One tcgen05.mma costs ~130 clk to issue whatever its N (measured, tools/mma_bench.cu), so the wider the
-// tile the fewer issue slots an output element costs; the SMs are filled by splitting K instead (plan_split, deterministic
-// fixed-order reduction).  128-wide tiles only when the split leaves each CTA <= 16 k-tiles (two accumulators).
+// Tile width and split-K.  Measured on the B = 512 training step (profiles/r02_notes.md): narrow tiles that spread a launch
+// over the SMs (and leave room for the other stream's GEMM) beat wide tiles + split-K, whose extra reduction launches cost
+// more than the tensor-core issue slots they save; launches that still cover fewer than half the SMs split K over several
+// CTAs (plan_tiles, deterministic fixed-order reduction).  NASREC_TC_BN / NASREC_TILE_POLICY are experiment knobs.
 constexpr int TC_SM_COUNT = 148;
 inline int tc_split_for(long long ctas, int ktiles) {
     if (ctas <= 0 || ctas > TC_SM_COUNT / 2) return 1;
@@ -508,11 +509,17 @@ inline int tc_split_for(long long ctas, int ktiles) {
 }
 template <class KTiles>
 inline int tc_pick_bn(const Prob* prob, int nprob, int maxN, KTiles ktiles_of, bool can_split) {
-    static const int forced = getenv("NASREC_TC_BN") ? atoi(getenv("NASREC_TC_BN")) : 0;      // experiments only
+    static const int forced = getenv("NASREC_TC_BN") ? atoi(getenv("NASREC_TC_BN")) : 0;
     if (forced) return forced;
+    static const int policy = getenv("NASREC_TILE_POLICY") ? atoi(getenv("NASREC_TILE_POLICY")) : 1;
     if (maxN <= 16) return 16;
+    if (policy == 1) {
+        if (maxN > 32 && tc_cta_count(prob, nprob, 64) >= 120) return 64;
+        return maxN <= 32 ? 32 : (tc_cta_count(prob, nprob, 32) > 296 ? 64 : 32);
+    }
     if (maxN <= 32) return 32;
-    if (maxN <= 64) return 64;
+    if (maxN <= 64 || policy == 2) return 64;
+    // policy 0: 128-wide tiles (two accumulators) when split-K leaves each CTA <= 16 k-tiles, which bounds the MMA chain
     const long long c128 = tc_cta_count(prob, nprob, 128);
     if (!can_split || c128 > TC_SM_COUNT / 2) return 64;
     for (int p = 0; p < nprob; ++p) {

@@ -851,10 +851,15 @@ Var* forward(Net& n, const int* choice, const float* int_x, const int64_t* cat_x
 
 template <class F>
 int guarded(F&& f) {
-    try { f(); return 0; }
-    catch (const OutOfArena&) { return NASREC_ENOSPACE; }
-    catch (const CallFailed& e) { return e.rc; }
-    catch (const std::bad_alloc&) { return NASREC_ETOOBIG; }
+    int rc = 0;
+    try { f(); }
+    catch (const OutOfArena&) { rc = NASREC_ENOSPACE; }
+    catch (const CallFailed& e) { rc = e.rc; }
+    catch (const std::bad_alloc&) { rc = NASREC_ETOOBIG; }
+    // the plane announcement is a hint for the calls THIS executor makes: never leave it behind for another caller of the
+    // GEMM entry points (whose copy of the weight may have moved on without the planes)
+    nasrec_set_weight_planes(nullptr, nullptr, nullptr, 0, 0, 0, 0);
+    return rc;
 }
 
 }  // namespace

@@ -7,6 +7,9 @@
 // which in eager PyTorch are ~10 elementwise launches per parameter tensor.
 #include "common.cuh"
 
+long long g_nasrec_launch_ns = 0, g_nasrec_launch_count = 0;
+int g_nasrec_host_prof = 0;
+
 namespace {
 
 __global__ void __launch_bounds__(1024) bce_kernel(const float* __restrict__ z, const float* __restrict__ y, int B,
@@ -202,6 +205,15 @@ __global__ void __launch_bounds__(256) planes_refresh_kernel(const float* __rest
 }  // namespace
 
 extern "C" {
+
+int64_t nasrec_host_prof(int what) {
+    switch (what) {
+        case 0: g_nasrec_host_prof = 0; return 0;
+        case 1: g_nasrec_host_prof = 1; g_nasrec_launch_ns = 0; g_nasrec_launch_count = 0; return 0;
+        case 2: return g_nasrec_launch_ns;
+        default: return g_nasrec_launch_count;
+    }
+}
 
 int nasrec_bce_fwd_bwd(const float* logits, const float* y, int B, float grad_scale, float* loss, float* dlogits,
                        void* stream) {

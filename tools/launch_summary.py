@@ -18,5 +18,5 @@ print(note + "\n")
 print("| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:26]:
     print("| `%s` | %d | %.1f | %.2f | %.1f %% |" % (k[:72], n, t / 1e3, t / n / 1e3, 100 * t / tot))
-g = sum(t for k, (n, t) in agg.items() if "gemm_tc" in k)
-print("\nTotal %.1f us over %d launches; `gemm_tc_kernel<BN>` family: %.1f %% of device time." % (tot / 1e3, len(rows), 100 * g / tot))
+g = sum(t for k, (n, t) in agg.items() if "gemm_t" in k)
+print("\nTotal %.1f us over %d launches; `gemm_tma_kernel` + `gemm_tc_kernel` family: %.1f %% of device time." % (tot / 1e3, len(rows), 100 * g / tot))
