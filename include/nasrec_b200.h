@@ -88,6 +88,10 @@ int nasrec_set_weight_planes(const float* W, const float* hi, const float* lo, i
                              int first);
 int nasrec_planes_refresh(const float* W, int64_t ldw, int rows, int cols, int first, float* hi, float* lo,
                           int64_t ldp, void* stream);
+/* Live GEMM accounting for roofline reports: what = 1 starts recording a CUDA-event pair (on the launching stream) and
+ * the algorithmic flops (2 M N K over the live support) of every GEMM launch of the library; what = 0 stops; what = 2
+ * stops, synchronises on the events and writes {total ms, launches, flops} to out3 (host doubles). */
+int nasrec_gemm_prof(int what, double* out3);
 /* Host-side launch accounting: what = 1 starts (and clears), 0 stops, 2 returns the nanoseconds spent inside
  * cudaLaunchKernelEx since the start, 3 the number of launches. */
 int64_t nasrec_host_prof(int what);

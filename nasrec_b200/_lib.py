@@ -77,7 +77,7 @@ _SIGS_I64["nasrec_tensor_map_stats"] = [_i]
 _SIGS_I64["nasrec_host_prof"] = [_i]
 EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace",
            "nasrec_set_side_stream", "nasrec_side_join", "nasrec_set_gemm_tma",
-           "nasrec_set_weight_planes"] + list(_SIGS) + list(_SIGS_I64)
+           "nasrec_set_weight_planes", "nasrec_gemm_prof"] + list(_SIGS) + list(_SIGS_I64)
 
 
 class _Lib:
@@ -144,6 +144,18 @@ class _Lib:
         self.load()
         if self.cdll.nasrec_set_weight_planes(W, hi, lo, ldp, rows, cols, first) != 0:
             raise ValueError("nasrec_set_weight_planes rejected its arguments")
+
+    def gemm_prof_start(self):
+        self.load()
+        self.cdll.nasrec_gemm_prof.argtypes = [C.c_int, C.c_void_p]
+        self.cdll.nasrec_gemm_prof(1, None)
+
+    def gemm_prof_stop(self):
+        """(total ms, launches, algorithmic flops) of the GEMM launches since gemm_prof_start; synchronises."""
+        out = (C.c_double * 3)()
+        self.cdll.nasrec_gemm_prof.argtypes = [C.c_int, C.c_void_p]
+        self.cdll.nasrec_gemm_prof(2, C.cast(out, C.c_void_p))
+        return float(out[0]), int(out[1]), float(out[2])
 
     def ensure_workspace(self, nfloats: int = 16 * 1024 * 1024):
         """Attach a split-K scratch buffer on the current CUDA device (kept alive here)."""

@@ -15,6 +15,7 @@
 #include "gemm_tma.cuh"
 #include <cstring>
 #include <cstddef>
+#include <vector>
 
 namespace {
 using namespace nasrec_gemm;
@@ -180,6 +181,44 @@ void ws_region(cudaStream_t st, float** base, long long* n) {
     *n = half;
 }
 
+// ---- live GEMM accounting (nasrec_gemm_prof): CUDA events around every GEMM launch of the library on the launching
+// stream, with the ALGORITHMIC flops of the launch (2 M N K over the live support) -- what bench.py's roofline reads.
+struct GemmProf {
+    bool on = false;
+    std::vector<cudaEvent_t> e0, e1;
+    std::vector<double> flops;
+    size_t used = 0;
+} g_prof;
+
+template <class ProbT, class KOf>
+double launch_flops(const ProbT* prob, int nprob, KOf k_of) {
+    double f = 0;
+    for (int p = 0; p < nprob; ++p) f += 2.0 * prob[p].M * prob[p].N * (double)k_of(p);
+    return f;
+}
+struct ProfScope {
+    bool active;
+    cudaStream_t st;
+    size_t slot = 0;
+    ProfScope(cudaStream_t s, double fl) : active(g_prof.on), st(s) {
+        if (!active) return;
+        if (g_prof.used == g_prof.e0.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            g_prof.e0.push_back(a);
+            g_prof.e1.push_back(b);
+            g_prof.flops.push_back(0);
+        }
+        slot = g_prof.used++;
+        g_prof.flops[slot] = fl;
+        cudaEventRecord(g_prof.e0[slot], st);
+    }
+    ~ProfScope() {
+        if (active) cudaEventRecord(g_prof.e1[slot], st);
+    }
+};
+
 int g_gemm_mode = 3;   // 0: fp32 FFMA; 1/3/4: tcgen05 kind::tf32 with 1/3/4 split products (default 3xTF32)
 
 View plain_view(const float* p, long long si, long long sj, int contig_j) {
@@ -250,6 +289,11 @@ int launch(Batch& bt, cudaStream_t st) {
         totz += bt.prob[i].nsplit;
     }
     if (maxM <= 0 || maxN <= 0 || totz <= 0) return 0;
+    ProfScope prof(st, launch_flops(bt.prob, bt.nprob, [&](int p) {
+        long long k = 0;
+        for (int t = 0; t < bt.prob[p].nterm; ++t) k += bt.term[bt.prob[p].term0 + t].K;
+        return k;
+    }));
     if (g_gemm_mode != 0) {
         RedBatch rb{};
         const int bn = plan_tiles(bt.prob, bt.nprob, [&](int p) {
@@ -468,6 +512,11 @@ int run_tma(TmaJob& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
         totz += tb.prob[i].nsplit;
     }
     if (maxM <= 0 || maxN <= 0 || totz <= 0) return 0;
+    ProfScope prof(st, launch_flops(tb.prob, tb.nprob, [&](int p) {
+        long long k = 0;
+        for (int t = 0; t < tb.prob[p].nterm; ++t) k += tb.term[tb.prob[p].term0 + t].K;
+        return k;
+    }));
     RedBatch rb{};
     const int bn = plan_tiles(tb.prob, tb.nprob, [&](int p) {
         int kt = 0;
@@ -955,6 +1004,22 @@ int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_
     int rc = launch(bt, as_stream(stream));
     if (rc) return rc;
     return launch_reduce(rb, as_stream(stream));
+}
+
+int nasrec_gemm_prof(int what, double* out3) {
+    if (what == 1) { g_prof.on = true; g_prof.used = 0; return 0; }
+    g_prof.on = false;
+    if (what == 2 && out3) {            // synchronises: total ms, launches, algorithmic flops since the start
+        double ms = 0, fl = 0;
+        for (size_t i = 0; i < g_prof.used; ++i) {
+            cudaEventSynchronize(g_prof.e1[i]);
+            float t = 0;
+            if (cudaEventElapsedTime(&t, g_prof.e0[i], g_prof.e1[i]) == cudaSuccess) ms += t;
+            fl += g_prof.flops[i];
+        }
+        out3[0] = ms; out3[1] = (double)g_prof.used; out3[2] = fl;
+    }
+    return 0;
 }
 
 int nasrec_set_gemm_tma(int on) {

@@ -25,6 +25,7 @@ class GraphedFusedTrainer:
         self._static = None
         self._out = None
         self._lr = None
+        self.kernels_per_replay = 0             # kernels of the library captured in the graph (each replay launches them)
 
     def _strategy_is_static(self) -> bool:
         m = self.trainer.model
@@ -41,6 +42,8 @@ class GraphedFusedTrainer:
             self._static[1].copy_(cat_x, non_blocking=True)
             self._static[2].copy_(y, non_blocking=True)
         self.graph.replay()
+        from .. import _lib
+        _lib.LIB.launches += self.kernels_per_replay
         return self._out
 
     def _capture(self, int_x, cat_x, y, lr):
@@ -57,8 +60,11 @@ class GraphedFusedTrainer:
         self.graph = torch.cuda.CUDAGraph()
         if self.overlap_wgrad:
             self.trainer.side_stream = torch.cuda.Stream()
+        from .. import _lib
+        before = _lib.LIB.launches
         try:
             with torch.cuda.graph(self.graph):
                 self._out = self.trainer.step(*self._static, lr=lr)
         finally:
             self.trainer.side_stream = None
+        self.kernels_per_replay = _lib.LIB.launches - before

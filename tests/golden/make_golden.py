@@ -394,7 +394,8 @@ def sampler_fixture():
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps", "lr", "finetune", "tokenizer", "transform", "avazu"]
+    which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps", "lr", "finetune", "tokenizer", "transform", "avazu",
+                             "zeros"]
     if "samplers" in which:
         sampler_fixture()
     if "fixed" in which:
@@ -407,6 +408,8 @@ if __name__ == "__main__":
         supernet_fixture("supernet_xlarge_kdd", "kdd", "xlarge", nchoices=2)
     if "avazu" in which:
         supernet_fixture("supernet_xlarge_avazu", "avazu", "xlarge", nchoices=1)
+    if "zeros" in which:        # the xlarge-zeros search space (supernet.py:151-168): Zeros2D / Zeros3D nodes
+        supernet_fixture("supernet_zeros_criteo", "criteo", "xlarge-zeros", nchoices=4)
     if "steps" in which:
         step_fixture()
     if "lr" in which:

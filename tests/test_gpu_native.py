@@ -29,7 +29,7 @@ def _pin(m, choice):
 
 
 @pytest.mark.parametrize("name", ["supernet_autoctr_criteo", "supernet_xlarge_criteo", "supernet_xlarge_kdd",
-                                  "supernet_xlarge_avazu"])
+                                  "supernet_xlarge_avazu", "supernet_zeros_criteo"])
 def test_native_steps_are_bit_identical_to_python_engine(name):
     meta, _ = load_golden(name)
     smeta, _ = load_golden("samplers")

@@ -67,7 +67,7 @@ def _compare(logits, loss, grads, logits_ref, loss_ref, gn_ref, small, emb_rows,
 
 
 @pytest.mark.parametrize("name", ["supernet_autoctr_criteo", "supernet_xlarge_criteo", "supernet_xlarge_kdd",
-                                  "supernet_xlarge_avazu"])
+                                  "supernet_xlarge_avazu", "supernet_zeros_criteo"])
 def test_supernet_matches_reference_golden(name):
     meta, arr = load_golden(name)
     m, sd = _build(meta["cfg"], meta["num_embeddings"], meta["nd"], meta["shapes"], meta["state_seed"])

@@ -34,7 +34,7 @@ def _check_case(cfg, sd, ne, nd, ds, choice, B, seed, logits_ref, loss_ref, gn_r
 
 
 @pytest.mark.parametrize("name", ["supernet_autoctr_criteo", "supernet_xlarge_criteo", "supernet_xlarge_kdd",
-                                  "supernet_xlarge_avazu"])
+                                  "supernet_xlarge_avazu", "supernet_zeros_criteo"])
 def test_oracle_matches_reference_supernet(name):
     meta, arr = load_golden(name)
     sd = orc.fill_state_dict(meta["shapes"], meta["state_seed"])

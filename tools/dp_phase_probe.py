@@ -17,8 +17,8 @@ torch.manual_seed(1234); np.random.seed(1234)
 model = SuperNet(num_blocks=7, ops_config=ops_config_lib["autoctr"], use_layernorm=True, num_embeddings=ne,
                  path_sampling_strategy="default", anypath_choice="binomial-0.5", supernet_training_steps=0).to(dev)
 model.materialize(13); model.apply(init_weights)
-tr = DataParallelTrainer(model, lr=bench.LR)
-pool = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in bench.synth_pool(32, bench.B_TRAIN, 13, ne, seed=1234 + rank)]
+tr = DataParallelTrainer(model, lr=0.12)
+pool = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in bench.synth_pool(32, 512, 13, ne, seed=1234 + rank)]
 for i in range(5):
     tr.step(*pool[i])
 dist.barrier(); torch.cuda.synchronize()

@@ -12,8 +12,8 @@ torch.manual_seed(1234); np.random.seed(1234)
 m = SuperNet(num_blocks=7, ops_config=ops_config_lib["autoctr"], use_layernorm=True, num_embeddings=ne,
              path_sampling_strategy="default", anypath_choice="binomial-0.5", supernet_training_steps=0).to(dev)
 m.materialize(13); m.apply(init_weights)
-tr = NativeTrainer(m, lr=bench.LR)
-pool = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in bench.synth_pool(32, bench.B_TRAIN, 13, ne, seed=1)]
+tr = NativeTrainer(m, lr=0.12)
+pool = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in bench.synth_pool(32, 512, 13, ne, seed=1)]
 for i in range(10): tr.step(*pool[i % 32])
 torch.cuda.synchronize()
 N = 200
