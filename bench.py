@@ -39,6 +39,7 @@ CAP = 500000
 _CRITEO = [1461, 584, 10131227, 2202609, 306, 25, 12518, 634, 4, 93146, 5684, 8351593, 3195, 28, 14993, 5461307, 11,
            5653, 2174, 5, 7046548, 19, 16, 286182, 106, 142573]
 _KDD = [26274, 641708, 14848, 22122011, 1188090, 3735797, 2934102, 20004011, 4, 8]
+_AVAZU = [10000, 241, 8, 8, 4738, 7746, 27, 8553, 560, 37, 2686409, 6729487, 8252, 6, 5, 2627, 9, 10, 436, 5, 69, 173, 61]
 
 CONFIGS = {
     "small_supernet": dict(
@@ -51,6 +52,12 @@ CONFIGS = {
         lr=0.16, nd=13, ne=None, strategy="fixed-path", anypath="uniform",
         workload="NASRec-Full best Criteo model (configs/criteo/ea_criteo_kaggle_xlarge_best_1shot.json, fixed, LN off), "
                  "B=256/GPU, synthetic Criteo shape, Adagrad(0.16)+clip5"),
+    "avazu_full_best": dict(
+        metric="avazu_full_best_train_samples_per_sec", unit="samples/s", ops="xlarge", fixed=True, ln=False, B=256,
+        lr=0.16, nd=1, ne=list(_AVAZU), strategy="fixed-path", anypath="uniform", best="avazu_xlarge", zero_dense=True,
+        workload="NASRec-Full best Avazu model (configs/avazu/ea_avazu_kaggle_xlarge_best_1shot.json, fixed, LN off), "
+                 "full-size tables (9.46 M rows), B=256/GPU, synthetic Avazu shape (1 all-zero dense + 23 sparse), "
+                 "Adagrad(0.16)+clip5"),
     "kdd_xlarge": dict(
         metric="kdd_xlarge_supernet_train_samples_per_sec", unit="samples/s", ops="xlarge", fixed=False, ln=True, B=2048,
         lr=0.12, nd=3, ne=[min(x, CAP) for x in _KDD], strategy="default", anypath="binomial-0.5",
@@ -75,13 +82,15 @@ def config_of(args):
 
 
 # ----------------------------------------------------------------------------- synthetic data
-def synth_pool(n_batches, batch, nd, num_embeddings, seed, zipf=True):
+def synth_pool(n_batches, batch, nd, num_embeddings, seed, zipf=True, zero_dense=False):
     """log1p(Poisson(3)) dense, Zipf(1.05)-ranked ids through a fixed permutation with id 0 =
     'missing' (p=0.02), Bernoulli(0.25) labels; a pool of distinct batches that is cycled."""
     rs = np.random.RandomState(seed)
     pool = []
     for _ in range(n_batches):
         int_x = np.log1p(rs.poisson(3.0, (batch, nd))).astype(np.float32)
+        if zero_dense:
+            int_x[:] = 0.0                 # Avazu has no dense features: one all-zero column (data_pipes.py:181)
         cols = []
         for n in num_embeddings:
             if n <= 1:
@@ -98,9 +107,9 @@ def synth_pool(n_batches, batch, nd, num_embeddings, seed, zipf=True):
     return pool
 
 
-def _best_choice():
+def _best_choice(which="criteo_xlarge"):
     meta = json.load(open(os.path.join(ROOT, "tests", "golden", "fixed_best.json")))
-    return meta["models"]["criteo_xlarge"]["choice"]
+    return meta["models"][which]["choice"]
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -180,7 +189,7 @@ def reference_train(cfg, steps, warmup, seed=1234):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B, nd, ne = cfg["B"], cfg["nd"], cfg["ne"]
-    pool = synth_pool(max(2, min(8, steps + warmup)), B, nd, ne, seed)
+    pool = synth_pool(max(2, min(8, steps + warmup)), B, nd, ne, seed, zero_dense=cfg.get("zero_dense", False))
     # one extra trailing batch: the reference's loop logs and evaluates on its last step, which must not be a timed one
     batches = [tuple(torch.from_numpy(a) for a in pool[i % len(pool)]) for i in range(warmup + steps + 1)]
     ref = _reference_modules()
@@ -192,7 +201,7 @@ def reference_train(cfg, steps, warmup, seed=1234):
         kw = dict(num_blocks=7, ops_config=ref_ops[cfg["ops"]], use_layernorm=cfg["ln"], num_embeddings=ne,
                   sparse_input_size=len(ne), path_sampling_strategy="full-path")
         if cfg["fixed"]:
-            kw.update(path_sampling_strategy="fixed-path", fixed=True, fixed_choice=_best_choice())
+            kw.update(path_sampling_strategy="fixed-path", fixed=True, fixed_choice=_best_choice(cfg.get("best", "criteo_xlarge")))
         else:
             kw.update(anypath_choice=cfg["anypath"], supernet_training_steps=0)
         m = RefNet(**kw)
@@ -244,7 +253,7 @@ def _port_train(cfg, batches, steps, warmup, seed):
     kw = dict(num_blocks=7, ops_config=ops_config_lib[cfg["ops"]], use_layernorm=cfg["ln"], num_embeddings=cfg["ne"],
               sparse_input_size=len(cfg["ne"]), path_sampling_strategy=cfg["strategy"])
     if cfg["fixed"]:
-        kw.update(fixed=True, fixed_choice=_best_choice())
+        kw.update(fixed=True, fixed_choice=_best_choice(cfg.get("best", "criteo_xlarge")))
     else:
         kw.update(anypath_choice=cfg["anypath"], supernet_training_steps=0)
     host = SuperNet(**kw)
@@ -254,7 +263,7 @@ def _port_train(cfg, batches, steps, warmup, seed):
     tr = orc.OracleTrainer(sd, dict(ops=cfg["ops"], use_layernorm=cfg["ln"], fixed=cfg["fixed"], num_blocks=7), lr=cfg["lr"])
     times = []
     for i, b in enumerate(batches):
-        choice = _best_choice() if cfg["fixed"] else (host._sample() and host.choice)
+        choice = _best_choice(cfg.get("best", "criteo_xlarge")) if cfg["fixed"] else (host._sample() and host.choice)
         t0 = time.perf_counter()
         tr.step(choice, *b)
         if i >= warmup:
@@ -408,7 +417,7 @@ def build_training(env, cfg, seed=1234):
     kw = dict(num_blocks=7, ops_config=ops_config_lib[cfg["ops"]], use_layernorm=cfg["ln"], num_embeddings=cfg["ne"],
               sparse_input_size=len(cfg["ne"]), path_sampling_strategy=cfg["strategy"])
     if cfg["fixed"]:
-        kw.update(fixed=True, fixed_choice=_best_choice())
+        kw.update(fixed=True, fixed_choice=_best_choice(cfg.get("best", "criteo_xlarge")))
     else:
         kw.update(anypath_choice=cfg["anypath"], supernet_training_steps=0)
     model = SuperNet(**kw).to(env.dev)
@@ -435,7 +444,7 @@ def measure_training(env, cfg, trainer, K, W, profile_gemm=True):
     from nasrec_b200 import _lib
     B, nd, ne = cfg["B"], cfg["nd"], cfg["ne"]
     NP = 64 if B <= 512 else 16
-    pool_h = synth_pool(NP, B, nd, ne, seed=1234 + rank)            # different data per rank, same choices
+    pool_h = synth_pool(NP, B, nd, ne, seed=1234 + rank, zero_dense=cfg.get("zero_dense", False))   # per-rank data, same choices
     pool_d = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in pool_h]
     pool_p = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in pool_h]
     for i in range(W):
@@ -671,13 +680,21 @@ def run_ours(args):
     cfg = config_of(args)
     K, W = max(1, args.steps), max(3, args.warmup)      # timing rules: at least 3 warm-up steps (the line reports W)
     line = None
+    if args.dtype == "bf16":
+        import nasrec_b200
+        nasrec_b200.set_precision("bf16")
+    arith = ("bf16 GEMM operands (round-to-nearest-even), one product per k-step on the tensor cores, fp32 TMEM accumulation; "
+             "fp32 master weights / Adagrad state / activations (logits within 2e-2 RMS of the reference under autocast)"
+             if args.dtype == "bf16" else
+             "fp32 storage and accumulation; GEMMs as 3xTF32-split tcgen05 MMAs (fp32-parity, logits within 1e-5 of the fp32 "
+             "reference)")
     if args.config == "ea":
         r = measure_ea(env, cfg)
         if rank == 0:
             line = {"metric": cfg["metric"], "value": r["value"], "unit": cfg["unit"], "n_gpus": world, "steps": r["n_cand"],
                     "warmup": 2, "ms_per_step": r["sec"] * 1e3 / r["n_cand"] * world, "higher_is_better": True, "scaling": "weak",
-                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                    "config": {"workload": cfg["workload"], "candidates": r["n_cand"], "per_rank": r["n_cand"] // world,
+                    "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                    "config": {"workload": cfg["workload"], "arithmetic": arith, "candidates": r["n_cand"], "per_rank": r["n_cand"] // world,
                                "eval_batches": EA_BATCHES, "eval_batch": cfg["B"], "l2": "evaluation set (8 x 8192 x 15 KB) and "
                                "the 171 M-parameter supernet exceed L2", "parallelism": "candidates sharded x%d" % world},
                     "gpu_launches": _lib.LIB.launches,
@@ -694,11 +711,9 @@ def run_ours(args):
         if rank == 0:
             line = {"metric": cfg["metric"], "value": r["value"], "unit": cfg["unit"], "n_gpus": world, "steps": K, "warmup": W,
                     "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                    "dtype": "f32", "data": "synthetic",
+                    "dtype": args.dtype, "data": "synthetic",
                     "config": {"workload": cfg["workload"], "per_gpu_batch": cfg["B"], "global_batch": cfg["B"] * world,
-                               "host": host,
-                               "arithmetic": "fp32 storage and accumulation; GEMMs as 3xTF32-split tcgen05 MMAs "
-                                             "(fp32-parity, logits within 1e-5 of the fp32 reference)",
+                               "host": host, "arithmetic": arith,
                                "parallelism": "dp%d" % world, "l2": "256 MB flush write between timed steps",
                                "ids": "zipf(1.05)"},
                     "clocks": r["clocks"], "gpu_launches": r["launches"],
@@ -712,7 +727,7 @@ def run_ours(args):
         del trainer, model
         torch.cuda.empty_cache()
         # the other BASELINE configs ride along as `extra` on the default line
-        if args.config == "small_supernet" and not args.no_extras:
+        if args.config == "small_supernet" and not args.no_extras and args.dtype == "f32":
             extra = {}
             ea = measure_ea(env, CONFIGS["ea"])
             extra["ea_subnets_per_sec_%dx8192" % EA_BATCHES] = ea["value"]
@@ -730,13 +745,25 @@ def run_ours(args):
                     extra[key + "_samples_per_sec_e2e"] = r2["e2e"]
                     del m2, t2
                     torch.cuda.empty_cache()
+                # bf16 compute (configs[3]): the Avazu NASRec-Full best model with full-size tables, and the EA scoring
+                import nasrec_b200
+                with nasrec_b200.precision("bf16"):
+                    c2 = config_of(argparse.Namespace(config="avazu_full_best", tables="full"))
+                    m2, t2, _h = build_training(env, c2)
+                    r2 = measure_training(env, c2, t2, max(10, K // 2), W, profile_gemm=False)
+                    extra["avazu_full_best_bf16_samples_per_sec"] = r2["value"]
+                    extra["avazu_full_best_bf16_samples_per_sec_e2e"] = r2["e2e"]
+                    del m2, t2
+                    torch.cuda.empty_cache()
+                    ea16 = measure_ea(env, CONFIGS["ea"])
+                    extra["ea_subnets_per_sec_%dx8192_bf16" % EA_BATCHES] = ea16["value"]
                 extra["hbm_kernels"] = measure_hbm_kernels(env)
             if rank == 0:
                 line["extra"] = extra
         if world == 1 and rank == 0 and not args.no_cpu:
             base, _ = reference_train(cfg, 12, 3)
             line["cpu_baseline"] = base
-            if args.config == "small_supernet" and not args.no_extras:
+            if args.config == "small_supernet" and not args.no_extras and args.dtype == "f32":
                 for name, tables in (("criteo_full_best", "capped"), ("criteo_full_best", "full")):
                     b2, _ = reference_train(config_of(argparse.Namespace(config=name, tables=tables)), 6, 2)
                     line["extra"]["%s_%s_tables_cpu_reference_samples_per_sec" % (name, tables)] = b2["value"]
@@ -755,6 +782,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="small_supernet", choices=sorted(CONFIGS))
     ap.add_argument("--tables", default="capped", choices=["capped", "full"], help="criteo_full_best: embedding table sizes")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="GEMM arithmetic: f32 = 3xTF32-split (fp32 parity); bf16 = bf16 operands, fp32 accumulate (use_amp)")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs' side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()

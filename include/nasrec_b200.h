@@ -55,7 +55,12 @@ int nasrec_version(int* sm);
  *   0  fp32 FFMA on CUDA cores (reference-exact fp32 products);
  *   3  tcgen05 kind::tf32 tensor cores, each fp32 operand split into tf32 hi+lo, products
  *      hi*hi + hi*lo + lo*hi accumulated in fp32 Tensor Memory ("3xTF32");
- *   4  as 3 plus lo*lo;   1  plain single-pass tf32 (not fp32 parity; diagnostics only).
+ *   4  as 3 plus lo*lo;   1  plain single-pass tf32 (not fp32 parity; diagnostics only);
+ *   2  bf16 compute (the reference's --use_amp path, train_utils.py:146,247-286): every GEMM operand is rounded to
+ *      nearest-even bfloat16 and ONE product per k-step is accumulated in fp32 Tensor Memory -- the products a
+ *      kind::f16 bf16 MMA forms, issued on the tf32 pipe from fp32 containers; master weights, Adagrad state,
+ *      activations and every non-GEMM kernel stay fp32.  The weight planes then hold rn_bf16(W): rebuild them
+ *      (nasrec_planes_refresh) after switching to or from this mode.
  * Process-wide; returns 0 or NASREC_EINVAL. */
 int nasrec_set_gemm_mode(int mode);
 int nasrec_get_gemm_mode(void);

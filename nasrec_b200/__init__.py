@@ -7,7 +7,34 @@ see INTEGRATION.md.  The arithmetic is hand-written CUDA behind the C ABI in
 from . import _lib  # noqa: F401
 from .supernet.supernet import SuperNet, SuperNetBlock, ops_config_lib, path_sampling_strategy_lib  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+
+class precision:
+    """``with nasrec_b200.precision("bf16"): ...`` -- GEMM arithmetic of everything run inside (process-wide switch):
+    "fp32" = 3xTF32-split tensor-core products (fp32 parity, the default), "bf16" = the reference's mixed-precision
+    path (train_utils.py:146,247-286 ``use_amp``): GEMM operands rounded to bfloat16, one product per k-step, fp32
+    accumulation; master weights, Adagrad state, activations and all non-GEMM kernels stay fp32.  Stated tolerance
+    (tests/test_gpu_bf16.py): logits within 2e-2 (RMS, relative) of the reference under torch.autocast(bfloat16)."""
+    MODES = {"fp32": 3, "bf16": 2, "tf32": 1, "ffma": 0}
+
+    def __init__(self, name: str):
+        if name not in self.MODES:
+            raise ValueError("precision must be one of %s" % sorted(self.MODES))
+        self.mode = self.MODES[name]
+
+    def __enter__(self):
+        self.prev = _lib.LIB.gemm_mode()
+        _lib.LIB.set_gemm_mode(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.LIB.set_gemm_mode(self.prev)
+
+
+def set_precision(name: str):
+    """Process-wide GEMM arithmetic: see ``precision``."""
+    _lib.LIB.set_gemm_mode(precision.MODES[name])
 
 
 def install_as_nasrec():

@@ -124,16 +124,20 @@ class _Lib:
         mode = os.environ.get("NASREC_GEMM_MODE")
         if mode is not None:
             if self.cdll.nasrec_set_gemm_mode(int(mode)) != 0:
-                raise ValueError("NASREC_GEMM_MODE=%s is not one of 0,1,3,4" % mode)
+                raise ValueError("NASREC_GEMM_MODE=%s is not one of 0..4" % mode)
         self.cdll.nasrec_version.argtypes = [C.POINTER(C.c_int)]
         self.cdll.nasrec_version.restype = C.c_int
         return self
 
     def set_gemm_mode(self, mode: int):
-        """0 = fp32 FFMA, 3/4 = tcgen05 3xTF32 / 4xTF32, 1 = single-pass tf32 (diagnostics)."""
+        """0 = fp32 FFMA, 3/4 = tcgen05 3xTF32 / 4xTF32, 2 = bf16 operands (one product, fp32 accumulate), 1 = single-pass
+        tf32 (diagnostics)."""
         self.load()
+        before = int(self.cdll.nasrec_get_gemm_mode())
         if self.cdll.nasrec_set_gemm_mode(int(mode)) != 0:
             raise ValueError("unsupported GEMM mode %r" % (mode,))
+        if (before == 2) != (int(mode) == 2):
+            self.weights_epoch += 1          # the weight planes hold a different rounding now: rebuild them
 
     def set_gemm_tma(self, on: bool):
         """TMA-fed operand path of the tensor-core GEMM on/off (both paths agree bit for bit)."""

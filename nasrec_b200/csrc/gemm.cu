@@ -219,7 +219,7 @@ struct ProfScope {
     }
 };
 
-int g_gemm_mode = 3;   // 0: fp32 FFMA; 1/3/4: tcgen05 kind::tf32 with 1/3/4 split products (default 3xTF32)
+int g_gemm_mode = 3;   // 0: fp32 FFMA; 1/3/4: tcgen05 kind::tf32 with 1/3/4 split products (default 3xTF32); 2: bf16 operands
 
 View plain_view(const float* p, long long si, long long sj, int contig_j) {
     View v{};
@@ -547,7 +547,7 @@ int run_tma(TmaJob& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
 
 inline bool tma_on() { return g_use_tma && g_gemm_mode != 0 && have_encoder(); }
 inline bool planes_for(const float* W, long long ldw) {
-    return g_pl.W == W && g_pl.hi && (g_gemm_mode == 1 || g_pl.lo) && g_pl.cols == (int)ldw;
+    return g_pl.W == W && g_pl.hi && (g_gemm_mode <= 2 || g_pl.lo) && g_pl.cols == (int)ldw;
 }
 
 constexpr int NOT_TMA = -1000;     // "this launch does not qualify": the caller takes the LDG-producer kernel
@@ -565,7 +565,7 @@ int tma_seg_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw,
     TmaJob& job = fresh_job();
     job.a_kind = OP_KM128; job.a_conv = 1; job.b_kind = OP_KM128; job.b_conv = 0;
     const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
-    const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
+    const int bl = g_gemm_mode > 2 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
     TBatch& tb = job.tb;
     tb.nprob = 1;
     Prob& p = tb.prob[0];
@@ -593,7 +593,7 @@ int tma_seg_dgrad(const float* dC, int64_t ldc, int N, const float* W, int64_t l
     job.a_kind = OP_KM128; job.a_conv = 1; job.b_kind = OP_MN128; job.b_conv = 0;
     const int ah = job.add(spec2d(dC, N, M, ldc), 0);
     const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
-    const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
+    const int bl = g_gemm_mode > 2 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
     TBatch& tb = job.tb;
     int np = 0;
     for (int s = 0; s < nseg; ++s) {
@@ -660,7 +660,7 @@ int tma_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ld
     TmaJob& job = fresh_job();
     job.a_kind = OP_MN3; job.a_conv = 1; job.b_kind = OP_KM128; job.b_conv = 0;
     const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
-    const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
+    const int bl = g_gemm_mode > 2 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
     TBatch& tb = job.tb;
     tb.nprob = 1;
     Prob& p = tb.prob[0];
@@ -688,7 +688,7 @@ int tma_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* W, 
     job.a_kind = OP_MN3; job.a_conv = 1; job.b_kind = OP_MN128; job.b_conv = 0;
     const int ah = job.add(spec3d(dZ, P, B, dz_bstride), 0);
     const int bh = job.add(spec2d(g_pl.hi, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1);
-    const int bl = g_gemm_mode > 1 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
+    const int bl = g_gemm_mode > 2 ? job.add(spec2d(g_pl.lo, g_pl.cols + g_pl.shift, g_pl.rows, g_pl.ldp), 1) : bh;
     TBatch& tb = job.tb;
     int np = 0;
     for (int s = 0; s < nseg; ++s) {
@@ -730,7 +730,7 @@ void nasrec_internal_set_side_stream(cudaStream_t s) { g_side = s; }
 extern "C" {
 
 int nasrec_set_gemm_mode(int mode) {
-    if (mode != 0 && mode != 1 && mode != 3 && mode != 4) return NASREC_EINVAL;
+    if (mode < 0 || mode > 4) return NASREC_EINVAL;
     g_gemm_mode = mode;
     return 0;
 }

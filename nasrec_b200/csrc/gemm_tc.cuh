@@ -86,6 +86,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// round to nearest-even bfloat16, kept in an fp32 container (every bf16 value is a tf32 value: the tf32 tensor pipe then
+// multiplies exactly what a kind::f16 bf16 MMA would)
+__device__ __forceinline__ float round_bf16(float a) {
+    const uint32_t u = __float_as_uint(a);
+    return __uint_as_float((u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u);
+}
+
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
     // hi = a rounded to nearest tf32 (10 explicit mantissa bits); lo = a - hi, exact in fp32 and
     // |lo| <= 2^-11 |a|.  The tensor core drops the low 13 mantissa bits of lo itself, an error of
@@ -126,9 +133,12 @@ __device__ __forceinline__ float4 ldg128_pred(const float* p, bool pred) {
     return v;
 }
 
-__device__ __forceinline__ void store_split4(uint8_t* s_hi, uint8_t* s_lo, uint32_t off, const float4& x, bool split) {
+__device__ __forceinline__ void store_split4(uint8_t* s_hi, uint8_t* s_lo, uint32_t off, const float4& x, bool split,
+                                             bool bf16 = false) {
     float4 h, l;
-    if (split) {
+    if (bf16) {
+        h = make_float4(round_bf16(x.x), round_bf16(x.y), round_bf16(x.z), round_bf16(x.w));
+    } else if (split) {
         split_tf32(x.x, h.x, l.x);
         split_tf32(x.y, h.y, l.y);
         split_tf32(x.z, h.z, l.z);
@@ -214,10 +224,10 @@ struct Stager {
         for (int q = 0; q < NV; ++q) ptr[q] += step;
         k0 += TC_BK;
     }
-    __device__ __forceinline__ void store(const float4 (&r)[NV], uint8_t* s_hi, uint8_t* s_lo, bool split) const {
+    __device__ __forceinline__ void store(const float4 (&r)[NV], uint8_t* s_hi, uint8_t* s_lo, bool split, bool bf16) const {
 #pragma unroll
         for (int q = 0; q < NV; ++q)
-            if (live & (1u << q)) store_split4(s_hi, s_lo, soff[q], r[q], split);
+            if (live & (1u << q)) store_split4(s_hi, s_lo, soff[q], r[q], split, bf16);
     }
 };
 
@@ -349,8 +359,8 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) gemm_tc_ke
                     const uint32_t ph = (uint32_t)(cur / Cfg::STAGES) & 1u;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
-                    sa.store(ra[h], st, st + Cfg::A_BYTES, nprod > 1);
-                    sb.store(rb[h], st + 2 * Cfg::A_BYTES, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, nprod > 1);
+                    sa.store(ra[h], st, st + Cfg::A_BYTES, nprod > 2, nprod == 2);
+                    sb.store(rb[h], st + 2 * Cfg::A_BYTES, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, nprod > 2, nprod == 2);
                     fence_proxy_async_smem();          // every writer orders its generic-proxy stores
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_full + 8 * s);
@@ -445,7 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) gemm_tc_ke
                 for (int k = 0; k < TC_BK / TC_UK; ++k) {
                     const uint64_t adv = (uint64_t)((k * TC_UK * 4) >> 4);     // +32 B per UMMA_K inside the atom
                     const uint32_t first = (it >= nacc || k > 0) ? 1u : 0u;    // first touch of this accumulator
-                    if (nprod > 1) {
+                    if (nprod > 2) {
                         // small cross terms first, the dominant hi*hi product last
                         umma_tf32(tacc, a_lo + adv, b_hi + adv, idesc, first);
                         umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);

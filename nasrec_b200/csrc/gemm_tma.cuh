@@ -143,7 +143,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 
 // hi = rn_tf32(x) written back in place, lo = x - hi into the lo plane at the same (swizzled) offset (B tiles of wgrad)
 template <int NV, int NT>
-__device__ __forceinline__ void convert_tile(uint8_t* hi, uint8_t* lo, int nchunk, int tid) {
+__device__ __forceinline__ void convert_tile(uint8_t* hi, uint8_t* lo, int nchunk, int tid, bool bf16) {
     float4 v[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
@@ -153,7 +153,7 @@ __device__ __forceinline__ void convert_tile(uint8_t* hi, uint8_t* lo, int nchun
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
         const int c = tid + q * NT;
-        if (c < nchunk) store_split4(hi, lo, (uint32_t)c * 16u, v[q], true);
+        if (c < nchunk) store_split4(hi, lo, (uint32_t)c * 16u, v[q], !bf16, bf16);
     }
 }
 
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const int ntiles = max(0, kt_end - kt_begin);
     const int nacc = min(Cfg::NACC_MAX, ntiles);
     const int nprod = tb.nprod;
+    // nprod: 1 = plain tf32 single pass, 2 = bf16-rounded operands single pass, 3/4 = tf32 hi/lo split products
     const bool conv_b = nprod > 1 && tb.lb.convert;
 
     if (tid == 0) {
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         if (ntiles > 0) {
             const OpLayout& LA = tb.la;
             const OpLayout& LB = tb.lb;
-            const bool b_lo = nprod > 1 && !LB.convert;                        // the weight's lo plane is fetched, not derived
+            const bool b_lo = nprod > 2 && !LB.convert;                        // the weight's lo plane is fetched, not derived
             const uint32_t tx = (uint32_t)(LA.nbox * LA.box_bytes + LB.nbox * LB.box_bytes * (b_lo ? 2 : 1));
             const int a_rank = LA.rank, a_nbox = LA.nbox, a_bb = LA.box_bytes, b_rank = LB.rank, b_nbox = LB.nbox, b_bb = LB.box_bytes;
             const int ar0 = m0 >> LA.rsh[0], ar1 = m0 >> LA.rsh[1], ar2 = m0 >> LA.rsh[2];
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     const uint64_t b_hi = (uint64_t)((((sb + ko) >> 4) & 0x3FFFu) | dlo) | dhi;
                     const uint64_t b_lo = (uint64_t)((((sb + Cfg::B_BYTES + ko) >> 4) & 0x3FFFu) | dlo) | dhi;
                     const uint32_t first = (it >= nacc || k > 0) ? 1u : 0u;
-                    if (nprod > 1) {
+                    if (nprod > 2) {
                         umma_tf32_ts_w(tacc, a_lo, b_hi, idesc, first);
                         umma_tf32_ts_w(tacc, a_hi, b_lo, idesc, 1u);
                         if (nprod > 3) umma_tf32_ts_w(tacc, a_lo, b_lo, idesc, 1u);
@@ -410,19 +411,23 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                             x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
                         }
                     }
-                    if (nprod > 1) {
+                    if (nprod > 2) {
                         float hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) split_tf32(x[j], hi[j], lo[j]);
                         tmem_st16(ta + (uint32_t)(h * 16), hi);
                         tmem_st16(ta + 32u + (uint32_t)(h * 16), lo);
+                    } else if (nprod == 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) x[j] = round_bf16(x[j]);
+                        tmem_st16(ta + (uint32_t)(h * 16), x);
                     } else {
                         tmem_st16(ta + (uint32_t)(h * 16), x);
                     }
                 }
                 if (conv_b) {
                     uint8_t* bh = const_cast<uint8_t*>(st) + Cfg::A_BYTES;
-                    convert_tile<(Cfg::B_BYTES / 16 + 127) / 128, 128>(bh, bh + Cfg::B_BYTES, nb, ctid);
+                    convert_tile<(Cfg::B_BYTES / 16 + 127) / 128, 128>(bh, bh + Cfg::B_BYTES, nb, ctid, nprod == 2);
                     fence_proxy_async_smem();
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

@@ -100,11 +100,14 @@ struct AdagradPack {
     float* lo[MT_MAX];
     int cols[MT_MAX];
     int ldp[MT_MAX];
+    int bf16;               // planes hold rn_bf16(w) (GEMM mode 2) instead of rn_tf32(w)
     int first[MT_MAX];      // plane column of w column c: c + (c >= first ? shift : 0), shift = (4 - first % 4) % 4
 };
 
-__device__ __forceinline__ void plane_split(float w, float& hi, float& lo) {
-    hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
+// bf16 != 0 (GEMM mode 2): hi = rn_bf16(w), what the single-pass bf16 product multiplies (lo is not used then)
+__device__ __forceinline__ void plane_split(float w, float& hi, float& lo, int bf16) {
+    const uint32_t u = __float_as_uint(w);
+    hi = bf16 ? __uint_as_float((u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u) : __uint_as_float((u + 0x1000u) & 0xFFFFE000u);
     lo = w - hi;
 }
 
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ Ad
         const unsigned r = (unsigned)i / cols, c = (unsigned)i - r * cols;
         const unsigned pc = c + (c >= first ? shift : 0u);
         float h, l;
-        plane_split(wi, h, l);
+        plane_split(wi, h, l, pk.bf16);
         ph[r * ldp + pc] = h;
         pl[r * ldp + pc] = l;
     };
@@ -158,10 +161,10 @@ __global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ Ad
                 const long long e = beg + (i << 2);
                 if (ldp == (long long)cols && shift == 0) {      // planes have w's own layout: 16-byte stores
                     float4 h4, l4;
-                    plane_split(wv.x, h4.x, l4.x);
-                    plane_split(wv.y, h4.y, l4.y);
-                    plane_split(wv.z, h4.z, l4.z);
-                    plane_split(wv.w, h4.w, l4.w);
+                    plane_split(wv.x, h4.x, l4.x, pk.bf16);
+                    plane_split(wv.y, h4.y, l4.y, pk.bf16);
+                    plane_split(wv.z, h4.z, l4.z, pk.bf16);
+                    plane_split(wv.w, h4.w, l4.w, pk.bf16);
                     *reinterpret_cast<float4*>(ph + e) = h4;
                     *reinterpret_cast<float4*>(pl + e) = l4;
                 } else {
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ Ad
 // hi/lo planes of a [rows, cols] weight (row stride ldw) with row stride ldp; pad columns are left alone (zero)
 __global__ void __launch_bounds__(256) planes_refresh_kernel(const float* __restrict__ w, long long ldw, int rows, int cols,
                                                              int first, float* __restrict__ hi, float* __restrict__ lo,
-                                                             long long ldp) {
+                                                             long long ldp, int bf16) {
     pdl_enter();
     const int shift = (4 - (first & 3)) & 3;
     const long long total = (long long)rows * cols;
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(256) planes_refresh_kernel(const float* __rest
         const long long r = i / cols;
         const int c = (int)(i - r * cols);
         float h, l;
-        plane_split(w[r * ldw + c], h, l);
+        plane_split(w[r * ldw + c], h, l, bf16);
         const long long o = r * ldp + c + (c >= first ? shift : 0);
         hi[o] = h;
         lo[o] = l;
@@ -263,7 +266,8 @@ int nasrec_planes_refresh(const float* W, int64_t ldw, int rows, int cols, int f
     const long long total = (long long)rows * cols;
     long long gx = (total + 255) / 256;
     if (gx > 2368) gx = 2368;
-    nasrec_launch(planes_refresh_kernel, (unsigned)gx, 256, 0, as_stream(stream), W, (long long)ldw, rows, cols, first, hi, lo, (long long)ldp);
+    nasrec_launch(planes_refresh_kernel, (unsigned)gx, 256, 0, as_stream(stream), W, (long long)ldw, rows, cols, first, hi, lo, (long long)ldp,
+                  nasrec_get_gemm_mode() == 2 ? 1 : 0);
     return nasrec_launch_status();
 }
 
@@ -281,6 +285,7 @@ int nasrec_adagrad_multi_planes(float* const* w, const float* const* grads, floa
     int done = 0;
     while (done < n) {
         AdagradPack pk{};
+        pk.bf16 = nasrec_get_gemm_mode() == 2 ? 1 : 0;
         int m = 0, chunks = 0;
         for (; done + m < n && m < MT_MAX; ++m) {
             pk.w[m] = w[done + m];

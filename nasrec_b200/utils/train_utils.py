@@ -102,7 +102,10 @@ def test_one_epoch(model, test_loader, loss_fn=None, gpu=None, max_steps: int = 
     (``nasrec_binary_metrics``), so only three scalars reach the host.  ``loss_fn`` is accepted
     for signature compatibility; the metric is BCE-with-logits, the only loss the reference wires."""
     from ..search import binary_metrics_device
-    assert not use_amp, "mixed precision is not part of the B200 path (SURVEY 0.5)"
+    if use_amp:          # train_utils.py:146 autocast: GEMMs on bf16 operands (nasrec_b200.precision)
+        from .. import precision
+        with precision("bf16"):
+            return test_one_epoch(model, test_loader, loss_fn, gpu, max_steps, False)
     was_training = model.training
     model.eval()
     preds, labels = [], []
@@ -131,7 +134,13 @@ def train_and_test_one_epoch(model, epoch: int, optimizer, lr_scheduler, train_l
     (``reference_style_step`` + the L2 term) -- or a ``FusedTrainer``, which replaces that body by
     the fused step when ``l2_loss_fn`` is None / weight decay is 0 (the shipped recipes)."""
     from ..search import binary_metrics_device
-    assert not use_amp, "mixed precision is not part of the B200 path (SURVEY 0.5)"
+    if use_amp:          # train_utils.py:247-286: autocast forward + (here unnecessary) loss scaling -> bf16 GEMM operands
+        from .. import precision
+        with precision("bf16"):
+            return train_and_test_one_epoch(model, epoch, optimizer, lr_scheduler, train_loader, test_loader, loss_fn,
+                                            l2_loss_fn, train_batch_size, gpu, display_interval, test_interval,
+                                            max_train_steps, max_eval_steps, test_only_at_last_step, grad_clip_value,
+                                            tb_writer, False)
     logs = {k: [] for k in ("train_loss", "train_AUROC", "train_Accuracy", "test_loss", "test_AUROC", "test_Accuracy",
                             "epoch", "iters")}
     fused = isinstance(optimizer, FusedTrainer)

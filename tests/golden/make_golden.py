@@ -209,6 +209,41 @@ def step_fixture():
     save("train_steps", meta, arrays)
 
 
+def bf16_fixture():
+    """bf16 compute (BASELINE config #4; the reference's --use_amp hooks, train_utils.py:146,247-286): the reference under
+    torch.autocast("cpu", dtype=bfloat16) -- linear layers in bf16 with fp32 accumulation and bf16 outputs, LayerNorm /
+    softmax / loss in fp32, fp32 master weights -- forward + backward on the Avazu and Criteo NASRec-Full best models and
+    on an autoctr supernet choice.  Pins the stated bf16 tolerance of GEMM mode 2."""
+    cfgdir = "/root/reference/nasrec/configs"
+    meta = dict(models={})
+    arrays = {}
+    cases = [("avazu_xlarge", "avazu", "avazu/ea_avazu_kaggle_xlarge_best_1shot.json", False),
+             ("criteo_xlarge", "criteo", "criteo/ea_criteo_kaggle_xlarge_best_1shot.json", False)]
+    for tag, ds, rel, ln in cases:
+        choice = json.load(open(os.path.join(cfgdir, rel)))
+        m, ne = build(ds, choice["config"], ln, fixed=True, choice=choice)
+        shapes = load_filled(m, seed=5)
+        D = DATASETS[ds]
+        int_x, cat_x, y = orc.synth_batch(64, D["nd"], ne, seed=42, all_zero_dense=(ds == "avazu"))
+        m.zero_grad()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            logits = m(int_x, cat_x)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(logits.float(), y)
+        loss.backward()
+        gn = {n: float(p.grad.double().norm()) for n, p in m.named_parameters() if p.grad is not None}
+        m.zero_grad()
+        ref32 = m(int_x, cat_x)
+        meta["models"][tag] = dict(dataset=ds, choice=jsonable(choice), num_embeddings=ne, nd=D["nd"],
+                                   cfg=dict(ops=choice["config"], use_layernorm=ln, fixed=True, num_blocks=7), state_seed=5,
+                                   batch=64, batch_seed=42, loss=float(loss), grad_norms=gn,
+                                   shapes={k: list(v) for k, v in shapes.items()},
+                                   fp32_vs_bf16_logit_rms=float((ref32.detach() - logits.detach().float()).pow(2).mean().sqrt()),
+                                   logit_rms=float(ref32.detach().pow(2).mean().sqrt()))
+        arrays["logits/" + tag] = logits.detach().float().numpy().copy()
+        arrays["logits_fp32/" + tag] = ref32.detach().numpy().copy()
+    save("bf16_autocast", meta, arrays)
+
+
 def lr_fixture():
     """lr sequences of the reference schedulers (utils/lr_schedule.py) as the EA fine-tune
     and main_train.py drive them: construct, step(epoch=-1), then step() per batch."""
@@ -395,7 +430,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["samplers", "fixed", "autoctr", "xlarge", "kdd", "steps", "lr", "finetune", "tokenizer", "transform", "avazu",
-                             "zeros"]
+                             "zeros", "bf16"]
     if "samplers" in which:
         sampler_fixture()
     if "fixed" in which:
@@ -408,6 +443,8 @@ if __name__ == "__main__":
         supernet_fixture("supernet_xlarge_kdd", "kdd", "xlarge", nchoices=2)
     if "avazu" in which:
         supernet_fixture("supernet_xlarge_avazu", "avazu", "xlarge", nchoices=1)
+    if "bf16" in which:
+        bf16_fixture()
     if "zeros" in which:        # the xlarge-zeros search space (supernet.py:151-168): Zeros2D / Zeros3D nodes
         supernet_fixture("supernet_zeros_criteo", "criteo", "xlarge-zeros", nchoices=4)
     if "steps" in which:
