@@ -596,6 +596,21 @@ def measure_ea(env, cfg, n_per_rank=8, n_batches=EA_BATCHES):
     out["h2d"] = sum(a.numel() * a.element_size() for b in pinned for a in b)
     out["n_records"] = len(recs)
     out["mean_auc"] = float(np.mean([r["test_auroc"] for r in recs]))
+    # what the regularized EA actually scores per generation (searcher.py:167-295): the mutated children of one parent,
+    # which differ from it in one field of one block -- the batched path shares the blocks they have in common
+    from nasrec_b200.search import Tokenizer
+    tok = Tokenizer(7, ops_config_lib["xlarge"])
+    np.random.seed(4321 + rank)
+    parent = tok.generate_random_choice()
+    gen = [tok.mutate_spec(parent) for _ in range(n_per_rank)]
+    ev.multi_stats = [0, 0]
+    env.barrier()
+    e0.record()
+    ev.score(gen, batches)
+    e1.record()
+    env.barrier()
+    out["generation_value"] = n_cand / (env.max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+    out["generation_blocks_computed_reused"] = list(ev.multi_stats)
     del m, ev, batches, dbatches
     torch.cuda.empty_cache()
     return out
@@ -699,7 +714,11 @@ def run_ours(args):
                                "the 171 M-parameter supernet exceed L2", "parallelism": "candidates sharded x%d" % world},
                     "gpu_launches": _lib.LIB.launches,
                     "e2e": {"value": r["e2e"], "unit": cfg["unit"], "h2d_bytes_per_step": r["h2d"] // max(1, r["n_cand"] // world),
-                            "d2h_bytes_per_step": 24, "mean_auc": r["mean_auc"]}}
+                            "d2h_bytes_per_step": 24, "mean_auc": r["mean_auc"]},
+                    "extra": {"ea_generation_subnets_per_sec": r["generation_value"],
+                              "ea_generation_blocks_computed_reused": r["generation_blocks_computed_reused"],
+                              "note": "generation = the mutated children of one parent (what the regularized EA scores "
+                                      "per generation); blocks shared between candidates are computed once"}}
             if world == 1 and not args.no_cpu:
                 base, _ = reference_ea(cfg)
                 if base is not None:
@@ -734,6 +753,8 @@ def run_ours(args):
             extra["ea_subnets_per_sec_e2e"] = ea["e2e"]
             extra["ea_candidates"] = ea["n_cand"]
             extra["ea_mean_auc"] = ea["mean_auc"]
+            extra["ea_generation_subnets_per_sec"] = ea["generation_value"]
+            extra["ea_generation_blocks_computed_reused"] = ea["generation_blocks_computed_reused"]
             if world == 1:
                 for name, tables in (("criteo_full_best", "capped"), ("criteo_full_best", "full"), ("kdd_xlarge", "capped")):
                     a2 = argparse.Namespace(config=name, tables=tables)

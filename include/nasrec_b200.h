@@ -353,6 +353,14 @@ int nasrec_net_set_seal_callback(void* net, nasrec_seal_cb_t cb);
 /* logits [B] for one subnet; emb_rows (optional) = [B,F,16] rows gathered once and shared by many candidates. */
 int nasrec_net_forward(void* net, const int* choice, const float* int_x, const int64_t* cat_x, const float* emb_rows,
                        int B, float* logits, void* stream);
+/* Batched multi-subnet evaluation (searcher_utils.py:57-104, eval_subnet_from_supernet.py:182-198): logits [n_cand, B] of
+ * n_cand subnets (choices: n_cand x num_blocks x 49 ints, layout as above) on ONE batch against the resident weights.
+ * A block's output depends only on its own choice and on the blocks it reads, so a block that several candidates agree
+ * on (together with everything upstream of it) is computed once and shared -- always the stem, and about half of the
+ * blocks for the children of one EA generation, which differ from their parent in one field of one block.  Results are
+ * bit-identical to n_cand nasrec_net_forward calls.  stats (host, may be NULL): {blocks computed, blocks reused}. */
+int nasrec_multi_subnet_eval(void* net, const int* choices, int n_cand, const float* int_x, const int64_t* cat_x,
+                             const float* emb_rows, int B, float* logits, int* stats, void* stream);
 /* forward + BCEWithLogits(mean)*grad_scale + backward.  Afterwards the dense parameter gradients lie back to
  * back in the pgrad arena (nasrec_net_grad_bucket: what data-parallel training all-reduces in place) and the
  * raw embedding gradient [B,F,16] is exposed by nasrec_net_sparse_raw. */

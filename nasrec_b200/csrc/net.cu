@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <deque>
 #include <functional>
+#include <map>
 #include <new>
 #include <stdexcept>
 #include <vector>
@@ -849,6 +850,99 @@ Var* forward(Net& n, const int* choice, const float* int_x, const int64_t* cat_x
     return linear_ln(n, segs, B, a);
 }
 
+// ------------------------------------------------------------------------------------------- many candidates, shared work
+// One-shot scoring evaluates many subnets against the SAME weights on the SAME batch (searcher_utils.py:57-104,
+// eval_subnet_from_supernet.py:182-198).  A block's output is a pure function of its own choice and of the outputs of the
+// sources it reads, so candidates that agree on a block and on everything upstream of it share that block: it is computed
+// once and its output tensors are handed to every candidate that needs them (the children of one EA generation differ
+// from their parent in one field of one block, so on average half of their blocks are shared; every candidate shares the
+// stem).  Keys are exact (the full dependency description, no hashing); shared tensors are read-only.
+struct MultiStats { int computed = 0, reused = 0; };
+
+std::vector<long long> block_key(Net& n, int i, const BlockChoice& c, const std::vector<int>& src_id) {
+    std::vector<long long> k{(long long)i, c.d, c.s, c.dsi, c.dfm, -1};
+    bool fc_dp = false, bin = false, sp = false;
+    for (int a : c.active) {
+        k.push_back(a);
+        const int t = n.blocks[i].nodes[a].type;
+        if (t == N_FC || t == N_DP) fc_dp = true;
+        if (is_dense_binary(t)) bin = true;
+        if (t == N_TRANS || t == N_EFC || t == N_DP) sp = true;
+    }
+    auto add = [&](const std::vector<int>& idx, long long tag, bool used) {
+        k.push_back(-2 - tag);
+        if (used) for (int j : idx) { k.push_back(j); k.push_back(src_id[j]); }
+    };
+    add(c.dense, 0, fc_dp); add(c.left, 1, bin); add(c.right, 2, bin); add(c.sparse, 3, sp);
+    return k;
+}
+
+void forward_multi(Net& n, const int* choices, int n_cand, const float* int_x, const int64_t* cat_x, const float* emb_rows,
+                   int B, float* logits, MultiStats& st) {
+    n.tape_on = false;
+    n.B = B;
+    n.cat_x = cat_x;
+    const int nd_ld = (n.nd + 3) & ~3;
+    Var* x0 = n.var((int64_t)B * nd_ld, nd_ld != n.nd);
+    if (nd_ld != n.nd) ck(nasrec_act_fwd(int_x, n.nd, B, n.nd, 0, x0->t, nd_ld, 0, n.st));
+    else x0->t = const_cast<float*>(int_x);
+    Var* sp0 = n.var((int64_t)B * n.F * E, emb_rows == nullptr);
+    if (emb_rows) sp0->t = const_cast<float*>(emb_rows);
+    else ck(nasrec_emb_gather_fwd(n.d_tables, n.d_rows, cat_x, sp0->t, B, n.F, n.d_err, n.st));
+    struct Entry { DSrc d; SSrc s; };
+    std::map<std::vector<long long>, int> ids;        // dependency description -> id of the computed block output
+    std::vector<Entry> outs;
+    const BlockDesc& last = n.blocks[n.num_blocks - 1];
+    for (int c = 0; c < n_cand; ++c) {
+        std::vector<BlockChoice> ch;
+        for (int i = 0; i < n.num_blocks; ++i) ch.push_back(decode(choices + ((size_t)c * n.num_blocks + i) * CHOICE_STRIDE));
+        for (auto& bc : ch) for (int a : bc.active) if (a < 0 || a >= 8) throw CallFailed(NASREC_EINVAL);
+        std::vector<DSrc> dsrc{DSrc{x0, n.nd, nd_ld}};
+        std::vector<SSrc> ssrc{SSrc{sp0, n.F, 0}};
+        std::vector<bool> have{true};
+        std::vector<int> src_id{-1};                  // the stem is the same tensor for every candidate
+        const std::vector<bool> need = liveness(n, ch);
+        for (int i = 0; i < n.num_blocks; ++i) {
+            if (!need[i + 1]) {
+                dsrc.push_back(DSrc{nullptr, 0, 0});
+                ssrc.push_back(SSrc{nullptr, 0, 0});
+                have.push_back(false);
+                src_id.push_back(-3);
+                continue;
+            }
+            const std::vector<long long> key = block_key(n, i, ch[i], src_id);
+            auto it = ids.find(key);
+            if (it == ids.end()) {
+                DSrc d;
+                SSrc s;
+                run_block(n, i, ch[i], dsrc, ssrc, have, B, d, s);
+                // the block's two output tensors are its first two arena allocations: everything behind them was scratch
+                char* end = std::max((char*)(d.v->t + d.v->n), (char*)(s.v->t + s.v->n));
+                n.act.off = (((size_t)(end - n.act.base)) + 255) & ~(size_t)255;
+                outs.push_back(Entry{d, s});
+                it = ids.emplace(key, (int)outs.size() - 1).first;
+                ++st.computed;
+            } else {
+                ++st.reused;
+            }
+            dsrc.push_back(outs[it->second].d);
+            ssrc.push_back(outs[it->second].s);
+            have.push_back(true);
+            src_id.push_back(it->second);
+        }
+        const size_t mark = n.act.off;
+        const DSrc& dl = dsrc.back();
+        const SSrc& sl = ssrc.back();
+        const int64_t bs = (int64_t)(sl.s + sl.g) * E;
+        Segs segs{Seg{dl.v, 0, dl.ld, dl.w, 0}, Seg{sl.v, 0, bs, (int64_t)sl.s * E, last.maxd}};
+        if (sl.g) segs.push_back(Seg{sl.v, (int64_t)sl.s * E, bs, (int64_t)sl.g * E, last.maxd + (int64_t)last.maxs * E});
+        LinArgs a; a.W = n.final_w; a.b = n.final_b; a.d_out = 1;
+        Var* out = linear_ln(n, segs, B, a);
+        ck((int)cudaMemcpyAsync(logits + (size_t)c * B, out->t, (size_t)B * 4, cudaMemcpyDeviceToDevice, n.st));
+        n.act.off = mark;
+    }
+}
+
 template <class F>
 int guarded(F&& f) {
     int rc = 0;
@@ -961,6 +1055,22 @@ int nasrec_net_forward(void* net, const int* choice, const float* int_x, const i
         Var* out = forward(*n, choice, int_x, cat_x, emb_rows, B, false);
         ck((int)cudaMemcpyAsync(logits, out->t, (size_t)B * 4, cudaMemcpyDeviceToDevice, n->st));
     });
+}
+
+// Logits [n_cand, B] of n_cand subnets on ONE batch against the resident weights; blocks shared between candidates are
+// computed once (see forward_multi).  stats (optional, host): {blocks computed, blocks reused}.
+int nasrec_multi_subnet_eval(void* net, const int* choices, int n_cand, const float* int_x, const int64_t* cat_x,
+                             const float* emb_rows, int B, float* logits, int* stats, void* stream) {
+    Net* n = (Net*)net;
+    CHECK_ARG(n && choices && n_cand > 0 && int_x && (cat_x || emb_rows) && logits && B > 0);
+    MultiStats ms;
+    const int rc = guarded([&] {
+        reset_step(*n, as_stream(stream));
+        n->step_valid = false;
+        forward_multi(*n, choices, n_cand, int_x, cat_x, emb_rows, B, logits, ms);
+    });
+    if (stats) { stats[0] = ms.computed; stats[1] = ms.reused; }
+    return rc;
 }
 
 // Forward + BCE + backward.  Afterwards the parameter gradients sit back to back in the pgrad arena

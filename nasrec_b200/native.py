@@ -37,6 +37,7 @@ _PROTOS = {
     "nasrec_net_set_reserve": ([_vp, _i], _i),
     "nasrec_net_set_seal_callback": ([_vp, _vp], _i),
     "nasrec_net_forward": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp], _i),
+    "nasrec_multi_subnet_eval": ([_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
     "nasrec_net_forward_backward": ([_vp, _vp, _vp, _vp, _vp, _i, _fl, _vp, _vp, _vp], _i),
     "nasrec_net_grad_bucket": ([_vp, _vp, _vp], _i),
     "nasrec_net_sparse_raw": ([_vp, _vp, _vp], _i),
@@ -314,6 +315,23 @@ class NativeNet:
         self._retrying("nasrec_net_forward", lambda: _fn("nasrec_net_forward")(
             self.handle, choice.ctypes.data, int_x.data_ptr(), cat_x.data_ptr() if cat_x is not None else None,
             emb_rows.data_ptr() if emb_rows is not None else None, B, logits.data_ptr(), st))
+        return logits
+
+    def forward_multi(self, choices: Sequence[np.ndarray], int_x: torch.Tensor, cat_x: Optional[torch.Tensor],
+                      emb_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Logits [C, B] of C candidates on one batch (nasrec_multi_subnet_eval): blocks that candidates share -- same
+        choice, same upstream -- are computed once.  ``self.last_multi_stats`` = (blocks computed, blocks reused)."""
+        B = int_x.shape[0]
+        C_ = len(choices)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32).reshape(-1) for c in choices]))
+        logits = torch.empty(C_, B, dtype=torch.float32, device=self.dev)
+        stats = (C.c_int * 2)()
+        st = _lib.stream_ptr()
+        _lib.LIB.ensure_workspace()
+        self._retrying("nasrec_multi_subnet_eval", lambda: _fn("nasrec_multi_subnet_eval")(
+            self.handle, flat.ctypes.data, C_, int_x.data_ptr(), cat_x.data_ptr() if cat_x is not None else None,
+            emb_rows.data_ptr() if emb_rows is not None else None, B, logits.data_ptr(), C.cast(stats, C.c_void_p), st))
+        self.last_multi_stats = (int(stats[0]), int(stats[1]))
         return logits
 
     def forward_backward(self, choice: np.ndarray, int_x, cat_x, y, grad_scale: float = 1.0):

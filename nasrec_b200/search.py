@@ -154,10 +154,16 @@ def binary_metrics_device(logits: torch.Tensor, y: torch.Tensor) -> Tuple[float,
 class SubnetEvaluator:
     """Scores many candidates against shared, resident supernet weights."""
 
-    def __init__(self, model: SuperNet, use_native: bool = True):
+    def __init__(self, model: SuperNet, use_native: bool = True, group: int = 16):
         assert not model._fixed, "one-shot scoring needs the weight-sharing supernet"
         self.model = model
+        # Gathered embedding rows of the evaluation batches, shared by the candidates of ONE score() call: the cache is
+        # keyed by the batch's device pointer, so it must not outlive the call (the allocator may hand the address to
+        # another batch, the caller may refill a staging buffer, training may move the tables in between).
         self._emb_cache: Dict[int, torch.Tensor] = {}
+        self._in_score = False
+        self.group = group                      # candidates per nasrec_multi_subnet_eval call
+        self.multi_stats = [0, 0]               # blocks computed / reused by the batched path so far
         self.use_native = use_native            # C++ executor (nasrec_b200/native.py) when the model allows it
         self._net = None
         self._native_checked = False
@@ -176,15 +182,19 @@ class SubnetEvaluator:
         if m._needs_materialize():
             m.materialize(int_x.shape[1])
         net = self._native()
-        if net is not None:
-            from .native import NativeNet
-            net.refresh()
-            rows = self._gathered(cat_x) if not any(e.weight.requires_grad for e in m._embedding) else None
-            return net.forward(NativeNet.encode_choice(choice["macro"], choice["micro"]), int_x.contiguous(),
-                               cat_x if rows is None else None, emb_rows=rows)
-        run = Run(Tape(False), emb_cache=self._emb_cache)
-        out = m._run_network(run, Var(int_x), cat_x, choice["macro"], choice["micro"])
-        return out.t
+        try:
+            if net is not None:
+                from .native import NativeNet
+                net.refresh()
+                rows = self._gathered(cat_x) if not any(e.weight.requires_grad for e in m._embedding) else None
+                return net.forward(NativeNet.encode_choice(choice["macro"], choice["micro"]), int_x.contiguous(),
+                                   cat_x if rows is None else None, emb_rows=rows)
+            run = Run(Tape(False), emb_cache=self._emb_cache)
+            out = m._run_network(run, Var(int_x), cat_x, choice["macro"], choice["micro"])
+            return out.t
+        finally:
+            if not self._in_score:
+                self._emb_cache.clear()
 
     @torch.no_grad()
     def _gathered(self, cat_x: torch.Tensor) -> torch.Tensor:
@@ -206,18 +216,50 @@ class SubnetEvaluator:
         the others (all batches must then share one shape), removing the per-launch host cost;
         capture + instantiation cost ~70 ms per candidate, so it only pays for many small batches
         (at 8192-sample batches scoring is device-bound and eager is faster)."""
+        self._in_score = True
+        try:
+            return self._score(choices, batches, use_cuda_graph)
+        finally:
+            self._in_score = False
+            self._emb_cache.clear()
+
+    def _score(self, choices, batches, use_cuda_graph):
         ys = torch.cat([b[2].reshape(-1) for b in batches])
         same_shape = all(b[0].shape == batches[0][0].shape for b in batches)
         res = []
+        m = self.model
+        if m._needs_materialize():
+            m.materialize(batches[0][0].shape[1])
+        net = self._native()
+        frozen = not any(e.weight.requires_grad for e in m._embedding)
+        if net is not None and not use_cuda_graph and frozen:
+            # batched multi-subnet path (nasrec_multi_subnet_eval): `group` candidates per call and per batch; blocks the
+            # candidates share (same choice, same upstream) are computed once
+            from .native import NativeNet
+            net.refresh()
+            enc = [NativeNet.encode_choice(ch["macro"], ch["micro"]) for ch in choices]
+            total = ys.numel()
+            for g0 in range(0, len(choices), self.group):
+                grp = enc[g0:g0 + self.group]
+                outs = torch.empty(len(grp), total, dtype=torch.float32, device=ys.device)
+                off = 0
+                for b in batches:
+                    cat = b[1] if b[1].dtype == torch.int64 else b[1].long()
+                    lg = net.forward_multi(grp, b[0].contiguous(), None, emb_rows=self._gathered(cat.contiguous()))
+                    self.multi_stats[0] += net.last_multi_stats[0]
+                    self.multi_stats[1] += net.last_multi_stats[1]
+                    outs[:, off:off + lg.shape[1]] = lg
+                    off += lg.shape[1]
+                for k in range(len(grp)):
+                    acc, auc, loss = binary_metrics_device(outs[k], ys)
+                    res.append({"test_acc": acc, "test_auroc": auc, "test_loss": loss})
+            return res
         if not (use_cuda_graph and same_shape and len(batches) > 2):
             for ch in choices:
                 outs = [self.logits(ch, b[0], b[1]).reshape(-1) for b in batches]
                 acc, auc, loss = binary_metrics_device(torch.cat(outs), ys)
                 res.append({"test_acc": acc, "test_auroc": auc, "test_loss": loss})
             return res
-        m = self.model
-        if m._needs_materialize():
-            m.materialize(batches[0][0].shape[1])
         rows = [self._gathered(b[1]) for b in batches]          # shared across candidates
         B = batches[0][0].shape[0]
         s_int = batches[0][0].clone()

@@ -110,3 +110,63 @@ def test_reference_training_loop_drop_in_matches_golden():
     assert abs(logs["test_loss"][0] - c["test_loss"]) < 1e-5
     assert np.abs(m._final.weight.detach().cpu().numpy() - A["cand1/final_weight"]).max() < 1e-5
     assert 0.0 <= logs["test_AUROC"][0] <= 1.0 and 0.0 <= logs["test_Accuracy"][0] <= 1.0
+
+
+def _xlarge_resident(seed=31):
+    meta, _ = load_golden("supernet_xlarge_criteo")
+    cfg, ne, nd = meta["cfg"], meta["num_embeddings"], meta["nd"]
+    m = SuperNet(num_blocks=7, ops_config=ops_config_lib["xlarge"], use_layernorm=True, num_embeddings=ne,
+                 sparse_input_size=len(ne), path_sampling_strategy="full-path").to("cuda")
+    m.materialize(nd)
+    sd = orc.fill_state_dict({k: tuple(v) for k, v in meta["shapes"].items()}, seed)
+    m.load_state_dict(sd, strict=True)
+    m.requires_grad_(False)
+    return m, sd, cfg, ne, nd
+
+
+def test_multi_subnet_eval_matches_oracle_per_candidate():
+    """nasrec_multi_subnet_eval (searcher_utils.py:57-104, eval_subnet_from_supernet.py:182-198): 16 NASRec-Full candidates
+    x 4 evaluation batches in batched calls == the oracle's logits candidate by candidate (1e-5), bit-identical to the
+    one-candidate-at-a-time executor path, and the same log-loss / AUC / accuracy records."""
+    from nasrec_b200.native import NativeNet
+    from nasrec_b200.search import generate_random_choice
+    m, sd, cfg, ne, nd = _xlarge_resident()
+    np.random.seed(5)
+    cands = [generate_random_choice(7, ops_config_lib["xlarge"]) for _ in range(16)]
+    host = [orc.synth_batch(96, nd, ne, seed=700 + b, zipf=True) for b in range(4)]
+    dev = [tuple(t.cuda() for t in b) for b in host]
+    ev = SubnetEvaluator(m, group=16)
+    recs = ev.score(cands, dev)
+    assert ev.multi_stats[0] > 0, "the batched path was not taken"
+    net = ev._native()
+    ys = torch.cat([b[2].reshape(-1) for b in host]).numpy()
+    for ci, ch in enumerate(cands):
+        z_ref = torch.cat([orc.supernet_forward(sd, cfg, ch, b[0], b[1]).reshape(-1) for b in host]).detach().numpy()
+        enc = NativeNet.encode_choice(ch["macro"], ch["micro"])
+        z_one = torch.cat([net.forward(enc, b[0].contiguous(), b[1].contiguous()).reshape(-1) for b in dev])
+        z_multi = torch.cat([net.forward_multi([enc], b[0].contiguous(), b[1].contiguous()).reshape(-1) for b in dev])
+        assert torch.equal(z_one, z_multi), ci
+        z = z_one.cpu().numpy()
+        assert np.abs(z - z_ref).max() <= 1e-5 * max(1.0, np.abs(z_ref).max()), ci
+        acc, auc, loss = orc.binary_metrics(z_ref, ys)
+        assert abs(recs[ci]["test_loss"] - loss) < 1e-5 and abs(recs[ci]["test_auroc"] - auc) < 1e-6
+        assert abs(recs[ci]["test_acc"] - acc) < 1e-6
+
+
+def test_multi_subnet_eval_shares_blocks_within_an_ea_generation():
+    """The children of one generation differ from their parent in one field of one block (tokenizer.py:192-265): the
+    batched path computes the blocks they share once, and every child's logits stay bit-identical to its own forward."""
+    from nasrec_b200.native import NativeNet
+    m, sd, cfg, ne, nd = _xlarge_resident(seed=32)
+    tok = Tokenizer(7, ops_config_lib["xlarge"])
+    np.random.seed(9)
+    parent = tok.generate_random_choice()
+    children = [tok.mutate_spec(parent) for _ in range(8)]
+    int_x, cat_x, _ = (t.cuda() for t in orc.synth_batch(130, nd, ne, seed=801, zipf=True))
+    net = NativeNet(m, state_of=None, pgrad_bytes=1 << 20)
+    encs = [NativeNet.encode_choice(c["macro"], c["micro"]) for c in [parent] + children]
+    z = net.forward_multi(encs, int_x.contiguous(), cat_x.contiguous())
+    computed, reused = net.last_multi_stats
+    assert reused > 0 and computed < 9 * 7, (computed, reused)
+    for k, e in enumerate(encs):
+        assert torch.equal(z[k], net.forward(e, int_x.contiguous(), cat_x.contiguous()).reshape(-1)), k
