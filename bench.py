@@ -662,8 +662,11 @@ def measure_hbm_kernels(env, B=8192):
                                      B, F, err.data_ptr()))
         by = B * F * (8 + 64 + 64)
         out["emb_gather_%s_B%d" % (tag, B)] = {"us": t * 1e6, "GBps": by / t / 1e9, "frac_of_measured_hbm": by / t / 1e9 / peak}
-        t = timeit(lambda: _lib.call("nasrec_emb_grad_sort_reduce", cat.data_ptr(), gout.data_ptr(), B, F, uniq.data_ptr(),
-                                     nuniq.data_ptr(), rg.data_ptr(), sumsq.data_ptr(), scratch.data_ptr()))
+        nb = _lib.query("nasrec_emb_grad_sort_reduce_big_ws_bytes", B, F)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        t = timeit(lambda: _lib.call("nasrec_emb_grad_sort_reduce_big", cat.data_ptr(), rows.data_ptr(), err.data_ptr(),
+                                     gout.data_ptr(), B, F, uniq.data_ptr(), nuniq.data_ptr(), rg.data_ptr(), sumsq.data_ptr(),
+                                     ws.data_ptr(), nb))
         torch.cuda.synchronize()
         u = int(nuniq.sum().item())
         by = B * F * (8 + 64) + u * (64 + 8)

@@ -116,7 +116,8 @@ int nasrec_emb_gather_fwd(const float* const* tables, const int64_t* num_rows, c
  * Deterministic: per table, (row, sample) keys are sorted; duplicate rows are summed in
  * ascending sample order.  Outputs per table f: uniq[f, 0..nuniq[f]) ascending row ids,
  * row_grad[f, u, :] the summed gradient rows, sumsq[f] = sum of squares of row_grad
- * (for the global clip norm).  seg_scratch: int32 [F, B+1].  B <= 16384. */
+ * (for the global clip norm).  seg_scratch: int32 [F, B+1].  One CTA per table, shared-memory sort: B <= 16384 and
+ * best for B <= 2048; larger batches: nasrec_emb_grad_sort_reduce_big. */
 int nasrec_emb_grad_sort_reduce(const int64_t* idx, const float* gout, int B, int F,
                                 int64_t* uniq, int* nuniq, float* row_grad, float* sumsq,
                                 int* seg_scratch, void* stream);
@@ -126,6 +127,15 @@ int nasrec_emb_grad_sort_reduce_checked(const int64_t* idx, const int64_t* num_r
                                         const float* gout, int B, int F, int64_t* uniq, int* nuniq,
                                         float* row_grad, float* sumsq, int* seg_scratch, void* stream);
 
+/* The same reduction for large batches (the data-parallel global batch, 16 K-sample KDD batches): multi-CTA, any B
+ * (B * F < 2^31, F <= 31, rows per table < 2^27) -- one stable device radix sort of (table, row, sample) keys, head
+ * flags + scan, 16 lanes per unique row (a whole CTA for rows with more than 256 duplicates, partial sums combined in a
+ * fixed order), per-table sums of squares.  Deterministic; duplicate rows are summed in ascending sample order up to 256
+ * duplicates, in 16 strided ascending runs beyond.  ws: nasrec_emb_grad_sort_reduce_big_ws_bytes(B, F) bytes. */
+int64_t nasrec_emb_grad_sort_reduce_big_ws_bytes(int B, int F);
+int nasrec_emb_grad_sort_reduce_big(const int64_t* idx, const int64_t* num_rows, int* err_flag, const float* gout,
+                                    int B, int F, int64_t* uniq, int* nuniq, float* row_grad, float* sumsq, void* ws,
+                                    int64_t ws_bytes, void* stream);
 /* Scatter the reduced rows into dense zero-initialised [N_f,16] gradients (what
  * nn.Embedding.weight.grad holds in the reference). */
 int nasrec_emb_grad_to_dense(const int64_t* uniq, const int* nuniq, const float* row_grad,

@@ -28,6 +28,7 @@ _SIGS = {
     "nasrec_emb_gather_fwd": ([_f, _f, _f, _f, _i, _i, _f, _f], 1),
     "nasrec_emb_grad_sort_reduce": ([_f, _f, _i, _i, _f, _f, _f, _f, _f, _f], 1),
     "nasrec_emb_grad_sort_reduce_checked": ([_f, _f, _f, _f, _i, _i, _f, _f, _f, _f, _f, _f], 1),
+    "nasrec_emb_grad_sort_reduce_big": ([_f, _f, _f, _f, _i, _i, _f, _f, _f, _f, _f, _l, _f], 10),
     "nasrec_emb_grad_to_dense": ([_f, _f, _f, _f, _i, _i, _f], 1),
     "nasrec_emb_rowwise_adagrad": ([_f, _f, _f, _f, _f, _i, _i, _fl, _fl, _f, _f], 1),
     "nasrec_seg_linear_fwd": ([_f, _i, _f, _l, _i, _i, _f, _f, _l, _i, _f], 1),
@@ -71,6 +72,7 @@ _SIGS_I64 = {
     "nasrec_sproj_wgrad_ws_floats": [_i, _l, _i],
     "nasrec_attn_bwd_ws_floats": [_i],
     "nasrec_sumsq_ws_floats": [_f, _i],
+    "nasrec_emb_grad_sort_reduce_big_ws_bytes": [_i, _i],
     "nasrec_binary_metrics_ws_bytes": [_l],
 }
 _SIGS_I64["nasrec_tensor_map_stats"] = [_i]

@@ -23,6 +23,7 @@ namespace {
 constexpr int E = NASREC_EMB_DIM;
 constexpr int GROUPS = 8;            // DS_INTERACT_NUM_SPLITS (supernet.py:49)
 constexpr float LN_EPS = 1e-5f;
+constexpr int BIG_REDUCE_ROWS = 1024;   // above this many ids per table the multi-CTA sorted-row reduction takes over
 
 struct OutOfArena : std::runtime_error { OutOfArena() : std::runtime_error("arena") {} };
 struct CallFailed : std::runtime_error { int rc; explicit CallFailed(int r) : std::runtime_error("call"), rc(r) {} };
@@ -99,6 +100,7 @@ struct Net {
     int res_rows = 0;
     int64_t* res_uniq = nullptr; int* res_nuniq = nullptr; float* res_row_grad = nullptr; float* res_sumsq = nullptr; int* res_scratch = nullptr;
     float* res_partial = nullptr; int64_t res_partial_n = 0;
+    void* res_big_ws = nullptr; int64_t res_big_bytes = 0;     // workspace of the multi-CTA reduction (large batches)
     bool step_valid = false;                  // false after nasrec_net_set_arenas: gradients of an earlier step are gone
     // data-parallel overlap: called during backward whenever a block's parameter gradients are final, with the
     // byte range of the gradient bucket that was sealed (the caller all-reduces it while backward continues)
@@ -1091,6 +1093,12 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
             n->res_row_grad = n->act.alloc((int64_t)F * rows * E);
             n->res_sumsq = n->act.alloc(F);
             n->res_scratch = (int*)n->act.alloc_bytes((size_t)F * (rows + 1) * 4);
+            n->res_big_ws = nullptr;
+            n->res_big_bytes = 0;
+            if (rows > BIG_REDUCE_ROWS && F <= 31) {
+                n->res_big_bytes = nasrec_emb_grad_sort_reduce_big_ws_bytes(rows, F);
+                n->res_big_ws = n->act.alloc_bytes((size_t)n->res_big_bytes);
+            }
             n->res_rows = rows;
             int64_t chunks = 0;
             for (const Par& p : n->par) chunks += (p.n + 16383) / 16384;      // >= nasrec_sumsq_ws_floats of any subset
@@ -1166,8 +1174,18 @@ int nasrec_net_sparse_reduce(void* net, const int64_t* cat_all, const float* gou
             n->sumsq = n->act.alloc(F);
             scratch = (int*)n->act.alloc_bytes((size_t)F * (Bs + 1) * 4);
         }
-        ck(nasrec_emb_grad_sort_reduce_checked(cat, n->d_rows, n->d_err, go, Bs, F, n->uniq, n->nuniq, n->row_grad, n->sumsq, scratch,
-                                               as_stream(stream)));
+        if (Bs > BIG_REDUCE_ROWS && F <= 31) {
+            // large (all-gathered / KDD) batches: multi-CTA radix-sort reduction
+            void* ws = n->res_big_ws;
+            int64_t wb = n->res_big_bytes;
+            const int64_t need = nasrec_emb_grad_sort_reduce_big_ws_bytes(Bs, F);
+            if (!ws || wb < need || Bs > n->res_rows) { ws = n->act.alloc_bytes((size_t)need); wb = need; }
+            ck(nasrec_emb_grad_sort_reduce_big(cat, n->d_rows, n->d_err, go, Bs, F, n->uniq, n->nuniq, n->row_grad, n->sumsq, ws, wb,
+                                               as_stream(stream)), 10);
+        } else {
+            ck(nasrec_emb_grad_sort_reduce_checked(cat, n->d_rows, n->d_err, go, Bs, F, n->uniq, n->nuniq, n->row_grad, n->sumsq,
+                                                   scratch, as_stream(stream)));
+        }
         n->sB = Bs;
         n->have_sparse = true;
     });

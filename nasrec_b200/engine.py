@@ -624,7 +624,7 @@ class EmbeddingTables:
 
 class SparseEmbGrad:
     """Result of the deterministic sorted-row reduction for one step."""
-    __slots__ = ("uniq", "nuniq", "row_grad", "sumsq", "B", "F")
+    __slots__ = ("uniq", "nuniq", "row_grad", "sumsq", "B", "F", "ws")
 
 
 class SparseSink(list):
@@ -646,7 +646,17 @@ def reduce_sparse(cat_x: torch.Tensor, gout: torch.Tensor, tables: Optional["Emb
     sg.row_grad = torch.empty(F, B, E, dtype=torch.float32, device=dev)
     sg.sumsq = torch.empty(F, dtype=torch.float32, device=dev)
     scratch = torch.empty(F, B + 1, dtype=torch.int32, device=dev)
-    if tables is not None and tables.rows is not None:
+    if B > 1024 and F <= 31:
+        # large batches (data-parallel global batch, KDD): multi-CTA radix-sort reduction (csrc/emb_big.cu)
+        from ._lib import query
+        nb = query("nasrec_emb_grad_sort_reduce_big_ws_bytes", B, F)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        has = tables is not None and tables.rows is not None
+        call("nasrec_emb_grad_sort_reduce_big", cat_x.data_ptr(), _p_i(tables.rows) if has else None,
+             _p_i(tables.err) if has else None, _p(gout), B, F, sg.uniq.data_ptr(), sg.nuniq.data_ptr(), _p(sg.row_grad),
+             _p(sg.sumsq), ws.data_ptr(), nb)
+        sg.ws = ws
+    elif tables is not None and tables.rows is not None:
         call("nasrec_emb_grad_sort_reduce_checked", cat_x.data_ptr(), _p_i(tables.rows), _p_i(tables.err), _p(gout), B, F,
              sg.uniq.data_ptr(), sg.nuniq.data_ptr(), _p(sg.row_grad), _p(sg.sumsq), scratch.data_ptr())
     else:
