@@ -22,7 +22,7 @@ def make():
     return m
 
 B = 256
-pools = [bench.synth_pool(4, B, 13, ne, seed=100 + r) for r in range(world)]
+pools = [bench.synth_pool(4, B, 13, ne, 100 + r) for r in range(world)]
 kind = sys.argv[1] if len(sys.argv) > 1 else "native"      # python | native | native-noverlap
 m = make()
 tr = DataParallelTrainer(m, lr=0.12) if kind == "python" else NativeDataParallelTrainer(m, lr=0.12)
@@ -49,6 +49,9 @@ if rank == 0:
     for (n, p), q in zip(m.named_parameters(), m1.parameters()):
         d = float((p - q).abs().max() / (q.abs().max() + 1e-12))
         worst = max(worst, d)
+    import json
+    print("DPCHECK " + json.dumps({"kind": kind, "native": getattr(getattr(tr, "_nt", None), "net", None) is not None,
+                                   "replicas_identical": bool(same), "max_rel_weight_diff": worst, "world": world, "B": B}), flush=True)
     print(kind, "| native path used:", getattr(getattr(tr, "_nt", None), "net", None) is not None,
           "| replicas bit-identical:", same, "| dp(2x%d) vs single(%d) max rel weight diff after 4 steps: %.2e" % (B, world * B, worst), flush=True)
 dist.destroy_process_group()
