@@ -93,6 +93,37 @@ static inline long long nasrec_now_ns() {
     return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
 }
 
+// cluster_z > 1: the grid is launched as thread-block clusters of (1, 1, cluster_z) CTAs (grid.z must be a multiple).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t nasrec_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                                int cluster_z, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cluster_z > 1) {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 1;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = (unsigned)cluster_z;
+        cfg.numAttrs = 2;
+    }
+    if (g_nasrec_host_prof) {
+        const long long t0 = nasrec_now_ns();
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+        g_nasrec_launch_ns += nasrec_now_ns() - t0;
+        ++g_nasrec_launch_count;
+        return e;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t nasrec_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                         Args&&... args) {
@@ -118,6 +149,10 @@ static inline cudaError_t nasrec_launch(void (*kernel)(KArgs...), dim3 grid, dim
 
 // library scratch attached with nasrec_set_workspace (gemm.cu); stream-ordered reuse by every kernel family
 void nasrec_internal_workspace(float** ws, long long* nfloats);
+// per-target accumulate flags for the NEXT nasrec_seg_linear_dgrad / nasrec_sproj_dgrad call (overrides its scalar
+// `accumulate`; cleared by that call): lets the op-level backward entry points serve fresh and accumulated gradient
+// targets with one launch
+void nasrec_internal_set_dgrad_flags(const int* flags);
 // optional second stream on which the op-level backward entry points issue weight-gradient work
 cudaStream_t nasrec_internal_side_stream();
 void nasrec_internal_set_side_stream(cudaStream_t s);

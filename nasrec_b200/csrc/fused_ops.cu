@@ -4,17 +4,19 @@
 #include "common.cuh"
 
 namespace {
-struct SegSplit {
-    nasrec_seg_t fresh[NASREC_MAX_SEGS];
-    nasrec_seg_t acc[NASREC_MAX_SEGS];
-    int nf = 0, na = 0;
+struct Targets {
+    nasrec_seg_t seg[NASREC_MAX_SEGS];
+    int flag[NASREC_MAX_SEGS];
+    int n = 0;
 };
-// grad targets: ptr == null -> no gradient wanted; flag 0 -> overwrite, 1 -> accumulate
-void split_targets(const nasrec_seg_t* dsegs, const int* acc_flags, int nseg, SegSplit& s) {
+// grad targets: ptr == null -> no gradient wanted; flag 0 -> overwrite, 1 -> accumulate.  Fresh and accumulated targets go
+// into ONE dgrad launch (per-problem accumulate, nasrec_internal_set_dgrad_flags): a launch costs ~7 us whatever its size.
+void wanted_targets(const nasrec_seg_t* dsegs, const int* acc_flags, int nseg, Targets& t) {
     for (int i = 0; i < nseg; ++i) {
         if (!dsegs[i].ptr || dsegs[i].width == 0) continue;
-        if (acc_flags && acc_flags[i]) s.acc[s.na++] = dsegs[i];
-        else s.fresh[s.nf++] = dsegs[i];
+        t.seg[t.n] = dsegs[i];
+        t.flag[t.n] = acc_flags ? (acc_flags[i] != 0) : 0;
+        ++t.n;
     }
 }
 
@@ -100,14 +102,12 @@ int nasrec_linear_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* 
             if (rc) return rc;
         }
     }
-    SegSplit s;
-    split_targets(dsegs, dseg_accumulate, nseg, s);
-    if (s.nf) {
-        rc = nasrec_seg_linear_dgrad(dz, N, N, W, ldw, n_off, s.fresh, s.nf, M, 0, stream);
-        if (rc) return rc;
-    }
-    if (s.na) {
-        rc = nasrec_seg_linear_dgrad(dz, N, N, W, ldw, n_off, s.acc, s.na, M, 1, stream);
+    Targets t;
+    wanted_targets(dsegs, dseg_accumulate, nseg, t);
+    if (t.n) {
+        nasrec_internal_set_dgrad_flags(t.flag);
+        rc = nasrec_seg_linear_dgrad(dz, N, N, W, ldw, n_off, t.seg, t.n, M, 0, stream);
+        nasrec_internal_set_dgrad_flags(nullptr);
         if (rc) return rc;
     }
     return 0;
@@ -145,14 +145,12 @@ int nasrec_sproj_ln_bwd(const float* dy, int64_t dy_bstride, int p_out, const fl
             if (rc) return rc;
         }
     }
-    SegSplit s;
-    split_targets(dsegs, dseg_accumulate, nseg, s);
-    if (s.nf) {
-        rc = nasrec_sproj_dgrad(dz, zbs, P, W, ldw, s.fresh, s.nf, B, 0, stream);
-        if (rc) return rc;
-    }
-    if (s.na) {
-        rc = nasrec_sproj_dgrad(dz, zbs, P, W, ldw, s.acc, s.na, B, 1, stream);
+    Targets t;
+    wanted_targets(dsegs, dseg_accumulate, nseg, t);
+    if (t.n) {
+        nasrec_internal_set_dgrad_flags(t.flag);
+        rc = nasrec_sproj_dgrad(dz, zbs, P, W, ldw, t.seg, t.n, B, 0, stream);
+        nasrec_internal_set_dgrad_flags(nullptr);
         if (rc) return rc;
     }
     return 0;

@@ -11,6 +11,7 @@
 // Replaces: F.linear on torch.cat([...zeros...]) in nasrec/supernet/modules.py
 // (:171,:223,:340,:359,:385,:489,:578,:584,:648,:740) and supernet.py:598,1140.
 #include "gemm_common.cuh"
+#include <cstdio>
 #include "gemm_tc.cuh"
 #include "gemm_tma.cuh"
 #include <cstring>
@@ -187,6 +188,8 @@ struct GemmProf {
     bool on = false;
     std::vector<cudaEvent_t> e0, e1;
     std::vector<double> flops;
+    struct Desc { int M, N, K, nprob, kind, bn, ns, tma; };
+    std::vector<Desc> desc;                      // shape and plan of each timed launch (NASREC_GEMM_TRACE dump)
     size_t used = 0;
 } g_prof;
 
@@ -209,6 +212,7 @@ struct ProfScope {
             g_prof.e0.push_back(a);
             g_prof.e1.push_back(b);
             g_prof.flops.push_back(0);
+            g_prof.desc.push_back(GemmProf::Desc{});
         }
         slot = g_prof.used++;
         g_prof.flops[slot] = fl;
@@ -236,25 +240,49 @@ void mark_vec16(View& v) {
     v.vec16 = v.contig_j && jplain && iok && ((reinterpret_cast<uintptr_t>(v.p) & 15) == 0);
 }
 
+const int* g_dgrad_flags = nullptr;   // see nasrec_internal_set_dgrad_flags (common.cuh)
+int g_plan_kind = 0;    // operand-layout class of the entry point being served (set on entry): 0 fwd, 1 dgrad, 2 wgrad / sparse-axis
+
 // Tile width + split-K plan of one launch, shared by both tensor-core paths (so that they sum in the same order and agree
-// bit for bit).  Skinny launches (few output tiles, long K) leave most SMs idle: their K range is split over several CTAs,
-// partials go to the library workspace and a fixed-order reduction follows (deterministic).
+// bit for bit): nasrec_gemm::tc_plan.  Split-K applies to plain row-major outputs (optionally accumulated in place).
 template <class KTiles>
-int plan_tiles(Prob* prob, int nprob, KTiles ktiles_of, int maxN, cudaStream_t st, RedBatch& rb, int& totz) {
+nasrec_gemm::TilePlan plan_launch(const Prob* prob, int nprob, KTiles ktiles_of, int maxN) {
+    bool eligible = true;
+    for (int p = 0; p < nprob; ++p) {
+        const Prob& pr = prob[p];
+        if (pr.nsplit != 1 || pr.c_sh_i != 0 || pr.c_hi_j != 1 || (pr.addend && pr.addend != pr.c)) eligible = false;
+    }
+    static const int kinds = getenv("NASREC_SPLIT_KINDS") ? atoi(getenv("NASREC_SPLIT_KINDS")) : 7;      // experiment knob
+    if (!((kinds >> g_plan_kind) & 1)) eligible = false;
+    static const int lo = getenv("NASREC_SPLIT_LO") ? atoi(getenv("NASREC_SPLIT_LO")) : -1;
+    static const int hi = getenv("NASREC_SPLIT_HI") ? atoi(getenv("NASREC_SPLIT_HI")) : 1 << 30;
+    static int counter = 0;
+    if (lo >= 0 && eligible) {
+        const int id = counter++;
+        if (id < lo || id >= hi) eligible = false;
+        else if (getenv("NASREC_SPLIT_VERBOSE"))
+            fprintf(stderr, "split launch %d kind %d nprob %d M %d N %d maxN %d\n", id, g_plan_kind, nprob, prob[0].M, prob[0].N, maxN);
+    }
+    const nasrec_gemm::TilePlan pl = nasrec_gemm::tc_plan(prob, nprob, maxN, ktiles_of, eligible, g_plan_kind);
+    if (lo >= 0 && eligible && getenv("NASREC_SPLIT_VERBOSE"))
+        fprintf(stderr, "   plan bn %d ns %d ktiles %d nterm %d c %p ldc %lld bias %p addend %p\n", pl.bn, pl.ns, ktiles_of(0), prob[0].nterm,
+                (void*)prob[0].c, (long long)prob[0].c_hi_i, (const void*)prob[0].bias, (const void*)prob[0].addend);
+    return pl;
+}
+
+// LDG-producer kernel: the split CTAs write partial tiles to the library workspace and a fixed-order reduction launch
+// follows.  Returns false (plan falls back to ns = 1) when the workspace cannot hold the partials.
+bool split_to_workspace(Prob* prob, int nprob, int ns, cudaStream_t st, RedBatch& rb, int& totz) {
     float* wsb = nullptr;
     long long wsn = 0;
     ws_region(st, &wsb, &wsn);
-    const int bn = nasrec_gemm::tc_pick_bn(prob, nprob, maxN, ktiles_of, wsb != nullptr);
-    const long long ctas = nasrec_gemm::tc_cta_count(prob, nprob, bn);
-    if (!wsb || ctas > nasrec_gemm::TC_SM_COUNT / 2) return bn;
+    long long need_all = 0;
+    for (int p = 0; p < nprob; ++p) need_all += (long long)ns * prob[p].M * prob[p].N;
+    if (!wsb || need_all > wsn || rb.nseg + nprob > NASREC_MAX_SEGS) return false;
     long long off = 0;
     for (int p = 0; p < nprob; ++p) {
         Prob& pr = prob[p];
-        if (pr.nsplit != 1 || pr.c_sh_i != 0 || pr.c_hi_j != 1) continue;
-        if (pr.addend && pr.addend != pr.c) continue;
-        const int ns = nasrec_gemm::tc_split_for(ctas, ktiles_of(p));
         const long long need = (long long)ns * pr.M * pr.N;
-        if (ns < 2 || off + need > wsn || rb.nseg >= NASREC_MAX_SEGS) continue;
         RedSeg& rs = rb.seg[rb.nseg++];
         rs.ws = wsb + off;
         rs.c = pr.c;
@@ -273,7 +301,7 @@ int plan_tiles(Prob* prob, int nprob, KTiles ktiles_of, int maxN, cudaStream_t s
         off += need;
         totz += ns - 1;
     }
-    return bn;
+    return true;
 }
 
 int launch(Batch& bt, cudaStream_t st) {
@@ -296,12 +324,15 @@ int launch(Batch& bt, cudaStream_t st) {
     }));
     if (g_gemm_mode != 0) {
         RedBatch rb{};
-        const int bn = plan_tiles(bt.prob, bt.nprob, [&](int p) {
+        const nasrec_gemm::TilePlan pl = plan_launch(bt.prob, bt.nprob, [&](int p) {
             int kt = 0;
             for (int t = 0; t < bt.prob[p].nterm; ++t) kt += (bt.term[bt.prob[p].term0 + t].K + 31) / 32;
             return kt;
-        }, maxN, st, rb, totz);
-        int rc = nasrec_gemm::launch_tc(bt, bn, maxM, maxN, totz, g_gemm_mode, st);
+        }, maxN);
+        if (prof.active)
+            g_prof.desc[prof.slot] = GemmProf::Desc{bt.prob[0].M, bt.prob[0].N, 0, bt.nprob, g_plan_kind, pl.bn, pl.ns, 0};
+        if (pl.ns > 1) split_to_workspace(bt.prob, bt.nprob, pl.ns, st, rb, totz);
+        int rc = nasrec_gemm::launch_tc(bt, pl.bn, maxM, maxN, totz, g_gemm_mode, st);
         if (rc || rb.nseg == 0) return rc;
         return launch_reduce(rb, st);
     }
@@ -389,8 +420,16 @@ bool get_map(CUtensorMap* out, const MapSpec& sp) {
     cuuint64_t gstr[3] = {sp.stride[0], sp.stride[1], sp.stride[2]};
     cuuint32_t box[4] = {sp.box[0], sp.box[1], sp.box[2], sp.box[3]};
     cuuint32_t estr[4] = {1, 1, 1, 1};
+    // the kernel issues one instruction form (3-D): 2-D operands get a unit third dimension
+    cuuint32_t rank = sp.rank;
+    if (rank == 2) {
+        rank = 3;
+        gdim[2] = 1;
+        box[2] = 1;
+        gstr[1] = gstr[0] * gdim[1];
+    }
     CUtensorMap m;
-    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)sp.rank, (void*)sp.base, gdim, gstr, box, estr,
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, (void*)sp.base, gdim, gstr, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE,
                           sp.swz == 0 ? CU_TENSOR_MAP_SWIZZLE_128B
                                       : (sp.swz == 1 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -517,13 +556,22 @@ int run_tma(TmaJob& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
         for (int t = 0; t < tb.prob[p].nterm; ++t) k += tb.term[tb.prob[p].term0 + t].K;
         return k;
     }));
-    RedBatch rb{};
-    const int bn = plan_tiles(tb.prob, tb.nprob, [&](int p) {
+    const nasrec_gemm::TilePlan pl = plan_launch(tb.prob, tb.nprob, [&](int p) {
         int kt = 0;
         for (int t = 0; t < tb.prob[p].nterm; ++t) kt += (tb.term[tb.prob[p].term0 + t].K + 31) / 32;
         return kt;
-    }, maxN, st, rb, totz);
+    }, maxN);
+    const int bn = pl.bn;
+    if (prof.active) {
+        int k = 0;
+        for (int t = 0; t < tb.prob[0].nterm; ++t) k += tb.term[tb.prob[0].term0 + t].K;
+        g_prof.desc[prof.slot] = GemmProf::Desc{tb.prob[0].M, maxN, k, tb.nprob, g_plan_kind, pl.bn, pl.ns, 1};
+    }
+    tb.cluster_ns = pl.ns;             // split-K inside thread-block clusters (DSMEM reduction in the kernel)
+    if (pl.ns > 1) totz *= pl.ns;      // eligible launches have nsplit == 1 everywhere: z = problem * ns + split
     tb.nprod = g_gemm_mode;
+    static const int dbg = getenv("NASREC_GEMM_DBG") ? atoi(getenv("NASREC_GEMM_DBG")) : 0;
+    tb.dbg = dbg;
     tb.la = make_layout(job.a_kind, nasrec_gemm::TC_BM, job.a_conv);
     tb.lb = make_layout(job.b_kind, bn, job.b_conv);
     for (int i = 0; i < job.nmap; ++i) {
@@ -539,13 +587,14 @@ int run_tma(TmaJob& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
     }
     if (rc) return rc;
     ++g_tma_launches;
-    if (rb.nseg) rc = launch_reduce(rb, st);
-    if (rc) return rc;
     if (extra_rb && extra_rb->nseg) rc = launch_reduce(*extra_rb, st);
     return rc;
 }
 
-inline bool tma_on() { return g_use_tma && g_gemm_mode != 0 && have_encoder(); }
+inline bool tma_on() {
+    static const bool off = getenv("NASREC_FORCE_NO_TMA") != nullptr;      // experiment knob (the API switch is nasrec_set_gemm_tma)
+    return !off && g_use_tma && g_gemm_mode != 0 && have_encoder();
+}
 inline bool planes_for(const float* W, long long ldw) {
     return g_pl.W == W && g_pl.hi && (g_gemm_mode <= 2 || g_pl.lo) && g_pl.cols == (int)ldw;
 }
@@ -603,7 +652,7 @@ int tma_seg_dgrad(const float* dC, int64_t ldc, int N, const float* W, int64_t l
         TTerm& t = tb.term[np];
         p.M = M; p.N = (int)dsegs[s].width; p.term0 = np; p.nterm = 1;
         p.c = const_cast<float*>(dsegs[s].ptr); p.c_hi_i = dsegs[s].ld; p.c_hi_j = 1;
-        p.addend = accumulate ? dsegs[s].ptr : nullptr;
+        p.addend = (g_dgrad_flags ? g_dgrad_flags[s] : accumulate) ? dsegs[s].ptr : nullptr;
         p.nsplit = 1;
         t.K = N;
         t.a_hi = t.a_lo = (short)ah;
@@ -699,7 +748,7 @@ int tma_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* W, 
         p.M = B * NASREC_EMB_DIM; p.N = (int)dsegs[s].width; p.term0 = np; p.nterm = 1;
         p.c = const_cast<float*>(dsegs[s].ptr);
         p.c_hi_i = dsegs[s].ld; p.c_lo_i = 1; p.c_sh_i = 4; p.c_hi_j = NASREC_EMB_DIM;
-        p.addend = accumulate ? dsegs[s].ptr : nullptr;
+        p.addend = (g_dgrad_flags ? g_dgrad_flags[s] : accumulate) ? dsegs[s].ptr : nullptr;
         p.nsplit = 1;
         t.K = P;
         t.a_hi = t.a_lo = (short)ah;
@@ -724,6 +773,7 @@ void nasrec_internal_workspace(float** ws, long long* nfloats) {   // main-strea
     ws_region(nullptr, ws, nfloats);
 }
 
+void nasrec_internal_set_dgrad_flags(const int* flags) { g_dgrad_flags = flags; }
 cudaStream_t nasrec_internal_side_stream() { return g_side; }
 void nasrec_internal_set_side_stream(cudaStream_t s) { g_side = s; }
 
@@ -746,6 +796,7 @@ int nasrec_set_workspace(float* ws, int64_t nfloats) {
 
 int nasrec_seg_linear_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int n_off, int N,
                           const float* bias, float* C, int64_t ldc, int M, void* stream) {
+    g_plan_kind = 0;
     CHECK_ARG(segs_ok(segs, nseg) && W && C && M > 0 && N > 0 && n_off >= 0);
     {
         const int rc = tma_seg_fwd(segs, nseg, W, ldw, n_off, N, bias, C, ldc, M, as_stream(stream));
@@ -776,6 +827,7 @@ int nasrec_seg_linear_fwd(const nasrec_seg_t* segs, int nseg, const float* W, in
 
 int nasrec_seg_linear_dgrad(const float* dC, int64_t ldc, int N, const float* W, int64_t ldw, int n_off,
                             const nasrec_seg_t* dsegs, int nseg, int M, int accumulate, void* stream) {
+    g_plan_kind = 1;
     CHECK_ARG(segs_ok(dsegs, nseg) && dC && W && M > 0 && N > 0);
     {
         const int rc = tma_seg_dgrad(dC, ldc, N, W, ldw, n_off, dsegs, nseg, M, accumulate, as_stream(stream));
@@ -794,7 +846,7 @@ int nasrec_seg_linear_dgrad(const float* dC, int64_t ldc, int N, const float* W,
         p.c = const_cast<float*>(dsegs[s].ptr);
         p.c_hi_i = dsegs[s].ld;
         p.c_hi_j = 1;
-        p.addend = accumulate ? dsegs[s].ptr : nullptr;
+        p.addend = (g_dgrad_flags ? g_dgrad_flags[s] : accumulate) ? dsegs[s].ptr : nullptr;
         p.nsplit = 1;
         t.K = N;
         t.a = plain_view(dC, ldc, 1, 1);
@@ -808,6 +860,7 @@ int nasrec_seg_linear_dgrad(const float* dC, int64_t ldc, int N, const float* W,
 
 int nasrec_seg_linear_wgrad(const float* dC, int64_t ldc, int N, const nasrec_seg_t* segs, int nseg, float* dW,
                             int64_t ldw, int n_off, int M, int accumulate, void* stream) {
+    g_plan_kind = 2;
     CHECK_ARG(segs_ok(segs, nseg) && dC && dW && M > 0 && N > 0);
     {
         const int rc = tma_seg_wgrad(dC, ldc, N, segs, nseg, dW, ldw, n_off, M, accumulate, as_stream(stream));
@@ -840,6 +893,7 @@ int nasrec_seg_linear_wgrad(const float* dC, int64_t ldc, int N, const nasrec_se
 // ---------------------------------------------------------------- 3-D (sparse axis)
 int nasrec_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t ldw, int P, const float* bias,
                      float* Z, int64_t z_bstride, int B, void* stream) {
+    g_plan_kind = 2;
     CHECK_ARG(segs_ok(segs, nseg) && W && Z && B > 0 && P > 0);
     {
         const int rc = tma_sproj_fwd(segs, nseg, W, ldw, P, bias, Z, z_bstride, B, as_stream(stream));
@@ -879,6 +933,7 @@ int nasrec_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t
 
 int nasrec_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* W, int64_t ldw,
                        const nasrec_seg_t* dsegs, int nseg, int B, int accumulate, void* stream) {
+    g_plan_kind = 2;
     CHECK_ARG(segs_ok(dsegs, nseg) && dZ && W && B > 0 && P > 0);
     {
         const int rc = tma_sproj_dgrad(dZ, dz_bstride, P, W, ldw, dsegs, nseg, B, accumulate, as_stream(stream));
@@ -899,7 +954,7 @@ int nasrec_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* 
         p.c_lo_i = 1;
         p.c_sh_i = 4;
         p.c_hi_j = NASREC_EMB_DIM;
-        p.addend = accumulate ? dsegs[s].ptr : nullptr;
+        p.addend = (g_dgrad_flags ? g_dgrad_flags[s] : accumulate) ? dsegs[s].ptr : nullptr;
         p.nsplit = 1;
         t.K = P;
         View a{};                      // A(m=(b,e), k=p) = dZ[b*zbs + p*16 + e]
@@ -928,7 +983,9 @@ int64_t nasrec_sproj_wgrad_ws_floats(int P, int64_t total_width, int B) {
     return (int64_t)sproj_nsplit(B) * P * total_width;
 }
 
-int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_seg_t* segs, int nseg, float* dW,
+// Large batches (B > 1024: more than 64 k-tiles per CTA even at 8 splits): up to 32 splits through the caller's workspace
+// and a reduction launch, which keeps the chain of MMAs per accumulator short (numerics, see gemm_tc.cuh).
+static int sproj_wgrad_presplit(const float* dZ, int64_t dz_bstride, int P, const nasrec_seg_t* segs, int nseg, float* dW,
                        int64_t ldw, int B, int accumulate, float* ws, void* stream) {
     CHECK_ARG(segs_ok(segs, nseg) && dZ && dW && ws && B > 0 && P > 0);
     const int ns = sproj_nsplit(B);
@@ -1006,6 +1063,74 @@ int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_
     return launch_reduce(rb, as_stream(stream));
 }
 
+int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_seg_t* segs, int nseg, float* dW,
+                       int64_t ldw, int B, int accumulate, float* ws, void* stream) {
+    // K = (b, e) is long (16 B) and the output small (P x rows): the launch is split over K like any other skinny GEMM --
+    // thread-block clusters with a DSMEM reduction in the TMA kernel, library workspace + reduction launch in the
+    // LDG-producer kernel (plan_launch).  `ws` is used only by the large-batch path above.
+    g_plan_kind = 2;
+    if (B > 1024) return sproj_wgrad_presplit(dZ, dz_bstride, P, segs, nseg, dW, ldw, B, accumulate, ws, stream);
+    CHECK_ARG(segs_ok(segs, nseg) && dZ && dW && B > 0 && P > 0);
+    Batch bt{};
+    int np = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segs[s].width == 0) continue;
+        const int w = (int)segs[s].width;
+        Prob& p = bt.prob[np];
+        Term& t = bt.term[np];
+        p.M = P;
+        p.N = w;
+        p.term0 = np;
+        p.nterm = 1;
+        p.c = dW + segs[s].w_off;
+        p.c_hi_i = ldw;
+        p.c_hi_j = 1;
+        p.addend = accumulate ? p.c : nullptr;
+        p.nsplit = 1;
+        t.K = B * NASREC_EMB_DIM;      // k = b*16 + e
+        View a{};                      // A(i=p, k=(b,e)) = dZ[b*zbs + p*16 + e]
+        a.p = dZ;
+        a.hi_i = NASREC_EMB_DIM;
+        a.hi_j = dz_bstride;
+        a.lo_j = 1;
+        a.sh_j = 4;
+        a.contig_j = 1;
+        t.a = a;
+        View b{};                      // B(i=r, k=(b,e)) = X[b*ld + r*16 + e]
+        b.p = segs[s].ptr;
+        b.hi_i = NASREC_EMB_DIM;
+        b.hi_j = segs[s].ld;
+        b.lo_j = 1;
+        b.sh_j = 4;
+        b.contig_j = 1;
+        t.b = b;
+        ++np;
+    }
+    bt.nprob = np;
+    if (np == 0) return 0;
+    bool tma_ok = tma_on() && al16(dZ) && !(dz_bstride & 3) && np + 1 <= nasrec_gemm::TM_MAXMAPS;
+    for (int s = 0; s < nseg && tma_ok; ++s)
+        if (segs[s].width > 0 && (!al16(segs[s].ptr) || (segs[s].ld & 3))) tma_ok = false;
+    if (tma_ok) {
+        TmaJob& job = fresh_job();
+        job.a_kind = OP_KM64; job.a_conv = 1; job.b_kind = OP_KM64; job.b_conv = 1;
+        const int ah = job.add(spec3d(dZ, P, B, dz_bstride), 0);
+        int q = 0;
+        for (int s = 0; s < nseg; ++s) {
+            if (segs[s].width == 0) continue;
+            job.tb.prob[q] = bt.prob[q];
+            TTerm& t = job.tb.term[q];
+            t.K = B * NASREC_EMB_DIM;
+            t.a_hi = t.a_lo = (short)ah;
+            t.b_hi = t.b_lo = (short)job.add(spec3d(segs[s].ptr, segs[s].width, B, segs[s].ld), 1);
+            ++q;
+        }
+        job.tb.nprob = np;
+        return run_tma(job, as_stream(stream));
+    }
+    return launch(bt, as_stream(stream));
+}
+
 int nasrec_gemm_prof(int what, double* out3) {
     if (what == 1) { g_prof.on = true; g_prof.used = 0; return 0; }
     g_prof.on = false;
@@ -1018,6 +1143,17 @@ int nasrec_gemm_prof(int what, double* out3) {
             fl += g_prof.flops[i];
         }
         out3[0] = ms; out3[1] = (double)g_prof.used; out3[2] = fl;
+        if (const char* path = getenv("NASREC_GEMM_TRACE")) {       // one line per timed launch: shape, plan, microseconds
+            if (FILE* f = fopen(path, "a")) {
+                for (size_t i = 0; i < g_prof.used; ++i) {
+                    float t = 0;
+                    cudaEventElapsedTime(&t, g_prof.e0[i], g_prof.e1[i]);
+                    const GemmProf::Desc& d = g_prof.desc[i];
+                    fprintf(f, "%d %d %d %d %d %d %d %d %.2f %.0f\n", d.kind, d.M, d.N, d.K, d.nprob, d.bn, d.ns, d.tma, t * 1e3, g_prof.flops[i]);
+                }
+                fclose(f);
+            }
+        }
     }
     return 0;
 }

@@ -505,40 +505,76 @@ inline long long tc_cta_count(const Prob* prob, int nprob, int bn) {
 }
 inline long long tc_cta_count(const Batch& bt, int bn) { return tc_cta_count(bt.prob, bt.nprob, bn); }
 
-// Tile width and split-K.  Measured on the B = 512 training step (profiles/r02_notes.md): narrow tiles that spread a launch
-// over the SMs (and leave room for the other stream's GEMM) beat wide tiles + split-K, whose extra reduction launches cost
-// more than the tensor-core issue slots they save; launches that still cover fewer than half the SMs split K over several
-// CTAs (plan_tiles, deterministic fixed-order reduction).  NASREC_TC_BN / NASREC_TILE_POLICY are experiment knobs.
+// Tile width and split-K: a small cost model fitted to measurements of this kernel family on B200 (profiles/r02_gemm.md).
+//   * a CTA's k-loop costs about the same per k-tile whatever the tile width (0.38-0.47 us: TMA issue, conversion of the
+//     128 x 32 A tile and twelve MMA issues are per-tile costs; only the B bytes grow with the width), so wide tiles do
+//     more work per unit of time -- but a launch of few wide tiles leaves SMs idle and its CTAs walk the whole K range;
+//   * split-K shortens that walk.  In the TMA kernel the CTAs of a thread-block cluster share an output tile and sum their
+//     partial tiles through distributed shared memory (no workspace, no second launch, ~1 us); the LDG-producer kernel
+//     uses the library workspace and a reduction launch with the SAME split count and summation order, so the two kernels
+//     agree bit for bit;
+//   * a launch costs whole waves of 148 CTAs.
+// Constraint from numerics: the tensor core truncates when it accumulates, so the chain of MMAs into one accumulator is
+// bounded -- 128-wide tiles have two accumulators and are used only when a CTA walks <= 16 k-tiles.
+// NASREC_TC_BN / NASREC_TC_NS force the choice (experiments); NASREC_TILE_POLICY=1 restores the round-1 narrow-tile rule.
 constexpr int TC_SM_COUNT = 148;
+struct TilePlan {
+    int bn, ns;
+};
 inline int tc_split_for(long long ctas, int ktiles) {
     if (ctas <= 0 || ctas > TC_SM_COUNT / 2) return 1;
     int ns = (int)(TC_SM_COUNT / ctas);
     if (ns > ktiles / 3) ns = ktiles / 3;
-    if (ns > 16) ns = 16;
-    return ns < 2 ? 1 : ns;
+    if (ns >= 8) return 8;
+    if (ns >= 4) return 4;
+    return ns < 2 ? 1 : 2;
 }
+// kind: 0 forward-like (both operands K-major), 1 dgrad-like (weight planes MN-major: bn / 32 boxes per plane and k-tile),
+// 2 wgrad-like (both operands MN-major, the B tile split in shared memory by the converter warps)
 template <class KTiles>
-inline int tc_pick_bn(const Prob* prob, int nprob, int maxN, KTiles ktiles_of, bool can_split) {
-    static const int forced = getenv("NASREC_TC_BN") ? atoi(getenv("NASREC_TC_BN")) : 0;
-    if (forced) return forced;
-    static const int policy = getenv("NASREC_TILE_POLICY") ? atoi(getenv("NASREC_TILE_POLICY")) : 1;
-    if (maxN <= 16) return 16;
-    if (policy == 1) {
-        if (maxN > 32 && tc_cta_count(prob, nprob, 64) >= 120) return 64;
-        return maxN <= 32 ? 32 : (tc_cta_count(prob, nprob, 32) > 296 ? 64 : 32);
-    }
-    if (maxN <= 32) return 32;
-    if (maxN <= 64 || policy == 2) return 64;
-    // policy 0: 128-wide tiles (two accumulators) when split-K leaves each CTA <= 16 k-tiles, which bounds the MMA chain
-    const long long c128 = tc_cta_count(prob, nprob, 128);
-    if (!can_split || c128 > TC_SM_COUNT / 2) return 64;
+inline TilePlan tc_plan(const Prob* prob, int nprob, int maxN, KTiles ktiles_of, bool can_split, int kind) {
+    static const int forced_bn = getenv("NASREC_TC_BN") ? atoi(getenv("NASREC_TC_BN")) : 0;
+    static const int forced_ns = getenv("NASREC_TC_NS") ? atoi(getenv("NASREC_TC_NS")) : 0;
+    static const int policy = getenv("NASREC_TILE_POLICY") ? atoi(getenv("NASREC_TILE_POLICY")) : 3;
+    int kt_max = 0, kt_min = 1 << 30;
     for (int p = 0; p < nprob; ++p) {
-        if (prob[p].N <= 64) continue;
         const int kt = ktiles_of(p);
-        const int ns = prob[p].nsplit > 1 ? prob[p].nsplit : tc_split_for(c128, kt);
-        if ((kt + ns - 1) / ns > 16) return 64;
+        kt_max = kt > kt_max ? kt : kt_max;
+        kt_min = kt < kt_min ? kt : kt_min;
     }
-    return 128;
+    if (policy == 1 && !forced_bn) {
+        int bn;
+        if (maxN <= 16) bn = 16;
+        else if (maxN > 32 && tc_cta_count(prob, nprob, 64) >= 120) bn = 64;
+        else bn = maxN <= 32 ? 32 : (tc_cta_count(prob, nprob, 32) > 296 ? 64 : 32);
+        return TilePlan{bn, can_split ? tc_split_for(tc_cta_count(prob, nprob, bn), kt_min) : 1};
+    }
+    TilePlan best{maxN <= 16 ? 16 : 32, 1};
+    double best_t = 1e30;
+    static const int widths[4] = {16, 32, 64, 128};
+    // measured us per k-tile of one CTA (gemm_prof2.py, B200, 3xTF32), by operand kind and tile width
+    static const double t_tile[3][4] = {{0.40, 0.42, 0.52, 0.78}, {0.40, 0.42, 0.60, 0.97}, {0.42, 0.42, 0.73, 1.20}};
+    static const int capacity[4] = {148, 148, 144, 128};      // SMs a grid of clusters of 1 / 2 / 4 / 8 one-CTA-per-SM CTAs can fill
+    const double* tt = t_tile[kind < 0 || kind > 2 ? 2 : kind];
+    for (int w = 0; w < 4; ++w) {
+        const int bn = widths[w];
+        if (forced_bn ? bn != forced_bn : ((bn == 16) != (maxN <= 16) || (bn > 32 && bn >= 2 * maxN))) continue;
+        const long long tiles = tc_cta_count(prob, nprob, bn);
+        for (int ns = 1, li = 0; ns <= 8; ns *= 2, ++li) {
+            if (ns > 1 && (!can_split || kt_min < 2 * ns)) break;
+            if (forced_ns && can_split && kt_min >= 2 * forced_ns && ns != forced_ns) continue;
+            const int walk = (kt_max + ns - 1) / ns;
+            if (bn == 128 && walk > 16 && !forced_bn) continue;
+            const double cta = 3.5 + walk * tt[w] + (ns > 1 ? 0.3 + 0.1 * (bn / 32) : 0.0);
+            const long long ctas = tiles * ns;
+            const double t = 2.5 + (double)((ctas + capacity[li] - 1) / capacity[li]) * cta + 0.002 * (double)ctas / TC_SM_COUNT;
+            if (t < best_t) {
+                best_t = t;
+                best = TilePlan{bn, ns};
+            }
+        }
+    }
+    return best;
 }
 
 inline int launch_tc(const Batch& bt, int bn, int maxM, int maxN, int totz, int nprod, cudaStream_t st) {

@@ -62,6 +62,8 @@ struct TTerm {
 struct TBatch {
     alignas(64) CUtensorMap maps[TM_MAXMAPS];
     int nprob, nprod;
+    int cluster_ns;         // > 1: split-K over a thread-block cluster of this many CTAs along z (DSMEM reduction); else 0/1
+    int dbg;                // experiment knob (NASREC_GEMM_DBG): 1 no TMA loads, 2 converters idle, 4 no MMAs, 8 no TMEM-slot wait
     OpLayout la, lb;
     Prob prob[MAXP];
     TTerm term[MAXT];
@@ -115,6 +117,62 @@ __device__ __forceinline__ void umma_commit_w(uint32_t bar) {
     asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar) : "memory");
 }
 
+
+// One TMA box.  Every tensor map of this kernel is encoded with rank 3 (2-D operands get a unit third dimension, gemm.cu
+// get_map), so that a single instruction form serves all operand layouts and the producer loop has no rank branches.
+__device__ __forceinline__ void tma_load_w(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// One k-tile of the 3xTF32 scheme in ONE asm block: 4 k-steps x (lo*hi, hi*lo, hi*hi) and the commit that frees the
+// stage.  Issuing the twelve MMAs separately costs ~20 SASS instructions each (election, moves into uniform registers,
+// votes) on a single warp -- ~1200 clk per k-tile, the bottleneck of the k-loop (profiles/r02_gemm.md); here the operands
+// enter the uniform datapath once per tile.  bh / bl: low words of the B hi / lo descriptors at k-step 0; k1..k3: the
+// (byte offset >> 4) of k-steps 1..3; ta: TMEM column of the A hi plane (lo plane 32 columns further).
+__device__ __forceinline__ void umma_tile3_w(uint32_t tacc, uint32_t ta, uint32_t bh, uint32_t bl, uint32_t dhi, uint32_t idesc,
+                                            uint32_t first, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pf, pt;\n\t"
+        ".reg .b32 al0, ah1, al1, ah2, al2, ah3, al3, x;\n\t"
+        ".reg .b64 h0, h1, h2, h3, l0, l1, l2, l3;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pf, %6, 0;\n\t"
+        "setp.eq.b32 pt, %6, %6;\n\t"
+        "mov.b64 h0, {%2, %4};\n\t"
+        "mov.b64 l0, {%3, %4};\n\t"
+        "add.u32 x, %2, %7;\n\tmov.b64 h1, {x, %4};\n\t"
+        "add.u32 x, %3, %7;\n\tmov.b64 l1, {x, %4};\n\t"
+        "add.u32 x, %2, %8;\n\tmov.b64 h2, {x, %4};\n\t"
+        "add.u32 x, %3, %8;\n\tmov.b64 l2, {x, %4};\n\t"
+        "add.u32 x, %2, %9;\n\tmov.b64 h3, {x, %4};\n\t"
+        "add.u32 x, %3, %9;\n\tmov.b64 l3, {x, %4};\n\t"
+        "add.u32 al0, %1, 32;\n\t"
+        "add.u32 ah1, %1, 8;\n\tadd.u32 al1, %1, 40;\n\t"
+        "add.u32 ah2, %1, 16;\n\tadd.u32 al2, %1, 48;\n\t"
+        "add.u32 ah3, %1, 24;\n\tadd.u32 al3, %1, 56;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [al0], h0, %5, pf;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], l0, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], h0, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [al1], h1, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], l1, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], h1, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [al2], h2, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], l2, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], h2, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [al3], h3, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], l3, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], h3, %5, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+        "}\n" ::"r"(tacc),
+        "r"(ta), "r"(bh), "r"(bl), "r"(dhi), "r"(idesc), "r"(first), "r"(k1), "r"(k2), "r"(k3), "r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ uint64_t tm_desc(const OpLayout& L, uint32_t saddr) {
     return (uint64_t)(((saddr >> 4) & 0x3FFFu) | (L.desc_lbo << 16)) | ((uint64_t)L.desc_hi32 << 32);
 }
@@ -162,6 +220,7 @@ struct TmCfg {
     static constexpr int A_BYTES = TC_BM * TC_BK * 4;                         // 16 KB raw landing zone
     static constexpr int B_BYTES = (BN < 32 ? 32 : BN) * TC_BK * 4;           // MN-major boxes are 32 wide
     static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+    static constexpr int PW = BN < 32 ? 32 : BN;                               // columns of a partial tile parked in shared memory (cluster split-K)
     static constexpr int STAGES = BN <= 32 ? 8 : (BN == 64 ? 6 : 4);          // 192 KB each: deep TMA prefetch, one CTA per SM
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
     static constexpr int ACC_STRIDE = TcCfg<BN>::ACC_STRIDE;
@@ -176,17 +235,28 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t s_tmem_base;
 
+    // Split-K comes in two forms.  cluster_ns > 1: the launch is a grid of clusters (1, 1, cluster_ns); the CTAs of a cluster
+    // share an output tile, each takes a slice of the k-tiles, and the partial tiles are summed through distributed shared
+    // memory in split order (no workspace, no reduction launch).  Otherwise a problem may carry its own nsplit with
+    // partials going to the caller's workspace (sparse-axis projections, which reduce over the batch).
+    const int cns = tb.cluster_ns > 1 ? tb.cluster_ns : 1;
     int z = blockIdx.z, pi = 0;
-    for (; pi < tb.nprob; ++pi) {
-        const int ns = tb.prob[pi].nsplit;
-        if (z < ns) break;
-        z -= ns;
+    if (cns > 1) {
+        pi = z / cns;
+        z -= pi * cns;
+    } else {
+        for (; pi < tb.nprob; ++pi) {
+            const int ns = tb.prob[pi].nsplit;
+            if (z < ns) break;
+            z -= ns;
+        }
     }
     if (pi >= tb.nprob) return;
     const Prob& pr = tb.prob[pi];
     const int split = z;
+    const int nsplit = cns > 1 ? cns : pr.nsplit;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-    if (m0 >= pr.M || n0 >= pr.N) return;
+    if (m0 >= pr.M || n0 >= pr.N) return;          // the whole cluster leaves together (same tile, same problem)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw = smem_u32(smem_raw);
@@ -200,7 +270,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
 
     int tot = 0;
     for (int t = 0; t < pr.nterm; ++t) tot += (tb.term[pr.term0 + t].K + TC_BK - 1) / TC_BK;
-    const int per = (tot + pr.nsplit - 1) / pr.nsplit;
+    const int per = (tot + nsplit - 1) / nsplit;
     const int kt_begin = split * per;
     const int kt_end = min(tot, kt_begin + per);
     const int ntiles = max(0, kt_end - kt_begin);
@@ -237,7 +307,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             const OpLayout& LB = tb.lb;
             const bool b_lo = nprod > 2 && !LB.convert;                        // the weight's lo plane is fetched, not derived
             const uint32_t tx = (uint32_t)(LA.nbox * LA.box_bytes + LB.nbox * LB.box_bytes * (b_lo ? 2 : 1));
-            const int a_rank = LA.rank, a_nbox = LA.nbox, a_bb = LA.box_bytes, b_rank = LB.rank, b_nbox = LB.nbox, b_bb = LB.box_bytes;
+            const int a_nbox = LA.nbox, a_bb = LA.box_bytes, b_nbox = LB.nbox, b_bb = LB.box_bytes;
             const int ar0 = m0 >> LA.rsh[0], ar1 = m0 >> LA.rsh[1], ar2 = m0 >> LA.rsh[2];
             const int br0 = n0 >> LB.rsh[0], br1 = n0 >> LB.rsh[1], br2 = n0 >> LB.rsh[2];
             const int ak0 = LA.ksh[0], ak1 = LA.ksh[1], ak2 = LA.ksh[2], bk0 = LB.ksh[0], bk1 = LB.ksh[1], bk2 = LB.ksh[2];
@@ -255,14 +325,18 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     kt += nk;
                 }
             }
-            int K = 0, a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+            // Running state: the coordinates of the current k-tile advance by constants (a k-tile is 32 k: +32, +2 (k >> 4)
+            // or +0 per dimension), so the loop body is wait / expect / issue with no address arithmetic beyond adds.
+            const int ai0 = ak0 == 31 ? 0 : (TC_BK >> ak0), ai1 = ak1 == 31 ? 0 : (TC_BK >> ak1), ai2 = ak2 == 31 ? 0 : (TC_BK >> ak2);
+            const int bi0 = bk0 == 31 ? 0 : (TC_BK >> bk0), bi1 = bk1 == 31 ? 0 : (TC_BK >> bk1), bi2 = bk2 == 31 ? 0 : (TC_BK >> bk2);
+            int left = 0, a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
             const CUtensorMap *map_a = nullptr, *map_bh = nullptr, *map_bl = nullptr;
-            auto load_term = [&](int t) {
+            auto load_term = [&](int t, int k_first) {
                 const TTerm& tm = tb.term[pr.term0 + t];
-                K = tm.K;
+                left = (tm.K + TC_BK - 1) / TC_BK - k_first;
                 map_a = &tb.maps[tm.a_hi]; map_bh = &tb.maps[tm.b_hi]; map_bl = &tb.maps[tm.b_lo];
-                a0 = tm.a_base[0] + ar0; a1 = tm.a_base[1] + ar1; a2 = tm.a_base[2] + ar2;
-                b0 = tm.b_base[0] + br0; b1 = tm.b_base[1] + br1; b2 = tm.b_base[2] + br2;
+                a0 = tm.a_base[0] + ar0 + k_first * ai0; a1 = tm.a_base[1] + ar1 + k_first * ai1; a2 = tm.a_base[2] + ar2 + k_first * ai2;
+                b0 = tm.b_base[0] + br0 + k_first * bi0; b1 = tm.b_base[1] + br1 + k_first * bi1; b2 = tm.b_base[2] + br2 + k_first * bi2;
             };
             if (lane == 0)
                 for (int t = 0; t < pr.nterm; ++t) {       // warm the descriptor cache
@@ -272,43 +346,31 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     if (b_lo) asm volatile("prefetch.tensormap [%0];" ::"l"(&tb.maps[tm.b_lo]) : "memory");
                 }
             __syncwarp();
-            load_term(t_cur);
+            load_term(t_cur, kk);
             const uint32_t tiles_u32 = smem_u32(tiles);
+            const bool no_tma = tb.dbg & 1;
+            int s = 0;
+            uint32_t ph = 1u;                              // parity the empty barrier of a fresh stage passes at once
 #pragma unroll 1
             for (int it = 0; it < ntiles; ++it) {
-                while (kk * TC_BK >= K) { load_term(++t_cur); kk = 0; }
-                const int s = it % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+                while (left == 0) load_term(++t_cur, 0);
                 const uint32_t full = bar_full + 8 * s;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                mbar_expect_tx_w(full, tx);
-                const int k0 = kk * TC_BK;
-                uint32_t dst = tiles_u32 + (uint32_t)(s * Cfg::STAGE_BYTES);
-                {
-                    int c0 = a0 + (k0 >> ak0), c1 = a1 + (k0 >> ak1);
-                    const int c2 = a2 + (k0 >> ak2);
-                    uint32_t d = dst;
-                    for (int i = 0; i < a_nbox; ++i) {
-                        if (a_rank == 2) tma_load_2d_w(d, map_a, full, c0, c1);
-                        else tma_load_3d_w(d, map_a, full, c0, c1, c2);
-                        d += a_bb; c0 += ad0; c1 += ad1;
-                    }
-                }
-                {
-                    int c0 = b0 + (k0 >> bk0), c1 = b1 + (k0 >> bk1);
-                    const int c2 = b2 + (k0 >> bk2);
-                    uint32_t d = dst + Cfg::A_BYTES;
+                mbar_wait(bar_empty + 8 * s, ph);
+                mbar_expect_tx_w(full, no_tma ? 0u : tx);
+                if (!no_tma) {
+                    const uint32_t dst = tiles_u32 + (uint32_t)(s * Cfg::STAGE_BYTES);
+                    for (int i = 0; i < a_nbox; ++i)
+                        tma_load_w(dst + (uint32_t)(i * a_bb), map_a, full, a0 + i * ad0, a1 + i * ad1, a2);
                     for (int i = 0; i < b_nbox; ++i) {
-                        if (b_rank == 2) tma_load_2d_w(d, map_bh, full, c0, c1);
-                        else tma_load_3d_w(d, map_bh, full, c0, c1, c2);
-                        if (b_lo) {
-                            if (b_rank == 2) tma_load_2d_w(d + Cfg::B_BYTES, map_bl, full, c0, c1);
-                            else tma_load_3d_w(d + Cfg::B_BYTES, map_bl, full, c0, c1, c2);
-                        }
-                        d += b_bb; c0 += bd0; c1 += bd1;
+                        const uint32_t d = dst + (uint32_t)(Cfg::A_BYTES + i * b_bb);
+                        tma_load_w(d, map_bh, full, b0 + i * bd0, b1 + i * bd1, b2);
+                        if (b_lo) tma_load_w(d + Cfg::B_BYTES, map_bl, full, b0 + i * bd0, b1 + i * bd1, b2);
                     }
                 }
-                ++kk;
+                a0 += ai0; a1 += ai1; a2 += ai2;
+                b0 += bi0; b1 += bi1; b2 += bi2;
+                --left;
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 8) {
@@ -320,33 +382,47 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
             const uint64_t dhi = (uint64_t)tb.lb.desc_hi32 << 32;
             const int ko0 = tb.lb.koff[0], ko1 = tb.lb.koff[1], ko2 = tb.lb.koff[2], ko3 = tb.lb.koff[3];
             const uint32_t tiles_u32 = smem_u32(tiles);
+            const uint32_t dhi32 = tb.lb.desc_hi32;
+            const uint32_t k1 = (uint32_t)ko1 >> 4, k2 = (uint32_t)ko2 >> 4, k3 = (uint32_t)ko3 >> 4;
+            const bool no_mma = tb.dbg & 4;
+            int s = 0, slot = 0, acc = 0;
+            uint32_t ph = 0u, wrapped = 0u;
 #pragma unroll 1
             for (int it = 0; it < ntiles; ++it) {
-                const int s = it % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
                 mbar_wait(bar_full + 8 * s, ph);
                 mbar_wait(bar_conv + 8 * s, ph);
                 tc_fence_after();
                 const uint32_t sb = tiles_u32 + (uint32_t)(s * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
-                const uint32_t ta = tm_u + (uint32_t)(TM_ACC_COLS + (it % TM_SLOTS) * 64);
-                const uint32_t tacc = tm_u + (uint32_t)((it % nacc) * Cfg::ACC_STRIDE);
+                const uint32_t ta = tm_u + (uint32_t)(TM_ACC_COLS + slot * 64);
+                const uint32_t tacc = tm_u + (uint32_t)(acc * Cfg::ACC_STRIDE);
+                const uint32_t bar_e = bar_empty + 8 * s;
+                if (nprod == 3 && !no_mma) {
+                    // hot path: the whole k-tile and its commit in one asm block
+                    umma_tile3_w(tacc, ta, ((sb >> 4) & 0x3FFFu) | dlo, (((sb + Cfg::B_BYTES) >> 4) & 0x3FFFu) | dlo, dhi32, idesc, wrapped, k1,
+                                 k2, k3, bar_e);
+                } else {
+                    if (!no_mma)
 #pragma unroll
-                for (int k = 0; k < TC_BK / TC_UK; ++k) {
-                    const int ko = k == 0 ? ko0 : (k == 1 ? ko1 : (k == 2 ? ko2 : ko3));
-                    const uint32_t a_hi = ta + (uint32_t)(k * TC_UK), a_lo = a_hi + 32u;
-                    const uint64_t b_hi = (uint64_t)((((sb + ko) >> 4) & 0x3FFFu) | dlo) | dhi;
-                    const uint64_t b_lo = (uint64_t)((((sb + Cfg::B_BYTES + ko) >> 4) & 0x3FFFu) | dlo) | dhi;
-                    const uint32_t first = (it >= nacc || k > 0) ? 1u : 0u;
-                    if (nprod > 2) {
-                        umma_tf32_ts_w(tacc, a_lo, b_hi, idesc, first);
-                        umma_tf32_ts_w(tacc, a_hi, b_lo, idesc, 1u);
-                        if (nprod > 3) umma_tf32_ts_w(tacc, a_lo, b_lo, idesc, 1u);
-                        umma_tf32_ts_w(tacc, a_hi, b_hi, idesc, 1u);
-                    } else {
-                        umma_tf32_ts_w(tacc, a_hi, b_hi, idesc, first);
-                    }
+                        for (int k = 0; k < TC_BK / TC_UK; ++k) {
+                            const int ko = k == 0 ? ko0 : (k == 1 ? ko1 : (k == 2 ? ko2 : ko3));
+                            const uint32_t a_hi = ta + (uint32_t)(k * TC_UK), a_lo = a_hi + 32u;
+                            const uint64_t b_hi = (uint64_t)((((sb + ko) >> 4) & 0x3FFFu) | dlo) | dhi;
+                            const uint64_t b_lo = (uint64_t)((((sb + Cfg::B_BYTES + ko) >> 4) & 0x3FFFu) | dlo) | dhi;
+                            const uint32_t first = (wrapped || k > 0) ? 1u : 0u;
+                            if (nprod > 2) {
+                                umma_tf32_ts_w(tacc, a_lo, b_hi, idesc, first);
+                                umma_tf32_ts_w(tacc, a_hi, b_lo, idesc, 1u);
+                                if (nprod > 3) umma_tf32_ts_w(tacc, a_lo, b_lo, idesc, 1u);
+                                umma_tf32_ts_w(tacc, a_hi, b_hi, idesc, 1u);
+                            } else {
+                                umma_tf32_ts_w(tacc, a_hi, b_hi, idesc, first);
+                            }
+                        }
+                    umma_commit_w(bar_e);
                 }
-                umma_commit_w(bar_empty + 8 * s);
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+                slot = (slot + 1) & (TM_SLOTS - 1);
+                if (++acc == nacc) { acc = 0; wrapped = 1u; }
             }
             umma_commit_w(bar_done);
         }
@@ -369,7 +445,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                 const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
                 mbar_wait(bar_full + 8 * s, ph);
                 const uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
-                if (it >= TM_SLOTS) {
+                if (it >= TM_SLOTS && !(tb.dbg & 8)) {
                     // the TMEM slot is free once the MMAs of k-tile it - TM_SLOTS have retired: their commit arrived on that
                     // tile's empty barrier (which cannot complete again before this tile has been converted)
                     const int jt = it - TM_SLOTS;
@@ -377,6 +453,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     tc_fence_after();
                 }
                 const uint32_t ta = lane_base + (uint32_t)((it % TM_SLOTS) * 64);
+                if (!(tb.dbg & 2))
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float x[16];
@@ -472,7 +549,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(u[j]);
                 }
-                if (transpose) {
+                if (cns > 1) {
+                    // partial tile -> this CTA's shared memory, rows padded by 4 floats (conflict-free float4 stores)
+                    float4* prow = reinterpret_cast<float4*>(reinterpret_cast<float*>(tiles) + (warp * 32 + lane) * (Cfg::PW + 4) + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) prow[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                } else if (transpose) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = r[j];
                     __syncwarp();
@@ -503,6 +585,66 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
         }
         tc_fence_before();
     }
+    if (cns > 1) {
+        // ------------------------------------------------------------ cluster split-K: fixed-order sum over the CTAs' partial
+        // tiles (split 0, 1, ...: the order of the workspace reduction of the LDG-producer kernel, bit for bit), each CTA
+        // finishing a slice of the rows; then bias, accumulate, store
+        asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+        if (tid < TM_CONV_THREADS) {
+            constexpr int C4 = Cfg::PW / 4;
+            const int rows_per = TC_BM / cns;
+            const int total = rows_per * C4;
+            const uint32_t p_local = smem_u32(tiles);
+            const bool vec = ((reinterpret_cast<uintptr_t>(pr.c) & 15) == 0) && ((pr.c_hi_i & 3) == 0) &&
+                             (!pr.addend || (reinterpret_cast<uintptr_t>(pr.addend) & 15) == 0);
+            for (int i = tid; i < total; i += TM_CONV_THREADS) {
+                const int rr = split * rows_per + i / C4, c4 = i % C4;
+                const int m = m0 + rr, n = n0 + c4 * 4;
+                if (m >= pr.M || n >= pr.N) continue;
+                const uint32_t off = p_local + (uint32_t)((rr * (Cfg::PW + 4) + c4 * 4) * 4);
+                float4 part[8];
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp)
+                    if (sp < cns) {
+                        uint32_t ra;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(off), "r"(sp));
+                        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(part[sp].x), "=f"(part[sp].y), "=f"(part[sp].z), "=f"(part[sp].w)
+                                     : "r"(ra)
+                                     : "memory");
+                    }
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp)
+                    if (sp < cns) {
+                        v[0] += part[sp].x; v[1] += part[sp].y; v[2] += part[sp].z; v[3] += part[sp].w;
+                    }
+                const long long o = (long long)m * pr.c_hi_i + n;
+                if (vec && n + 3 < pr.N) {
+                    if (pr.bias) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] += __ldg(pr.bias + n + j);
+                    }
+                    if (pr.addend) {
+                        const float4 a = *reinterpret_cast<const float4*>(pr.addend + o);
+                        v[0] = a.x + v[0]; v[1] = a.y + v[1]; v[2] = a.z + v[2]; v[3] = a.w + v[3];
+                    }
+                    *reinterpret_cast<float4*>(pr.c + o) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (n + j >= pr.N) break;
+                        float w = v[j];
+                        if (pr.bias) w += __ldg(pr.bias + n + j);
+                        if (pr.addend) w = pr.addend[o + j] + w;
+                        pr.c[o + j] = w;
+                    }
+                }
+            }
+        }
+        // nobody leaves (and frees its shared memory) while a neighbour may still be reading it
+        asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+    }
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
@@ -521,7 +663,12 @@ inline int launch_tma_bn(const TBatch& tb, int maxM, int maxN, int totz, cudaStr
     }
     dim3 grid((maxN + BN - 1) / BN, (maxM + TC_BM - 1) / TC_BM, totz);
     if (grid.y > 65535 || grid.z > 65535) return NASREC_ETOOBIG;
-    nasrec_launch(gemm_tma_kernel<BN>, grid, TM_THREADS, Cfg::SMEM_BYTES, st, tb);
+    if (tb.cluster_ns > 1) {
+        // clusters of 192 KB CTAs need the non-portable opt-in only above 8; ns <= 8 here
+        nasrec_launch_cluster(gemm_tma_kernel<BN>, grid, TM_THREADS, Cfg::SMEM_BYTES, st, tb.cluster_ns, tb);
+    } else {
+        nasrec_launch(gemm_tma_kernel<BN>, grid, TM_THREADS, Cfg::SMEM_BYTES, st, tb);
+    }
     return (int)cudaGetLastError();
 }
 

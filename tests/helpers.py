@@ -47,3 +47,62 @@ def relu_kink_margin(sd, cfg, choice, int_x, cat_x):
     finally:
         torch.relu = orig
     return min(rec) if rec else 1.0
+
+
+def relu_kink_candidates(sd, cfg, choice, int_x, cat_x, margin=6e-6, most=6):
+    """ReLU inputs of the oracle forward that lie within `margin` (relative to the median |input| of their call) of
+    zero: [(relative distance, relu call index, flat element index, value)], closest first.  These are the units whose
+    side two correct fp32 implementations may legitimately disagree on."""
+    import torch
+    from oracle import nasrec_oracle as orc
+    rec = []
+    orig = torch.relu
+
+    def spy(x):
+        a = x.detach().abs().flatten()
+        med = float(a.median())
+        if med > 0:
+            near = torch.nonzero(a < margin * med).flatten().tolist()
+            for i in near[:most]:
+                rec.append((float(a[i]) / med, spy.calls, int(i), float(x.detach().flatten()[i])))
+        spy.calls += 1
+        return orig(x)
+
+    spy.calls = 0
+    torch.relu = spy
+    try:
+        with torch.no_grad():
+            orc.supernet_forward(sd, cfg, choice, int_x, cat_x)
+    finally:
+        torch.relu = orig
+    return sorted(rec)[:most]
+
+
+class flipped_relu:
+    """Context manager: inside it, the oracle's ReLU call number `call` sees element `idx` moved across zero (a constant
+    offset of minus twice its value on that one element -- everything stays differentiable)."""
+
+    def __init__(self, call, idx, val):
+        self.call, self.idx, self.val = call, idx, val
+
+    def __enter__(self):
+        import torch
+        self.orig = torch.relu
+        count = [0]
+
+        def relu(x):
+            c = count[0]
+            count[0] += 1
+            if c == self.call:
+                off = torch.zeros_like(x).flatten()
+                off[self.idx] = -2.0 * self.val
+                x = x + off.view_as(x)
+            return self.orig(x)
+
+        torch.relu = relu
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.relu = self.orig
+        return False
