@@ -481,6 +481,28 @@ def measure_training(env, cfg, trainer, K, W, profile_gemm=True):
         env.barrier()
         out["gemm"] = _lib.LIB.gemm_prof_stop()
         out["gemm_pass_ms_per_step"] = sum(a.elapsed_time(b) for a, b in evp) / K
+        # kernel pass: the same K steps once more with an event pair around EVERY launch of the library (both streams),
+        # aggregated by kernel name -- each kernel's time inside the real step (warm L2), not ncu's cold serialised replays
+        import tempfile
+        tf = tempfile.NamedTemporaryFile("r", suffix=".trace", delete=False)
+        os.environ["NASREC_TRACE_FILE"] = tf.name
+        env.barrier()
+        _lib.query("nasrec_host_prof", 10)
+        for i in range(K):
+            flush.zero_()
+            trainer.step(*pool_d[(W + i) % NP])
+        env.barrier()
+        n_traced = _lib.query("nasrec_host_prof", 11)
+        rows = [l.rsplit(" ", 2) for l in open(tf.name).read().splitlines() if l.strip()]
+        os.unlink(tf.name)
+        os.environ.pop("NASREC_TRACE_FILE", None)
+        tot = sum(float(r[2]) for r in rows) or 1.0
+        top = sorted(rows, key=lambda r: -float(r[2]))[:14]
+        out["kernel_trace"] = {"launches_per_step": n_traced / K, "sum_us_per_step": tot / K,
+                               "note": "CUDA events around every launch inside the native step (both streams; event records between "
+                                       "launches suppress programmatic dependent launch, so the sum exceeds ms_per_step)",
+                               "top": [{"kernel": r[0].split("(")[0][-48:], "launches_per_step": round(int(r[1]) / K, 2),
+                                        "us_per_step": round(float(r[2]) / K, 1), "share": round(float(r[2]) / tot, 4)} for r in top]}
     # pipelined (back-to-back, one event pair; informational)
     env.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -746,6 +768,8 @@ def run_ours(args):
                 line["dp_consistent"] = cons
             if r["gemm"] is not None and r["gemm"][1] > 0:
                 line["roofline"] = roofline_of(r["gemm"], r["ms_per_step"], K, r.get("gemm_pass_ms_per_step"))
+            if r.get("kernel_trace"):
+                line["kernel_trace"] = r["kernel_trace"]
         del trainer, model
         torch.cuda.empty_cache()
         # the other BASELINE configs ride along as `extra` on the default line

@@ -81,6 +81,11 @@ int nasrec_side_join(void* stream);
  * pre-split planes have been announced with nasrec_set_weight_planes; anything else takes the LDG-producer
  * kernel.  Both paths use the same arithmetic and agree to the last bit. */
 int nasrec_set_gemm_tma(int on);
+/* Contractions of at most `k` elements (one or two k-tiles: 13 dense features, 16-wide FM / DotProduct projections, 26..64
+ * sparse rows) run on the CUDA-core kernel instead of the tensor-core pipeline, whose set-up (TMEM allocation, tensor maps,
+ * mbarrier ring) costs more than such a problem; fp32-parity modes (3, 4) only.  Default 0 = off (the generic CUDA-core
+ * kernel measured slower inside the training step).  Returns the previous value. */
+int nasrec_set_small_k(int k);
 /* Pre-split copies of a [rows, cols] weight W (modules.py nn.LazyLinear weights keep the reference layout, whose
  * row stride such as 1037 floats no tensor map can describe, and whose second concat source starts at column
  * nd = 13 or F = 26, which no TMA box can start at): hi = rn_tf32(W), lo = W - hi, both [rows, ldp] with

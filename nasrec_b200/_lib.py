@@ -78,7 +78,7 @@ _SIGS_I64 = {
 _SIGS_I64["nasrec_tensor_map_stats"] = [_i]
 _SIGS_I64["nasrec_host_prof"] = [_i]
 EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace",
-           "nasrec_set_side_stream", "nasrec_side_join", "nasrec_set_gemm_tma",
+           "nasrec_set_side_stream", "nasrec_side_join", "nasrec_set_gemm_tma", "nasrec_set_small_k",
            "nasrec_set_weight_planes", "nasrec_gemm_prof"] + list(_SIGS) + list(_SIGS_I64)
 
 
@@ -118,6 +118,8 @@ class _Lib:
         self.cdll.nasrec_get_gemm_mode.restype = C.c_int
         self.cdll.nasrec_set_gemm_tma.argtypes = [C.c_int]
         self.cdll.nasrec_set_gemm_tma.restype = C.c_int
+        self.cdll.nasrec_set_small_k.argtypes = [C.c_int]
+        self.cdll.nasrec_set_small_k.restype = C.c_int
         self.cdll.nasrec_set_weight_planes.argtypes = [_f, _f, _f, _l, _i, _i, _i]
         self.cdll.nasrec_set_weight_planes.restype = C.c_int
         tma = os.environ.get("NASREC_GEMM_TMA")
@@ -145,6 +147,11 @@ class _Lib:
         """TMA-fed operand path of the tensor-core GEMM on/off (both paths agree bit for bit)."""
         self.load()
         self.cdll.nasrec_set_gemm_tma(1 if on else 0)
+
+    def set_small_k(self, k: int) -> int:
+        """Largest contraction length served by the CUDA-core kernel instead of the tensor-core pipeline (0 = never)."""
+        self.load()
+        return int(self.cdll.nasrec_set_small_k(int(k)))
 
     def set_weight_planes(self, W: int, hi: int, lo: int, ldp: int, rows: int, cols: int, first: int = 0):
         self.load()

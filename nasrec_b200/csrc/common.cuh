@@ -87,6 +87,13 @@ __device__ __forceinline__ void pdl_enter() {
 // host-side launch accounting (nasrec_host_prof): nanoseconds spent inside cudaLaunchKernelEx and the number of launches
 extern long long g_nasrec_launch_ns, g_nasrec_launch_count;
 extern int g_nasrec_host_prof;
+// device-side trace (nasrec_host_prof(10 / 11)): CUDA events around EVERY kernel launch of the library on its own stream,
+// aggregated by kernel name -- per-kernel time inside the real step (warm L2, both streams), which ncu's serialised
+// cold-cache replays cannot give.  The event records sit between launches, so programmatic dependent launch does not
+// overlap across them: the traced step is a little slower than the timed one; shares, not absolutes.
+extern int g_nasrec_trace;
+void nasrec_trace_begin(const void* func, cudaStream_t st);
+void nasrec_trace_end(cudaStream_t st);
 static inline long long nasrec_now_ns() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -114,6 +121,12 @@ static inline cudaError_t nasrec_launch_cluster(void (*kernel)(KArgs...), dim3 g
         attr[1].val.clusterDim.z = (unsigned)cluster_z;
         cfg.numAttrs = 2;
     }
+    if (g_nasrec_trace) {
+        nasrec_trace_begin(reinterpret_cast<const void*>(kernel), st);
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+        nasrec_trace_end(st);
+        return e;
+    }
     if (g_nasrec_host_prof) {
         const long long t0 = nasrec_now_ns();
         const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
@@ -137,6 +150,12 @@ static inline cudaError_t nasrec_launch(void (*kernel)(KArgs...), dim3 grid, dim
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (g_nasrec_trace) {
+        nasrec_trace_begin(reinterpret_cast<const void*>(kernel), st);
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+        nasrec_trace_end(st);
+        return e;
+    }
     if (g_nasrec_host_prof) {
         const long long t0 = nasrec_now_ns();
         const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

@@ -223,7 +223,21 @@ struct ProfScope {
     }
 };
 
+// Contractions of at most g_small_k elements (one or two k-tiles: the 13 dense features, a 16-wide FM / DotProduct
+// projection, 26..64 sparse rows) skip the tensor-core kernels: TMEM allocation, tensor maps and the mbarrier pipeline cost
+// ~7 us per launch before the first MMA.  OFF by default (0): measured inside the B = 512 step the generic CUDA-core
+// kernel below (scalar view loads) takes ~19 us per launch against ~13 us for the tensor-core kernels on the same
+// problems (1.57 vs 1.49 ms per step, profiles/r02_notes.md); the switch stays for a kernel that earns it.  fp32-parity
+// modes only: the bf16 mode keeps its operand rounding.  NASREC_SMALL_K / nasrec_set_small_k override.
+int g_small_k = getenv("NASREC_SMALL_K") ? atoi(getenv("NASREC_SMALL_K")) : 0;
 int g_gemm_mode = 3;   // 0: fp32 FFMA; 1/3/4: tcgen05 kind::tf32 with 1/3/4 split products (default 3xTF32); 2: bf16 operands
+
+inline bool small_k_mode() { return g_small_k > 0 && g_gemm_mode >= 3; }
+inline long long seg_total(const nasrec_seg_t* segs, int nseg) {
+    long long k = 0;
+    for (int s = 0; s < nseg; ++s) k += segs[s].width;
+    return k;
+}
 
 View plain_view(const float* p, long long si, long long sj, int contig_j) {
     View v{};
@@ -263,7 +277,12 @@ nasrec_gemm::TilePlan plan_launch(const Prob* prob, int nprob, KTiles ktiles_of,
         else if (getenv("NASREC_SPLIT_VERBOSE"))
             fprintf(stderr, "split launch %d kind %d nprob %d M %d N %d maxN %d\n", id, g_plan_kind, nprob, prob[0].M, prob[0].N, maxN);
     }
-    const nasrec_gemm::TilePlan pl = nasrec_gemm::tc_plan(prob, nprob, maxN, ktiles_of, eligible, g_plan_kind);
+    // SM budget of backward launches (experiment knob; measured: planning the two backward streams for half of the SMs
+    // each changes nothing on the B = 512 step, 1.566 vs 1.574 ms).  Must not depend on whether a side stream is attached:
+    // the Python engine and the executor have to plan -- and round -- alike.
+    static const int bwd_sms = getenv("NASREC_BWD_SMS") ? atoi(getenv("NASREC_BWD_SMS")) : nasrec_gemm::TC_SM_COUNT;
+    const int budget = g_plan_kind != 0 ? bwd_sms : nasrec_gemm::TC_SM_COUNT;
+    const nasrec_gemm::TilePlan pl = nasrec_gemm::tc_plan(prob, nprob, maxN, ktiles_of, eligible, g_plan_kind, budget);
     if (lo >= 0 && eligible && getenv("NASREC_SPLIT_VERBOSE"))
         fprintf(stderr, "   plan bn %d ns %d ktiles %d nterm %d c %p ldc %lld bias %p addend %p\n", pl.bn, pl.ns, ktiles_of(0), prob[0].nterm,
                 (void*)prob[0].c, (long long)prob[0].c_hi_i, (const void*)prob[0].bias, (const void*)prob[0].addend);
@@ -322,7 +341,13 @@ int launch(Batch& bt, cudaStream_t st) {
         for (int t = 0; t < bt.prob[p].nterm; ++t) k += bt.term[bt.prob[p].term0 + t].K;
         return k;
     }));
-    if (g_gemm_mode != 0) {
+    bool small = small_k_mode();
+    for (int p = 0; p < bt.nprob && small; ++p) {
+        long long k = 0;
+        for (int t = 0; t < bt.prob[p].nterm; ++t) k += bt.term[bt.prob[p].term0 + t].K;
+        small = k <= g_small_k;
+    }
+    if (g_gemm_mode != 0 && !small) {
         RedBatch rb{};
         const nasrec_gemm::TilePlan pl = plan_launch(bt.prob, bt.nprob, [&](int p) {
             int kt = 0;
@@ -798,7 +823,7 @@ int nasrec_seg_linear_fwd(const nasrec_seg_t* segs, int nseg, const float* W, in
                           const float* bias, float* C, int64_t ldc, int M, void* stream) {
     g_plan_kind = 0;
     CHECK_ARG(segs_ok(segs, nseg) && W && C && M > 0 && N > 0 && n_off >= 0);
-    {
+    if (!(small_k_mode() && seg_total(segs, nseg) <= g_small_k)) {
         const int rc = tma_seg_fwd(segs, nseg, W, ldw, n_off, N, bias, C, ldc, M, as_stream(stream));
         if (rc != NOT_TMA) return rc;
     }
@@ -829,7 +854,7 @@ int nasrec_seg_linear_dgrad(const float* dC, int64_t ldc, int N, const float* W,
                             const nasrec_seg_t* dsegs, int nseg, int M, int accumulate, void* stream) {
     g_plan_kind = 1;
     CHECK_ARG(segs_ok(dsegs, nseg) && dC && W && M > 0 && N > 0);
-    {
+    if (!(small_k_mode() && N <= g_small_k)) {
         const int rc = tma_seg_dgrad(dC, ldc, N, W, ldw, n_off, dsegs, nseg, M, accumulate, as_stream(stream));
         if (rc != NOT_TMA) return rc;
     }
@@ -895,7 +920,7 @@ int nasrec_sproj_fwd(const nasrec_seg_t* segs, int nseg, const float* W, int64_t
                      float* Z, int64_t z_bstride, int B, void* stream) {
     g_plan_kind = 2;
     CHECK_ARG(segs_ok(segs, nseg) && W && Z && B > 0 && P > 0);
-    {
+    if (!(small_k_mode() && seg_total(segs, nseg) <= g_small_k)) {
         const int rc = tma_sproj_fwd(segs, nseg, W, ldw, P, bias, Z, z_bstride, B, as_stream(stream));
         if (rc != NOT_TMA) return rc;
     }
@@ -935,7 +960,7 @@ int nasrec_sproj_dgrad(const float* dZ, int64_t dz_bstride, int P, const float* 
                        const nasrec_seg_t* dsegs, int nseg, int B, int accumulate, void* stream) {
     g_plan_kind = 2;
     CHECK_ARG(segs_ok(dsegs, nseg) && dZ && W && B > 0 && P > 0);
-    {
+    if (!(small_k_mode() && P <= g_small_k)) {
         const int rc = tma_sproj_dgrad(dZ, dz_bstride, P, W, ldw, dsegs, nseg, B, accumulate, as_stream(stream));
         if (rc != NOT_TMA) return rc;
     }
@@ -1069,7 +1094,8 @@ int nasrec_sproj_wgrad(const float* dZ, int64_t dz_bstride, int P, const nasrec_
     // thread-block clusters with a DSMEM reduction in the TMA kernel, library workspace + reduction launch in the
     // LDG-producer kernel (plan_launch).  `ws` is used only by the large-batch path above.
     g_plan_kind = 2;
-    if (B > 1024) return sproj_wgrad_presplit(dZ, dz_bstride, P, segs, nseg, dW, ldw, B, accumulate, ws, stream);
+    static const bool old_path = getenv("NASREC_SPROJ_WGRAD_OLD") != nullptr;      // experiment knob
+    if (B > 1024 || old_path) return sproj_wgrad_presplit(dZ, dz_bstride, P, segs, nseg, dW, ldw, B, accumulate, ws, stream);
     CHECK_ARG(segs_ok(segs, nseg) && dZ && dW && B > 0 && P > 0);
     Batch bt{};
     int np = 0;
@@ -1156,6 +1182,12 @@ int nasrec_gemm_prof(int what, double* out3) {
         }
     }
     return 0;
+}
+
+int nasrec_set_small_k(int k) {
+    const int old = g_small_k;
+    g_small_k = k < 0 ? 0 : k;
+    return old;
 }
 
 int nasrec_set_gemm_tma(int on) {

@@ -513,7 +513,9 @@ inline long long tc_cta_count(const Batch& bt, int bn) { return tc_cta_count(bt.
 //     partial tiles through distributed shared memory (no workspace, no second launch, ~1 us); the LDG-producer kernel
 //     uses the library workspace and a reduction launch with the SAME split count and summation order, so the two kernels
 //     agree bit for bit;
-//   * a launch costs whole waves of 148 CTAs.
+//   * a launch costs whole waves of 148 CTAs -- of `sm_budget` CTAs when the caller knows that another stream's GEMMs run
+//     concurrently (backward: the weight-gradient GEMMs on the side stream and the dY -> dX chain on the main one each plan
+//     for half of the SMs, so that they overlap instead of queueing behind each other's full-GPU launches).
 // Constraint from numerics: the tensor core truncates when it accumulates, so the chain of MMAs into one accumulator is
 // bounded -- 128-wide tiles have two accumulators and are used only when a CTA walks <= 16 k-tiles.
 // NASREC_TC_BN / NASREC_TC_NS force the choice (experiments); NASREC_TILE_POLICY=1 restores the round-1 narrow-tile rule.
@@ -532,7 +534,7 @@ inline int tc_split_for(long long ctas, int ktiles) {
 // kind: 0 forward-like (both operands K-major), 1 dgrad-like (weight planes MN-major: bn / 32 boxes per plane and k-tile),
 // 2 wgrad-like (both operands MN-major, the B tile split in shared memory by the converter warps)
 template <class KTiles>
-inline TilePlan tc_plan(const Prob* prob, int nprob, int maxN, KTiles ktiles_of, bool can_split, int kind) {
+inline TilePlan tc_plan(const Prob* prob, int nprob, int maxN, KTiles ktiles_of, bool can_split, int kind, int sm_budget = TC_SM_COUNT) {
     static const int forced_bn = getenv("NASREC_TC_BN") ? atoi(getenv("NASREC_TC_BN")) : 0;
     static const int forced_ns = getenv("NASREC_TC_NS") ? atoi(getenv("NASREC_TC_NS")) : 0;
     static const int policy = getenv("NASREC_TILE_POLICY") ? atoi(getenv("NASREC_TILE_POLICY")) : 3;
@@ -567,7 +569,9 @@ inline TilePlan tc_plan(const Prob* prob, int nprob, int maxN, KTiles ktiles_of,
             if (bn == 128 && walk > 16 && !forced_bn) continue;
             const double cta = 3.5 + walk * tt[w] + (ns > 1 ? 0.3 + 0.1 * (bn / 32) : 0.0);
             const long long ctas = tiles * ns;
-            const double t = 2.5 + (double)((ctas + capacity[li] - 1) / capacity[li]) * cta + 0.002 * (double)ctas / TC_SM_COUNT;
+            int cap = capacity[li] < sm_budget ? capacity[li] : sm_budget / ns * ns;
+            if (cap < ns) cap = ns;
+            const double t = 2.5 + (double)((ctas + cap - 1) / cap) * cta + 0.002 * (double)ctas / TC_SM_COUNT;
             if (t < best_t) {
                 best_t = t;
                 best = TilePlan{bn, ns};

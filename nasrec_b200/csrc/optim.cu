@@ -7,8 +7,39 @@
 // which in eager PyTorch are ~10 elementwise launches per parameter tensor.
 #include "common.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
 long long g_nasrec_launch_ns = 0, g_nasrec_launch_count = 0;
 int g_nasrec_host_prof = 0;
+int g_nasrec_trace = 0;
+
+namespace {
+struct TraceRec {
+    const void* func;
+    cudaEvent_t e0, e1;
+};
+std::vector<TraceRec> g_trace;
+size_t g_trace_used = 0;
+}  // namespace
+
+void nasrec_trace_begin(const void* func, cudaStream_t st) {
+    if (g_trace_used == g_trace.size()) {
+        TraceRec r{};
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        g_trace.push_back(r);
+    }
+    g_trace[g_trace_used].func = func;
+    cudaEventRecord(g_trace[g_trace_used].e0, st);
+}
+void nasrec_trace_end(cudaStream_t st) {
+    cudaEventRecord(g_trace[g_trace_used].e1, st);
+    ++g_trace_used;
+}
 
 namespace {
 
@@ -214,6 +245,29 @@ int64_t nasrec_host_prof(int what) {
         case 0: g_nasrec_host_prof = 0; return 0;
         case 1: g_nasrec_host_prof = 1; g_nasrec_launch_ns = 0; g_nasrec_launch_count = 0; return 0;
         case 2: return g_nasrec_launch_ns;
+        case 10: g_nasrec_trace = 1; g_trace_used = 0; return 0;
+        case 11: {            // stop; synchronise; append "name launches total_us" lines to $NASREC_TRACE_FILE; returns launches
+            g_nasrec_trace = 0;
+            std::map<std::string, std::pair<long long, double>> agg;
+            for (size_t i = 0; i < g_trace_used; ++i) {
+                cudaEventSynchronize(g_trace[i].e1);
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, g_trace[i].e0, g_trace[i].e1) != cudaSuccess) continue;
+                const char* name = nullptr;
+                if (cudaFuncGetName(&name, g_trace[i].func) != cudaSuccess || !name) name = "?";
+                auto& a = agg[name];
+                a.first += 1;
+                a.second += ms * 1e3;
+            }
+            if (const char* path = getenv("NASREC_TRACE_FILE")) {
+                if (FILE* f = fopen(path, "a")) {
+                    for (auto& kv : agg) fprintf(f, "%s %lld %.1f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+                    fclose(f);
+                }
+            }
+            cudaGetLastError();
+            return (int64_t)g_trace_used;
+        }
         default: return g_nasrec_launch_count;
     }
 }

@@ -39,13 +39,17 @@ def _tma_launches():
 def _both(fn):
     """Run fn() with the TMA path off, then on; returns (ldg_result, tma_result) and asserts TMA was really taken."""
     L = _lib()
-    L.LIB.set_gemm_tma(False)
-    a = fn()
-    L.LIB.set_gemm_tma(True)
-    before = _tma_launches()
-    b = fn()
-    torch.cuda.synchronize()
-    assert _tma_launches() > before, "the launch did not qualify for the TMA path"
+    small = L.LIB.set_small_k(0)          # this file is about the two tensor-core kernels: no CUDA-core shortcut for short K
+    try:
+        L.LIB.set_gemm_tma(False)
+        a = fn()
+        L.LIB.set_gemm_tma(True)
+        before = _tma_launches()
+        b = fn()
+        torch.cuda.synchronize()
+        assert _tma_launches() > before, "the launch did not qualify for the TMA path"
+    finally:
+        L.LIB.set_small_k(small)
     return a, b
 
 
@@ -201,3 +205,38 @@ def test_adagrad_keeps_planes_in_step():
         assert torch.equal(w, wr) and torch.equal(s, sr)
         hi, lo, _, _ = _planes(w, f)
         assert torch.equal(pl[0], hi) and torch.equal(pl[1], lo)
+
+
+@pytest.mark.parametrize("M,N,widths", [(512, 1024, [16]), (512, 1024, [13]), (512, 16, [13]), (300, 64, [13, 48])])
+def test_small_k_cuda_core_path(M, N, widths):
+    """K <= 64 goes to the CUDA-core kernel (nasrec_set_small_k): same contract, against fp64, and the tensor-core path
+    agrees to the 3xTF32 error level.  Replaces the narrow linears of modules.py:171 (dense stem), :340 / :385 (16-wide
+    DotProduct / FM projections)."""
+    L = _lib()
+    g = torch.Generator().manual_seed(5)
+    offs, o = [], 0
+    for w in widths:
+        offs.append(o)
+        o += w
+    Ktot = o
+    xs = [torch.randn(M, (w + 3) & ~3, generator=g).cuda() for w in widths]
+    W = (torch.randn(N, Ktot, generator=g) / np.sqrt(Ktot)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    dC = torch.randn(M, N, generator=g).cuda()
+    sp, ns = L.segs([(x.data_ptr(), x.stride(0), w, off) for x, w, off in zip(xs, widths, offs)])
+    ref = sum(x[:, :w].double() @ W[:, off:off + w].double().t() for x, w, off in zip(xs, widths, offs)) + bias.double()
+    outs = []
+    for k in (64, 0):
+        old = L.LIB.set_small_k(k)
+        try:
+            before = _tma_launches()
+            C = torch.zeros(M, N, device="cuda")
+            L.call("nasrec_seg_linear_fwd", sp, ns, W.data_ptr(), Ktot, 0, N, bias.data_ptr(), C.data_ptr(), N, M)
+            torch.cuda.synchronize()
+            if k:
+                assert _tma_launches() == before
+        finally:
+            L.LIB.set_small_k(old)
+        assert _rel(C, ref) < 5e-6
+        outs.append(C)
+    assert _rel(outs[0], outs[1].double()) < 5e-6
