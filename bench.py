@@ -469,7 +469,13 @@ def measure_training(env, cfg, trainer, K, W, profile_gemm=True):
            "gemm": None}
     if profile_gemm:
         # roofline pass: the same K steps again with the library recording a CUDA-event pair around every GEMM launch
-        # (kept apart from the timed pass above: two event records per launch are not free at ~70 launches per step)
+        # (kept apart from the timed pass above: two event records per launch are not free at ~70 launches per step).
+        # The pass runs on ONE stream (no weight-gradient side stream): with two streams a launch's event pair also
+        # counts the time it waits for SMs held by the other stream's GEMM, and the per-kernel times summed past the step.
+        nt = getattr(trainer, "_nt", trainer)
+        had_overlap = getattr(nt, "overlap_wgrad", None)
+        if had_overlap:
+            nt.overlap_wgrad = False
         evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         env.barrier()
         _lib.LIB.gemm_prof_start()
@@ -499,10 +505,13 @@ def measure_training(env, cfg, trainer, K, W, profile_gemm=True):
         tot = sum(float(r[2]) for r in rows) or 1.0
         top = sorted(rows, key=lambda r: -float(r[2]))[:14]
         out["kernel_trace"] = {"launches_per_step": n_traced / K, "sum_us_per_step": tot / K,
-                               "note": "CUDA events around every launch inside the native step (both streams; event records between "
-                                       "launches suppress programmatic dependent launch, so the sum exceeds ms_per_step)",
+                               "note": "CUDA events around every launch inside the native step, run on one stream (no side-stream overlap; "
+                                       "event records between launches also suppress programmatic dependent launch, so the sum "
+                                       "exceeds ms_per_step)",
                                "top": [{"kernel": r[0].split("(")[0][-48:], "launches_per_step": round(int(r[1]) / K, 2),
                                         "us_per_step": round(float(r[2]) / K, 1), "share": round(float(r[2]) / tot, 4)} for r in top]}
+        if had_overlap:
+            nt.overlap_wgrad = True
     # pipelined (back-to-back, one event pair; informational)
     env.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -564,13 +573,14 @@ def roofline_of(gemm, ms_per_step, K, pass_ms_per_step=None):
             "gemm_mode": _lib.LIB.gemm_mode(), "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": which,
             "attainable_frac_note": "3xTF32 spends three TF32 MMAs (half the bf16 rate each) per algorithmic product: <= 1/6",
-            "traffic": 2.3e6,
-            "traffic_source": "mean dram__bytes_read+write per GEMM launch of this workload, ncu --set full "
-                              "(profiles/r02_gemm.md); operands are mostly L2-resident, the kernel is not HBM-bound",
+            "traffic": 6.2e6,
+            "traffic_source": "mean dram__bytes_read+write over 6 gemm_tma_kernel launches inside this workload's step, ncu --set "
+                              "full, cold caches (profiles/r02_notes.md); in the live step the operands are mostly L2-resident, "
+                              "the kernel is not HBM-bound",
             "launches_timed": n, "avg_launch_us": ms * 1e3 / max(n, 1), "gflop_per_launch": fl / max(n, 1) / 1e9,
             "gemm_ms_per_step": ms / K, "instrumented_ms_per_step": ms_per_step, "share_of_step": (ms / K) / ms_per_step,
-            "share_note": "CUDA-event time of every GEMM launch inside the timed native steps (both streams; the weight-"
-                          "gradient GEMMs overlap the dY->dX chain, so shares of overlapped work can sum past 1)"}
+            "share_note": "CUDA-event time of every GEMM launch of K native steps run on one stream (no side-stream overlap), "
+                          "over the duration of those same steps (instrumented_ms_per_step)"}
 
 
 def measure_ea(env, cfg, n_per_rank=8, n_batches=EA_BATCHES):
@@ -639,8 +649,18 @@ def measure_ea(env, cfg, n_per_rank=8, n_batches=EA_BATCHES):
 
 
 def measure_hbm_kernels(env, B=8192):
-    """HBM-bound kernels named by the north star, alone, at the evaluation batch: achieved GB/s of ALGORITHMIC bytes
-    (gather F*(8+64+64) B/sample; row-wise Adagrad u*(64*5) B) against the measured copy peak."""
+    """HBM-bound kernels named by the north star, alone, at the evaluation batch and at 4x that: achieved GB/s of
+    ALGORITHMIC bytes (gather F*(8+64+64) B/sample; row-wise Adagrad u*(64*5) B) against the measured copy
+    peak.  At B = 8192 these kernels move 8-30 MB, i.e. 1-5 us of HBM time behind a ~5 us chain of dependent latencies
+    (launch, id -> row address -> row): the second size separates that floor from the streaming rate."""
+    out = _measure_hbm_kernels(env, B)
+    big = _measure_hbm_kernels(env, 4 * B, ln=False)
+    big.pop("peak_GBps", None)
+    out.update(big)
+    return out
+
+
+def _measure_hbm_kernels(env, B, ln=True):
     torch, dev = env.torch, env.dev
     from nasrec_b200 import _lib
     try:
@@ -698,6 +718,9 @@ def measure_hbm_kernels(env, B=8192):
                                      sp.data_ptr(), B, F, 0.12, 1e-2, None))
         by = u * (64 * 5 + 8)
         out["emb_rowwise_adagrad_%s_B%d" % (tag, B)] = {"us": t * 1e6, "GBps": by / t / 1e9, "frac_of_measured_hbm": by / t / 1e9 / peak}
+    out["peak_GBps"] = peak
+    if not ln:
+        return out
     # LayerNorm + ReLU + prefix mask over [B, 1024] (the epilogue of every dense linear)
     x = torch.randn(B, 1024, device=dev)
     g = torch.ones(1024, device=dev)

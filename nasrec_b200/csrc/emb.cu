@@ -11,24 +11,46 @@
 
 namespace {
 
+// Four (pair, quarter-row) items per thread, a block apart, with every index load, then every row load, then every store
+// issued together: the kernel is a chain of three dependent memory latencies (id -> row address -> row), and at the
+// evaluation batch it is only ~30 MB, so what counts is how many of those chains a thread keeps in flight.
+constexpr int GATHER_UNR = 4;
 __global__ void __launch_bounds__(256) emb_gather_kernel(const float* const* __restrict__ tables,
                                                          const int64_t* __restrict__ num_rows,
                                                          const int64_t* __restrict__ idx,
                                                          float* __restrict__ out, long long n_pairs, int F,
                                                          int* err_flag) {
     pdl_enter();
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long pair = t >> 2;          // (b,f) flattened, same order as idx and out
-    if (pair >= n_pairs) return;
-    const int q = (int)(t & 3);
-    const int f = (int)(pair % F);
-    long long row = idx[pair];
-    if ((unsigned long long)row >= (unsigned long long)num_rows[f]) {
-        if (err_flag) atomicOr(err_flag, 1);
-        row = 0;
+    const long long t0 = blockIdx.x * (long long)(blockDim.x * GATHER_UNR) + threadIdx.x;
+    long long pair[GATHER_UNR], row[GATHER_UNR];
+    int f[GATHER_UNR];
+    bool ok[GATHER_UNR];
+#pragma unroll
+    for (int u = 0; u < GATHER_UNR; ++u) {
+        const long long t = t0 + (long long)u * blockDim.x;
+        pair[u] = t >> 2;                   // (b,f) flattened, same order as idx and out
+        ok[u] = pair[u] < n_pairs;
+        row[u] = ok[u] ? idx[pair[u]] : 0;
+        f[u] = (int)(pair[u] % F);
     }
-    const float4 v = __ldg(reinterpret_cast<const float4*>(tables[f] + row * NASREC_EMB_DIM) + q);
-    reinterpret_cast<float4*>(out + pair * NASREC_EMB_DIM)[q] = v;
+    const float4* src[GATHER_UNR];
+    bool bad = false;
+#pragma unroll
+    for (int u = 0; u < GATHER_UNR; ++u) {
+        if (ok[u] && (unsigned long long)row[u] >= (unsigned long long)num_rows[f[u]]) {
+            bad = true;
+            row[u] = 0;
+        }
+        src[u] = reinterpret_cast<const float4*>(tables[ok[u] ? f[u] : 0] + row[u] * NASREC_EMB_DIM) + (int)((t0 + (long long)u * blockDim.x) & 3);
+    }
+    if (bad && err_flag) atomicOr(err_flag, 1);
+    float4 v[GATHER_UNR];
+#pragma unroll
+    for (int u = 0; u < GATHER_UNR; ++u)
+        if (ok[u]) v[u] = __ldg(src[u]);
+#pragma unroll
+    for (int u = 0; u < GATHER_UNR; ++u)
+        if (ok[u]) __stcs(reinterpret_cast<float4*>(out + pair[u] * NASREC_EMB_DIM) + (int)((t0 + (long long)u * blockDim.x) & 3), v[u]);
 }
 
 // One CTA per table: bitonic sort of (row << 32 | sample) keys in shared memory,
@@ -166,6 +188,9 @@ __global__ void __launch_bounds__(256) emb_to_dense_kernel(const int64_t* __rest
     }
 }
 
+// Four unique rows per 16-lane group (64 per CTA), all of their loads in flight before the first use: per row the kernel is
+// a chain id -> (state, weight, gradient) -> two stores, i.e. latency, not bytes, at the sizes of a step.
+constexpr int ADAGRAD_UNR = 4;
 __global__ void __launch_bounds__(256) emb_adagrad_kernel(const int64_t* __restrict__ uniq,
                                                           const int* __restrict__ nuniq,
                                                           const float* __restrict__ row_grad,
@@ -175,14 +200,35 @@ __global__ void __launch_bounds__(256) emb_adagrad_kernel(const int64_t* __restr
     pdl_enter();
     const int f = blockIdx.y;
     const int U = nuniq[f];
-    const int e = threadIdx.x & 15;
+    const int e = threadIdx.x & 15, g = threadIdx.x >> 4;
+    const int u0 = blockIdx.x * (16 * ADAGRAD_UNR) + g;
+    if (u0 >= U) return;
     const float coef = clip_coef ? clip_coef[0] : 1.f;
-    for (int u = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); u < U; u += gridDim.x * (blockDim.x >> 4)) {
-        const long long o = uniq[(long long)f * B + u] * NASREC_EMB_DIM + e;
-        const float g = row_grad[((long long)f * B + u) * NASREC_EMB_DIM + e] * coef;
-        const float s = states[f][o] + g * g;
-        states[f][o] = s;
-        tables[f][o] = tables[f][o] - lr * (g / (sqrtf(s) + eps));
+    float* const tab = tables[f];
+    float* const sta = states[f];
+    long long o[ADAGRAD_UNR];
+    bool ok[ADAGRAD_UNR];
+#pragma unroll
+    for (int j = 0; j < ADAGRAD_UNR; ++j) {
+        const int u = u0 + 16 * j;
+        ok[j] = u < U;
+        o[j] = ok[j] ? uniq[(long long)f * B + u] * NASREC_EMB_DIM + e : 0;
+    }
+    float gr[ADAGRAD_UNR], st[ADAGRAD_UNR], w[ADAGRAD_UNR];
+#pragma unroll
+    for (int j = 0; j < ADAGRAD_UNR; ++j) {
+        if (!ok[j]) continue;
+        gr[j] = row_grad[((long long)f * B + u0 + 16 * j) * NASREC_EMB_DIM + e];
+        st[j] = sta[o[j]];
+        w[j] = tab[o[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < ADAGRAD_UNR; ++j) {
+        if (!ok[j]) continue;
+        const float gg = gr[j] * coef;
+        const float s2 = st[j] + gg * gg;
+        sta[o[j]] = s2;
+        tab[o[j]] = w[j] - lr * (gg / (sqrtf(s2) + eps));
     }
 }
 
@@ -199,8 +245,8 @@ int nasrec_emb_gather_fwd(const float* const* tables, const int64_t* num_rows, c
                           int B, int F, int* err_flag, void* stream) {
     CHECK_ARG(tables && num_rows && idx && out && B > 0 && F > 0);
     const long long n_pairs = (long long)B * F;
-    nasrec_launch(emb_gather_kernel, cdiv(n_pairs * 4, 256), 256, 0, as_stream(stream), tables, num_rows, idx, out, n_pairs, F,
-                                                                            err_flag);
+    nasrec_launch(emb_gather_kernel, cdiv(n_pairs * 4, 256 * GATHER_UNR), 256, 0, as_stream(stream), tables, num_rows, idx, out,
+                  n_pairs, F, err_flag);
     return nasrec_launch_status();
 }
 
@@ -242,7 +288,7 @@ int nasrec_emb_rowwise_adagrad(const int64_t* uniq, const int* nuniq, const floa
                                float* const* states, int B, int F, float lr, float eps, const float* clip_coef,
                                void* stream) {
     CHECK_ARG(uniq && nuniq && row_grad && tables && states && B > 0 && F > 0);
-    dim3 grid(cdiv(B, 16), F);
+    dim3 grid(cdiv(B, 16 * ADAGRAD_UNR), F);
     nasrec_launch(emb_adagrad_kernel, grid, 256, 0, as_stream(stream), uniq, nuniq, row_grad, tables, states, B, lr, eps,
                                                             clip_coef);
     return nasrec_launch_status();

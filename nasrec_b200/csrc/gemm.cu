@@ -125,6 +125,106 @@ __global__ void __launch_bounds__(256) gemm64_kernel(const __grid_constant__ Bat
     }
 }
 
+// Short contractions (total K <= SK_KMAX: the 13 dense features, 16-wide FM / DotProduct projections, 26..64 sparse rows
+// or projection channels).  Same contract as gemm64_kernel (Batch of strided views, any operand layout), but the WHOLE K
+// range of a 64 x 64 output tile is fetched at once -- every load in flight before the first use, one barrier -- so the
+// kernel is one global-memory latency long instead of one per 16-wide k-slab; ~9 KB of registers' worth of loads per
+// thread, 35 KB of shared memory, no tensor-memory allocation, several CTAs per SM (a successor launched with
+// programmatic dependent launch becomes resident while this one drains).  For these shapes the tensor-core kernels pay
+// ~5 us per CTA before their first MMA, times the number of waves: an [8192 x 64 x 64] sparse-axis projection with seven
+// gradient targets took 49 us there (profiles/r02_notes.md).
+constexpr int SK_KMAX = 64;
+__global__ void __launch_bounds__(256) gemm_smallk_kernel(const __grid_constant__ Batch bt) {
+    pdl_trigger();
+    __shared__ __align__(16) float As[SK_KMAX][BM + PADM];
+    __shared__ __align__(16) float Bs[SK_KMAX][BN + PADM];
+    __shared__ int kterm[SK_KMAX], kin[SK_KMAX];
+    int pi = blockIdx.z;
+    if (pi >= bt.nprob) return;
+    const Prob& pr = bt.prob[pi];
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (m0 >= pr.M || n0 >= pr.N) return;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    // k -> (term, k inside the term)
+    int Ktot = 0;
+    for (int t = 0; t < pr.nterm; ++t) Ktot += bt.term[pr.term0 + t].K;
+    if (tid < SK_KMAX) {
+        int k = tid, t = 0;
+        while (t < pr.nterm && k >= bt.term[pr.term0 + t].K) { k -= bt.term[pr.term0 + t].K; ++t; }
+        kterm[tid] = t < pr.nterm ? pr.term0 + t : -1;
+        kin[tid] = k;
+    }
+    __syncthreads();
+    pdl_wait();
+    // operand tiles: thread -> (row i, column k) chosen so that a warp reads along the operand's contiguous axis
+    const bool a_kc = bt.term[pr.term0].a.contig_j != 0, b_kc = bt.term[pr.term0].b.contig_j != 0;
+    float va[16], vb[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        // 64 x 64 elements = 16 per thread.  k-contiguous: 16 consecutive k per row group (tid & 15 = k low); else tid & 63 = i
+        const int ka = a_kc ? ((tid & 15) + 16 * (q & 3)) : ((tid >> 6) + 4 * q);
+        const int ia = a_kc ? ((tid >> 4) + 16 * (q >> 2)) : (tid & 63);
+        float v = 0.f;
+        if (ka < Ktot && m0 + ia < pr.M) {
+            const Term& tm = bt.term[kterm[ka]];
+            v = __ldg(tm.a.p + voff(tm.a, m0 + ia, kin[ka]));
+        }
+        va[q] = v;
+        const int kb = b_kc ? ((tid & 15) + 16 * (q & 3)) : ((tid >> 6) + 4 * q);
+        const int ib = b_kc ? ((tid >> 4) + 16 * (q >> 2)) : (tid & 63);
+        v = 0.f;
+        if (kb < Ktot && n0 + ib < pr.N) {
+            const Term& tm = bt.term[kterm[kb]];
+            v = __ldg(tm.b.p + voff(tm.b, n0 + ib, kin[kb]));
+        }
+        vb[q] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int ka = a_kc ? ((tid & 15) + 16 * (q & 3)) : ((tid >> 6) + 4 * q);
+        const int ia = a_kc ? ((tid >> 4) + 16 * (q >> 2)) : (tid & 63);
+        As[ka][ia] = va[q];
+        const int kb = b_kc ? ((tid & 15) + 16 * (q & 3)) : ((tid >> 6) + 4 * q);
+        const int ib = b_kc ? ((tid >> 4) + 16 * (q >> 2)) : (tid & 63);
+        Bs[kb][ib] = vb[q];
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    const int kend = Ktot < SK_KMAX ? Ktot : SK_KMAX;
+#pragma unroll 4
+    for (int j = 0; j < kend; ++j) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[j][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[j][tx * 4]);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    const int cmask = (1 << pr.c_sh_i) - 1;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int m = m0 + ty * 4 + r;
+        if (m >= pr.M) continue;
+        const long long ro = (long long)(m >> pr.c_sh_i) * pr.c_hi_i + (long long)(m & cmask) * pr.c_lo_i;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int n = n0 + tx * 4 + c;
+            if (n >= pr.N) continue;
+            const long long o = ro + (long long)n * pr.c_hi_j;
+            float v = acc[r][c];
+            if (pr.bias) v += __ldg(pr.bias + n);
+            if (pr.addend) v += pr.addend[o];
+            pr.c[o] = v;
+        }
+    }
+}
+
 struct RedSeg {
     const float* ws;      // [nsplit][M][N] partial sums
     float* c;             // destination, row stride ldc
@@ -363,7 +463,19 @@ int launch(Batch& bt, cudaStream_t st) {
     }
     dim3 grid(cdiv(maxN, BN), cdiv(maxM, BM), totz);
     if (grid.y > 65535 || grid.z > 65535) return NASREC_ETOOBIG;
-    nasrec_launch(gemm64_kernel, grid, 256, 0, st, bt);
+    bool whole_k = small && totz == bt.nprob;          // short contraction, no caller-imposed split: one-shot kernel
+    for (int p = 0; p < bt.nprob && whole_k; ++p) {
+        long long k = 0;
+        for (int t = 0; t < bt.prob[p].nterm; ++t) {
+            k += bt.term[bt.prob[p].term0 + t].K;
+            // one layout flag per operand and problem decides the thread -> element mapping
+            if (bt.term[bt.prob[p].term0 + t].a.contig_j != bt.term[bt.prob[p].term0].a.contig_j ||
+                bt.term[bt.prob[p].term0 + t].b.contig_j != bt.term[bt.prob[p].term0].b.contig_j) whole_k = false;
+        }
+        if (k > SK_KMAX) whole_k = false;
+    }
+    if (whole_k) nasrec_launch(gemm_smallk_kernel, grid, 256, 0, st, bt);
+    else nasrec_launch(gemm64_kernel, grid, 256, 0, st, bt);
     return nasrec_launch_status();
 }
 

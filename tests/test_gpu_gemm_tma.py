@@ -240,3 +240,40 @@ def test_small_k_cuda_core_path(M, N, widths):
         assert _rel(C, ref) < 5e-6
         outs.append(C)
     assert _rel(outs[0], outs[1].double()) < 5e-6
+
+
+@pytest.mark.parametrize("B,P,rows", [(512, 64, [26]), (257, 45, [26, 30]), (64, 16, [10, 8, 40])])
+def test_small_k_sparse_projection(B, P, rows):
+    """Sparse-axis projections with short contractions (K = rows <= 64 forward, K = P <= 64 backward) on the one-shot
+    CUDA-core kernel, several gradient targets in one launch (ElasticLinear3D / DotProduct, modules.py:223-262, 340-359)."""
+    L = _lib()
+    g = torch.Generator().manual_seed(7)
+    E = 16
+    offs, o = [], 0
+    for r in rows:
+        offs.append(o)
+        o += r
+    Stot = o
+    xs = [torch.randn(B, r + 2, E, generator=g).cuda() for r in rows]
+    W = (torch.randn(P, Stot, generator=g) / np.sqrt(Stot)).cuda()
+    bias = torch.randn(P, generator=g).cuda()
+    dZ = torch.randn(B, P, E, generator=g).cuda()
+    sp, ns = L.segs([(x.data_ptr(), x.stride(0), r, off) for x, r, off in zip(xs, rows, offs)])
+    old = L.LIB.set_small_k(64)
+    try:
+        before = _tma_launches()
+        Z = torch.zeros(B, P, E, device="cuda")
+        L.call("nasrec_sproj_fwd", sp, ns, W.data_ptr(), Stot, P, bias.data_ptr(), Z.data_ptr(), P * E, B)
+        dxs = [torch.full_like(x, 0.25) for x in xs]
+        dsp, _ = L.segs([(d.data_ptr(), d.stride(0), r, off) for d, r, off in zip(dxs, rows, offs)])
+        L.call("nasrec_sproj_dgrad", dZ.data_ptr(), P * E, P, W.data_ptr(), Stot, dsp, ns, B, 1)
+        torch.cuda.synchronize()
+        if Stot <= 64:
+            assert _tma_launches() == before
+    finally:
+        L.LIB.set_small_k(old)
+    ref = sum(torch.einsum("pr,bre->bpe", W[:, off:off + r].double(), x[:, :r].double()) for x, r, off in zip(xs, rows, offs))
+    assert _rel(Z, ref + bias.double()[None, :, None]) < 5e-6
+    for d, r, off in zip(dxs, rows, offs):
+        assert _rel(d[:, :r], torch.einsum("bpe,pr->bre", dZ.double(), W[:, off:off + r].double()) + 0.25) < 5e-6
+        assert float((d[:, r:] - 0.25).abs().max()) == 0.0
