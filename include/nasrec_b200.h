@@ -81,6 +81,16 @@ int nasrec_side_join(void* stream);
  * pre-split planes have been announced with nasrec_set_weight_planes; anything else takes the LDG-producer
  * kernel.  Both paths use the same arithmetic and agree to the last bit. */
 int nasrec_set_gemm_tma(int on);
+/* Deferred weight gradients.  dW of a linear is read only by the optimizer, so while deferral is on,
+ * nasrec_seg_linear_wgrad (and the op-level backward entry points built on it) only QUEUE their work when it qualifies for
+ * the TMA kernel; nasrec_wgrad_flush(stream) then runs everything queued as one batched launch -- one grid over the output
+ * tiles of all queued problems (up to 64 problems per launch) -- on `stream`.  Operands (dC, the input segments, dW) must stay
+ * valid and unchanged until the flush; a call with accumulate != 0 drains the queue and runs at once.  Switching deferral off
+ * drops the queue (flush first).  nasrec_wgrad_defer returns the previous setting; nasrec_wgrad_pending the queue length.
+ * The step executor (nasrec_net_forward_backward) does this by itself unless nasrec_net_set_defer_wgrad(net, 0). */
+int nasrec_wgrad_defer(int on);
+int nasrec_wgrad_flush(void* stream);
+int64_t nasrec_wgrad_pending(void);
 /* Contractions of at most `k` elements (one or two k-tiles: 13 dense features, 16-wide FM / DotProduct projections, 26..64
  * sparse rows) run on the CUDA-core kernel instead of the tensor-core pipeline, whose set-up (TMEM allocation, tensor maps,
  * mbarrier ring) costs more than such a problem; fp32-parity modes (3, 4) only.  Default 0 = off (the generic CUDA-core
@@ -360,6 +370,7 @@ int nasrec_net_set_planes(void* net, float* const* hi, float* const* lo, const i
  * two later calls never run out of arena after the step's gradients exist. */
 int nasrec_net_set_reserve(void* net, int rows);
 int nasrec_net_set_overlap(void* net, int on);      /* join the side stream (nasrec_set_side_stream) after backward */
+int nasrec_net_set_defer_wgrad(void* net, int on); /* queue dense weight gradients during backward, one batched launch at its end (default on) */
 /* Data-parallel overlap: during nasrec_net_forward_backward, cb(offset_bytes, nbytes) is called on the host each
  * time a block's parameter gradients are final -- the byte range of the gradient bucket sealed since the last call,
  * already ordered on `stream` -- so the caller can start all-reducing it while backward continues.  NULL: off. */

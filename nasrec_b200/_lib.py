@@ -34,6 +34,7 @@ _SIGS = {
     "nasrec_seg_linear_fwd": ([_f, _i, _f, _l, _i, _i, _f, _f, _l, _i, _f], 1),
     "nasrec_seg_linear_dgrad": ([_f, _l, _i, _f, _l, _i, _f, _i, _i, _i, _f], 1),
     "nasrec_seg_linear_wgrad": ([_f, _l, _i, _f, _i, _f, _l, _i, _i, _i, _f], 1),
+    "nasrec_wgrad_flush": ([_f], 1),
     "nasrec_colsum": ([_f, _l, _i, _i, _f, _i, _f], 1),
     "nasrec_sproj_fwd": ([_f, _i, _f, _l, _i, _f, _f, _l, _i, _f], 1),
     "nasrec_sproj_dgrad": ([_f, _l, _i, _f, _l, _f, _i, _i, _i, _f], 1),
@@ -77,8 +78,9 @@ _SIGS_I64 = {
 }
 _SIGS_I64["nasrec_tensor_map_stats"] = [_i]
 _SIGS_I64["nasrec_host_prof"] = [_i]
+_SIGS_I64["nasrec_wgrad_pending"] = []
 EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace",
-           "nasrec_set_side_stream", "nasrec_side_join", "nasrec_set_gemm_tma", "nasrec_set_small_k",
+           "nasrec_set_side_stream", "nasrec_side_join", "nasrec_set_gemm_tma", "nasrec_set_small_k", "nasrec_wgrad_defer",
            "nasrec_set_weight_planes", "nasrec_gemm_prof"] + list(_SIGS) + list(_SIGS_I64)
 
 
@@ -118,6 +120,8 @@ class _Lib:
         self.cdll.nasrec_get_gemm_mode.restype = C.c_int
         self.cdll.nasrec_set_gemm_tma.argtypes = [C.c_int]
         self.cdll.nasrec_set_gemm_tma.restype = C.c_int
+        self.cdll.nasrec_wgrad_defer.argtypes = [C.c_int]
+        self.cdll.nasrec_wgrad_defer.restype = C.c_int
         self.cdll.nasrec_set_small_k.argtypes = [C.c_int]
         self.cdll.nasrec_set_small_k.restype = C.c_int
         self.cdll.nasrec_set_weight_planes.argtypes = [_f, _f, _f, _l, _i, _i, _i]

@@ -172,6 +172,9 @@ void nasrec_internal_workspace(float** ws, long long* nfloats);
 // `accumulate`; cleared by that call): lets the op-level backward entry points serve fresh and accumulated gradient
 // targets with one launch
 void nasrec_internal_set_dgrad_flags(const int* flags);
+// fork: returns the side stream ordered after everything issued to `main` so far (or `main` itself when none is attached);
+// the work must be joined with nasrec_side_join
+cudaStream_t nasrec_internal_fork_side(cudaStream_t main);
 // optional second stream on which the op-level backward entry points issue weight-gradient work
 cudaStream_t nasrec_internal_side_stream();
 void nasrec_internal_set_side_stream(cudaStream_t s);

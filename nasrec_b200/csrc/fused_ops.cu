@@ -52,6 +52,8 @@ cudaStream_t fork_for_wgrad(cudaStream_t main) {
 }
 }  // namespace
 
+cudaStream_t nasrec_internal_fork_side(cudaStream_t main) { return fork_for_wgrad(main); }
+
 extern "C" {
 
 int nasrec_set_side_stream(void* stream) {

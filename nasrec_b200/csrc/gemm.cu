@@ -653,10 +653,11 @@ MapSpec spec3d(const float* base, uint64_t rows, uint64_t B, long long bstride) 
     return sp;
 }
 // Work description filled by the entry points before the tile width is known.
-struct TmaJob {
-    TBatch tb;
-    MapSpec spec[nasrec_gemm::TM_MAXMAPS];
-    int side[nasrec_gemm::TM_MAXMAPS];     // 0: A operand map, 1: B operand map
+template <class TB, int MAPS>
+struct TmaJobT {
+    TB tb;
+    MapSpec spec[MAPS];
+    int side[MAPS];     // 0: A operand map, 1: B operand map
     int nmap = 0;
     int a_kind = 0, b_kind = 0, a_conv = 1, b_conv = 0;
     int add(const MapSpec& sp, int which) {
@@ -664,23 +665,30 @@ struct TmaJob {
         side[nmap] = which;
         return nmap++;
     }
+    void reset() {
+        nmap = 0;
+        std::memset(&tb.nprob, 0, sizeof(TB) - offsetof(TB, nprob));
+    }
 };
-TmaJob* g_job = nullptr;       // one reusable job (host-side scratch; the library is single-threaded per process)
+using TmaJob = TmaJobT<TBatch, nasrec_gemm::TM_MAXMAPS>;
+using TmaJobBig = TmaJobT<nasrec_gemm::TBatchBig, nasrec_gemm::BIG_MAPS>;
+TmaJob* g_job = nullptr;       // reusable jobs (host-side scratch; the library is single-threaded per process)
+TmaJobBig* g_big_job = nullptr;
 
 TmaJob& fresh_job() {
     if (!g_job) g_job = new TmaJob();
-    g_job->nmap = 0;
-    std::memset(&g_job->tb.nprob, 0, sizeof(TBatch) - offsetof(TBatch, nprob));
+    g_job->reset();
     return *g_job;
 }
-
-template <int BNv>
-int launch_tma_job(TmaJob& job, int maxM, int maxN, int totz, cudaStream_t st) {
-    return nasrec_gemm::launch_tma_bn<BNv>(job.tb, maxM, maxN, totz, st);
+TmaJobBig& fresh_big_job() {
+    if (!g_big_job) g_big_job = new TmaJobBig();
+    g_big_job->reset();
+    return *g_big_job;
 }
 
-int run_tma(TmaJob& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
-    TBatch& tb = job.tb;
+template <class Job>
+int run_tma(Job& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
+    auto& tb = job.tb;
     int maxM = 0, maxN = 0, totz = 0;
     for (int i = 0; i < tb.nprob; ++i) {
         maxM = tb.prob[i].M > maxM ? tb.prob[i].M : maxM;
@@ -704,6 +712,7 @@ int run_tma(TmaJob& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
         for (int t = 0; t < tb.prob[0].nterm; ++t) k += tb.term[tb.prob[0].term0 + t].K;
         g_prof.desc[prof.slot] = GemmProf::Desc{tb.prob[0].M, maxN, k, tb.nprob, g_plan_kind, pl.bn, pl.ns, 1};
     }
+    if (getenv("NASREC_WGRAD_VERBOSE") && tb.flat) fprintf(stderr, "   plan bn %d ns %d\n", pl.bn, pl.ns);
     tb.cluster_ns = pl.ns;             // split-K inside thread-block clusters (DSMEM reduction in the kernel)
     if (pl.ns > 1) totz *= pl.ns;      // eligible launches have nsplit == 1 everywhere: z = problem * ns + split
     tb.nprod = g_gemm_mode;
@@ -715,12 +724,22 @@ int run_tma(TmaJob& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
         set_box(job.spec[i], job.side[i] ? job.b_kind : job.a_kind, job.side[i] ? bn : nasrec_gemm::TC_BM);
         if (!get_map(&tb.maps[i], job.spec[i])) return NASREC_EINVAL;
     }
+    dim3 grid((maxN + bn - 1) / bn, (maxM + nasrec_gemm::TC_BM - 1) / nasrec_gemm::TC_BM, totz);
+    if (tb.flat) {
+        // one CTA (or cluster) per REAL output tile: running tile totals per problem; flat launches carry no pre-split problems
+        int tot = 0;
+        for (int i = 0; i < tb.nprob; ++i) {
+            tot += ((tb.prob[i].M + nasrec_gemm::TC_BM - 1) / nasrec_gemm::TC_BM) * ((tb.prob[i].N + bn - 1) / bn);
+            tb.tile_end[i] = tot;
+        }
+        grid = dim3((unsigned)tot, 1, (unsigned)(pl.ns > 1 ? pl.ns : 1));
+    }
     int rc;
     switch (bn) {
-        case 16: rc = launch_tma_job<16>(job, maxM, maxN, totz, st); break;
-        case 32: rc = launch_tma_job<32>(job, maxM, maxN, totz, st); break;
-        case 64: rc = launch_tma_job<64>(job, maxM, maxN, totz, st); break;
-        default: rc = launch_tma_job<128>(job, maxM, maxN, totz, st); break;
+        case 16: rc = nasrec_gemm::launch_tma_bn<16>(tb, grid, st); break;
+        case 32: rc = nasrec_gemm::launch_tma_bn<32>(tb, grid, st); break;
+        case 64: rc = nasrec_gemm::launch_tma_bn<64>(tb, grid, st); break;
+        default: rc = nasrec_gemm::launch_tma_bn<128>(tb, grid, st); break;
     }
     if (rc) return rc;
     ++g_tma_launches;
@@ -801,6 +820,69 @@ int tma_seg_dgrad(const float* dC, int64_t ldc, int N, const float* W, int64_t l
     return run_tma(job, st);
 }
 
+// ---- deferred weight gradients (nasrec_wgrad_defer / nasrec_wgrad_flush) -------------------------------------------------
+// dW of a linear is read only by the optimizer.  Launched one by one behind their LayerNorm backward, the ~13 dense
+// weight-gradient GEMMs of a B = 512 step each pay the ~6 us launch floor, fill the SMs unevenly (one problem per
+// launch) and -- on the side stream -- take SMs from the dY -> dX chain exactly while it is the critical path
+// (event-timed launches in the step are ~1.6x their isolated duration).  Deferred, they wait in a queue (operands are
+// step-lifetime buffers of the caller) and run as ONE grid over all their output tiles when the backward pass is done:
+// same kernel, one launch floor, full waves, nothing competing with the chain.
+struct PendingWgrad {
+    const float* dC;
+    int64_t ldc;
+    int N;
+    nasrec_seg_t segs[NASREC_MAX_SEGS];
+    int nseg;
+    float* dW;
+    int64_t ldw;
+    int n_off, M;
+};
+std::vector<PendingWgrad> g_wq;
+bool g_wdefer = false;
+
+int wgrad_flush(cudaStream_t st) {
+    size_t i = 0;
+    const int saved_kind = g_plan_kind;
+    g_plan_kind = 2;
+    int rc = 0;
+    while (i < g_wq.size() && rc == 0) {
+        TmaJobBig& job = fresh_big_job();
+        job.a_kind = OP_MN128; job.a_conv = 1; job.b_kind = OP_MN128; job.b_conv = 1;
+        auto& tb = job.tb;
+        int np = 0;
+        const int M = g_wq[i].M;            // a batch shares the contraction length (the batch size of the step)
+        for (; i < g_wq.size(); ++i) {
+            const PendingWgrad& w = g_wq[i];
+            if (w.M != M || np + w.nseg > nasrec_gemm::BIG_P || job.nmap + 1 + w.nseg > nasrec_gemm::BIG_MAPS) break;
+            const int ah = job.add(spec2d(w.dC, w.N, w.M, w.ldc), 0);
+            for (int s = 0; s < w.nseg; ++s) {
+                Prob& p = tb.prob[np];
+                TTerm& t = tb.term[np];
+                p.M = w.N; p.N = (int)w.segs[s].width; p.term0 = np; p.nterm = 1;
+                p.c = w.dW + (long long)w.n_off * w.ldw + w.segs[s].w_off; p.c_hi_i = w.ldw; p.c_hi_j = 1;
+                p.addend = nullptr;
+                p.nsplit = 1;
+                t.K = w.M;
+                t.a_hi = t.a_lo = (short)ah;
+                t.b_hi = t.b_lo = (short)job.add(spec2d(w.segs[s].ptr, w.segs[s].width, w.M, w.segs[s].ld), 1);
+                ++np;
+            }
+        }
+        tb.nprob = np;
+        tb.flat = 1;
+        if (getenv("NASREC_WGRAD_VERBOSE")) {
+            fprintf(stderr, "wgrad batch: %d problems, %d maps\n", np, job.nmap);
+            for (int q = 0; q < np; ++q)
+                fprintf(stderr, "   M %d N %d K %d c %p ldc %lld a %d b %d\n", tb.prob[q].M, tb.prob[q].N, tb.term[q].K, (void*)tb.prob[q].c,
+                        (long long)tb.prob[q].c_hi_i, tb.term[q].a_hi, tb.term[q].b_hi);
+        }
+        rc = np ? run_tma(job, st) : NASREC_EINVAL;
+    }
+    g_wq.clear();
+    g_plan_kind = saved_kind;
+    return rc;
+}
+
 int tma_seg_wgrad(const float* dC, int64_t ldc, int N, const nasrec_seg_t* segs, int nseg, float* dW, int64_t ldw, int n_off,
                   int M, int accumulate, cudaStream_t st) {
     if (!tma_on() || !al16(dC) || (ldc & 3)) return NOT_TMA;
@@ -811,6 +893,21 @@ int tma_seg_wgrad(const float* dC, int64_t ldc, int N, const nasrec_seg_t* segs,
         ++live;
     }
     if (live + 1 > nasrec_gemm::TM_MAXMAPS || live > MAXP) return NOT_TMA;
+    if (g_wdefer && live > 0) {
+        // deferred: the weight gradient is consumed only by the optimizer, so it joins the batched launch of wgrad_flush.
+        // An in-place accumulate may depend on a queued writer of the same rows: drain the queue first, then run it now.
+        if (accumulate) {
+            const int rc = wgrad_flush(st);
+            if (rc) return rc;
+        } else {
+            PendingWgrad pw{};
+            pw.dC = dC; pw.ldc = ldc; pw.N = N; pw.dW = dW; pw.ldw = ldw; pw.n_off = n_off; pw.M = M;
+            for (int s = 0; s < nseg; ++s)
+                if (segs[s].width > 0) pw.segs[pw.nseg++] = segs[s];
+            g_wq.push_back(pw);
+            return 0;
+        }
+    }
     TmaJob& job = fresh_job();
     job.a_kind = OP_MN128; job.a_conv = 1; job.b_kind = OP_MN128; job.b_conv = 1;
     const int ah = job.add(spec2d(dC, N, M, ldc), 0);          // A(i = output row, k = sample) = dC[k*ldc + i]
@@ -1295,6 +1392,20 @@ int nasrec_gemm_prof(int what, double* out3) {
     }
     return 0;
 }
+
+int nasrec_wgrad_defer(int on) {
+    const int old = g_wdefer ? 1 : 0;
+    g_wdefer = on != 0;
+    if (!g_wdefer) g_wq.clear();          // switching off drops what is still queued: flush first
+    return old;
+}
+
+int nasrec_wgrad_flush(void* stream) {
+    if (g_wq.empty()) return 0;
+    return wgrad_flush(as_stream(stream));
+}
+
+int64_t nasrec_wgrad_pending(void) { return (int64_t)g_wq.size(); }
 
 int nasrec_set_small_k(int k) {
     const int old = g_small_k;

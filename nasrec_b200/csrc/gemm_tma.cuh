@@ -59,15 +59,25 @@ struct TTerm {
     int a_base[4], b_base[4];         // coordinates of (row 0, k 0)
 };
 
-struct TBatch {
-    alignas(64) CUtensorMap maps[TM_MAXMAPS];
+// P problems, T terms, MAPS tensor maps.  The everyday launches (one operator direction: <= 16 problems) use the small
+// instance; the batched weight-gradient launch (gemm.cu, wgrad_flush: every deferred weight gradient of a backward pass in
+// one grid) uses the big one -- kernel parameters are copied per launch, so the common case stays at ~5 KB.
+template <int P, int T, int MAPS>
+struct TBatchT {
+    alignas(64) CUtensorMap maps[MAPS];
     int nprob, nprod;
     int cluster_ns;         // > 1: split-K over a thread-block cluster of this many CTAs along z (DSMEM reduction); else 0/1
     int dbg;                // experiment knob (NASREC_GEMM_DBG): 1 no TMA loads, 2 converters idle, 4 no MMAs, 8 no TMEM-slot wait
+    int flat;               // 1: blockIdx.x counts output tiles over ALL problems (tile_end = running totals), so that problems of
+                            // very different sizes share a grid without empty CTAs; 0: grid (N tiles, M tiles, problem x split)
     OpLayout la, lb;
-    Prob prob[MAXP];
-    TTerm term[MAXT];
+    Prob prob[P];
+    TTerm term[T];
+    int tile_end[P];
 };
+using TBatch = TBatchT<MAXP, MAXT, TM_MAXMAPS>;
+constexpr int BIG_P = 64, BIG_MAPS = 96;
+using TBatchBig = TBatchT<BIG_P, BIG_P, BIG_MAPS>;
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -228,8 +238,8 @@ struct TmCfg {
     static_assert(BN <= 128 && NACC_MAX * ACC_STRIDE <= TM_ACC_COLS, "accumulators and A slots share the 512 TMEM columns");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_constant__ TBatch tb) {
+template <int BN, class TB>
+__global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_constant__ TB tb) {
     pdl_trigger();
     using Cfg = TmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -240,8 +250,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     // memory in split order (no workspace, no reduction launch).  Otherwise a problem may carry its own nsplit with
     // partials going to the caller's workspace (sparse-axis projections, which reduce over the batch).
     const int cns = tb.cluster_ns > 1 ? tb.cluster_ns : 1;
-    int z = blockIdx.z, pi = 0;
-    if (cns > 1) {
+    int z = blockIdx.z, pi = 0, tile_m = blockIdx.y, tile_n = blockIdx.x;
+    if (tb.flat) {
+        const int t = blockIdx.x;                   // z is the split index (clusters along z)
+        while (pi < tb.nprob && t >= tb.tile_end[pi]) ++pi;
+        if (pi >= tb.nprob) return;
+        const int local = t - (pi ? tb.tile_end[pi - 1] : 0);
+        const int ntn = (tb.prob[pi].N + BN - 1) / BN;
+        tile_m = local / ntn;
+        tile_n = local - tile_m * ntn;
+    } else if (cns > 1) {
         pi = z / cns;
         z -= pi * cns;
     } else {
@@ -255,7 +273,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     const Prob& pr = tb.prob[pi];
     const int split = z;
     const int nsplit = cns > 1 ? cns : pr.nsplit;
-    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    const int m0 = tile_m * TC_BM, n0 = tile_n * BN;
     if (m0 >= pr.M || n0 >= pr.N) return;          // the whole cluster leaves together (same tile, same problem)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -652,22 +670,21 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     }
 }
 
-template <int BN>
-inline int launch_tma_bn(const TBatch& tb, int maxM, int maxN, int totz, cudaStream_t st) {
+template <int BN, class TB>
+inline int launch_tma_bn(const TB& tb, dim3 grid, cudaStream_t st) {
     using Cfg = TmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<BN, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    dim3 grid((maxN + BN - 1) / BN, (maxM + TC_BM - 1) / TC_BM, totz);
     if (grid.y > 65535 || grid.z > 65535) return NASREC_ETOOBIG;
     if (tb.cluster_ns > 1) {
         // clusters of 192 KB CTAs need the non-portable opt-in only above 8; ns <= 8 here
-        nasrec_launch_cluster(gemm_tma_kernel<BN>, grid, TM_THREADS, Cfg::SMEM_BYTES, st, tb.cluster_ns, tb);
+        nasrec_launch_cluster(gemm_tma_kernel<BN, TB>, grid, TM_THREADS, Cfg::SMEM_BYTES, st, tb.cluster_ns, tb);
     } else {
-        nasrec_launch(gemm_tma_kernel<BN>, grid, TM_THREADS, Cfg::SMEM_BYTES, st, tb);
+        nasrec_launch(gemm_tma_kernel<BN, TB>, grid, TM_THREADS, Cfg::SMEM_BYTES, st, tb);
     }
     return (int)cudaGetLastError();
 }

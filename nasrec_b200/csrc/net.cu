@@ -94,6 +94,7 @@ struct Net {
     int64_t* uniq = nullptr; int* nuniq = nullptr; float* row_grad = nullptr; float* sumsq = nullptr; int sB = 0;
     bool have_sparse = false;
     bool overlap = false;
+    bool defer_wgrad = true;   // dense weight gradients queue up during backward and run as one batched launch (nasrec_wgrad_flush)
     // scratch of nasrec_net_sparse_reduce / nasrec_net_apply, reserved by forward_backward so that those two calls cannot
     // overflow an arena after the step's gradients exist (growing the arenas then would leave them pointing at freed memory)
     int reserve_rows = 0;                     // rows of the (all-gathered) batch the sparse reduction will see
@@ -1034,6 +1035,7 @@ int nasrec_net_set_planes(void* net, float* const* hi, float* const* lo, const i
 }
 
 int nasrec_net_set_overlap(void* net, int on) { ((Net*)net)->overlap = on != 0; return 0; }
+int nasrec_net_set_defer_wgrad(void* net, int on) { ((Net*)net)->defer_wgrad = on != 0; return 0; }
 
 int nasrec_net_set_reserve(void* net, int rows) {
     CHECK_ARG(net && rows >= 0);
@@ -1114,24 +1116,37 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
         // block's first record every gradient written so far is final: seal that part of the bucket.
         size_t sealed = 0;
         int mark = (int)n->block_mark.size() - 1;
+        nasrec_wgrad_defer(n->defer_wgrad ? 1 : 0);
+        // queued weight gradients run as one batched launch per block, on the side stream when one is attached: the batch
+        // then overlaps the dY -> dX chain of the next block instead of extending the step by its ~90 us
+        auto flush_wgrads = [&]() {
+            if (nasrec_wgrad_pending() == 0) return;
+            ck(nasrec_wgrad_flush(n->overlap ? nasrec_internal_fork_side(st) : st), 0);
+        };
         for (size_t i = n->tape.size(); i-- > 0;) {
             n->tape[i]();
-            if (n->seal_cb && mark >= 0 && i == n->block_mark[mark]) {
+            if (mark >= 0 && i == n->block_mark[mark]) {
                 --mark;
-                if (n->pg.off >= sealed + n->seal_min_bytes) {       // few, large exchanges: each one costs host time
-                    if (n->overlap) ck(nasrec_side_join(st), 0);     // the sealed range includes side-stream wgrads
+                flush_wgrads();
+                if (n->seal_cb && n->pg.off >= sealed + n->seal_min_bytes) {       // few, large exchanges: each one costs host time
+                    if (n->overlap) ck(nasrec_side_join(st), 0);     // the sealed range includes side-stream work
                     n->seal_cb((int64_t)sealed, (int64_t)(n->pg.off - sealed));
                     sealed = n->pg.off;
                 }
             }
         }
         n->tape.clear();
+        flush_wgrads();
+        nasrec_wgrad_defer(0);
         if (n->overlap) ck(nasrec_side_join(st), 0);
         if (n->seal_cb && n->pg.off > sealed) n->seal_cb((int64_t)sealed, (int64_t)(n->pg.off - sealed));
         n->pg_dirty = n->pg.off;
         n->step_valid = true;
     });
-    if (rc) n->pg_dirty = n->pg.cap;       // a failed step may have scribbled anywhere in the bucket: clear all of it next time
+    if (rc) {
+        n->pg_dirty = n->pg.cap;       // a failed step may have scribbled anywhere in the bucket: clear all of it next time
+        nasrec_wgrad_defer(0);         // ... and nothing of it may stay queued (turning deferral off drops the queue)
+    }
     return rc;
 }
 

@@ -34,6 +34,7 @@ _PROTOS = {
     "nasrec_net_set_requires_grad": ([_vp, _vp, _i], _i),
     "nasrec_net_set_planes": ([_vp, _vp, _vp, _vp, _vp, _i], _i),
     "nasrec_net_set_overlap": ([_vp, _i], _i),
+    "nasrec_net_set_defer_wgrad": ([_vp, _i], _i),
     "nasrec_net_set_reserve": ([_vp, _i], _i),
     "nasrec_net_set_seal_callback": ([_vp, _vp], _i),
     "nasrec_net_forward": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp], _i),
@@ -406,8 +407,11 @@ class NativeTrainer(FusedTrainer):
     supernet, every parameter's Adagrad state pre-allocated); otherwise it is a FusedTrainer."""
 
     def __init__(self, model: SuperNet, lr: float, eps: float = 1e-2, clip: Optional[float] = 5.0,
-                 overlap_wgrad: bool = True):
+                 overlap_wgrad: bool = True, defer_wgrad: bool = True):
         super().__init__(model, lr, eps, clip)
+        # dense weight gradients queue up during backward and run as one batched launch at its end (nasrec_wgrad_flush);
+        # off = one launch per operator, the Python engine's launch sequence (bit-identical to it)
+        self.defer_wgrad = defer_wgrad
         self.net: Optional[NativeNet] = None
         self.fallback_reason: Optional[str] = None
         # weight-gradient GEMMs on a second stream, off the dY -> dX critical path (joined before the optimizer)
@@ -435,6 +439,8 @@ class NativeTrainer(FusedTrainer):
             if self.fallback_reason is None:
                 try:
                     self.net = NativeNet(m, state_of=self._state_of)
+                    _check(_fn("nasrec_net_set_defer_wgrad")(self.net.handle, 1 if self.defer_wgrad else 0),
+                           "nasrec_net_set_defer_wgrad")
                 except (NotImplementedError, ValueError) as e:      # a model shape the executor does not describe
                     self.fallback_reason = str(e)
         return self.net

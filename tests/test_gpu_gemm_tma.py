@@ -277,3 +277,50 @@ def test_small_k_sparse_projection(B, P, rows):
     for d, r, off in zip(dxs, rows, offs):
         assert _rel(d[:, :r], torch.einsum("bpe,pr->bre", dZ.double(), W[:, off:off + r].double()) + 0.25) < 5e-6
         assert float((d[:, r:] - 0.25).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shapes", [
+    [(512, 1024, [13, 1024]), (512, 64, [416]), (512, 16, [1024, 1024, 128])],      # a block's worth: split-K clusters + flat grid
+    [(512, 1024, [1024] * 3), (512, 1024, [13]), (512, 128, [1024]), (512, 1024, [1035]), (512, 256, [13, 416, 1024])] * 3,
+])
+def test_deferred_weight_gradients_batched_launch(shapes):
+    """nasrec_wgrad_defer / nasrec_wgrad_flush: queued weight gradients of several linears run as one grid over all their
+    output tiles (flat tile index, one plan for the batch); every dW equals the fp64 product and the one-by-one launches
+    to the 3xTF32 error level.  Replaces the per-parameter weight.grad of loss.backward() (train_utils.py:283)."""
+    L = _lib()
+    g = torch.Generator().manual_seed(11)
+    cases = []
+    for M, N, widths in shapes:
+        xs = [torch.randn(M, (w + 3) & ~3, generator=g).cuda() for w in widths]
+        offs, o = [], 0
+        for w in widths:
+            offs.append(o)
+            o += w
+        dC = torch.randn(M, N, generator=g).cuda()
+        cases.append((M, N, widths, xs, offs, o, dC))
+
+    def run(defer):
+        outs = []
+        old = L.LIB.load().cdll.nasrec_wgrad_defer(1 if defer else 0)
+        try:
+            for M, N, widths, xs, offs, Ktot, dC in cases:
+                dW = torch.zeros(N, Ktot, device="cuda")
+                sp, ns = L.segs([(x.data_ptr(), x.stride(0), w, off) for x, w, off in zip(xs, widths, offs)])
+                L.call("nasrec_seg_linear_wgrad", dC.data_ptr(), N, N, sp, ns, dW.data_ptr(), Ktot, 0, M, 0)
+                outs.append(dW)
+            if defer:
+                assert L.query("nasrec_wgrad_pending") == len(cases)
+                assert float(outs[0].abs().max()) == 0.0                  # nothing ran yet
+                L.call("nasrec_wgrad_flush")
+                assert L.query("nasrec_wgrad_pending") == 0
+        finally:
+            L.LIB.cdll.nasrec_wgrad_defer(old)
+        torch.cuda.synchronize()
+        return outs
+
+    one_by_one, batched = run(False), run(True)
+    for (M, N, widths, xs, offs, Ktot, dC), a, b in zip(cases, one_by_one, batched):
+        for x, w, off in zip(xs, widths, offs):
+            ref = dC.double().t() @ x[:, :w].double()
+            assert _rel(b[:, off:off + w], ref) < 5e-6
+            assert _rel(a[:, off:off + w], ref) < 5e-6

@@ -39,7 +39,7 @@ def test_native_steps_are_bit_identical_to_python_engine(name):
         choices += smeta["ea_candidates"]["xlarge"][:4]
     a = _model(cfg, ne, nd, meta["shapes"], 5)
     b = _model(cfg, ne, nd, meta["shapes"], 5)
-    ta, tb = FusedTrainer(a, lr=0.12), NativeTrainer(b, lr=0.12)
+    ta, tb = FusedTrainer(a, lr=0.12), NativeTrainer(b, lr=0.12, defer_wgrad=False)
     for si, ch in enumerate(choices * 2):
         int_x, cat_x, y = (t.cuda() for t in orc.synth_batch(37 + si, nd, ne, seed=40 + si,
                                                              all_zero_dense=(meta.get("dataset") == "avazu")))
@@ -100,7 +100,7 @@ def test_native_forward_and_frozen_modes():
     for m in (a, b):
         _pin(m, ch)
         m.set_mode_to_finelune_last_only()
-    ta, tb = FusedTrainer(a, lr=0.1), NativeTrainer(b, lr=0.1)
+    ta, tb = FusedTrainer(a, lr=0.1), NativeTrainer(b, lr=0.1, defer_wgrad=False)
     before = {k: v.clone() for k, v in b.state_dict().items()}
     for _ in range(3):
         la, _ = ta.step(int_x, cat_x, y)
@@ -128,7 +128,7 @@ def test_native_arena_growth_and_fallback():
     a = _model(cfg, ne, nd, meta["shapes"], 2)
     b = _model(cfg, ne, nd, meta["shapes"], 2)
     ch = meta["cases"][0]["choice"]
-    ta, tb = FusedTrainer(a, lr=0.1), NativeTrainer(b, lr=0.1)
+    ta, tb = FusedTrainer(a, lr=0.1), NativeTrainer(b, lr=0.1, defer_wgrad=False)
     int_x, cat_x, y = (t.cuda() for t in orc.synth_batch(64, nd, ne, seed=5))
     _pin(a, ch)
     _pin(b, ch)
@@ -171,3 +171,33 @@ def test_subnet_evaluator_native_equals_python_engine():
     assert ra == rb
     for ch in cands:
         assert torch.equal(a.logits(ch, batches[0][0], batches[0][1]), b.logits(ch, batches[0][0], batches[0][1]))
+
+
+@pytest.mark.parametrize("name", ["supernet_autoctr_criteo", "supernet_xlarge_kdd"])
+def test_deferred_weight_gradients_match_per_operator_launches(name):
+    """Default executor mode: the dense weight gradients of a backward pass are queued and run as batched launches over
+    all their output tiles (one per block, nasrec_wgrad_defer / nasrec_wgrad_flush) instead of one launch per operator.
+    From identical weights the forward pass -- and with it every ReLU mask -- is bit-identical in both modes, so ONE step
+    isolates the weight gradients: updated weights agree to fp32 summation order (the batched plan may pick another tile
+    width / split-K), nothing stays queued.  (Several steps would compound: a 1e-7 weight difference eventually puts a
+    near-zero ReLU input on the other side, see test_gpu_baseline_sizes.)"""
+    from nasrec_b200 import _lib
+    meta, _ = load_golden(name)
+    cfg, ne, nd = meta["cfg"], meta["num_embeddings"], meta["nd"]
+    for si, case in enumerate(meta["cases"][:4]):
+        ch = case["choice"]
+        a = _model(cfg, ne, nd, meta["shapes"], 9)
+        b = _model(cfg, ne, nd, meta["shapes"], 9)
+        ta, tb = NativeTrainer(a, lr=0.12, defer_wgrad=False), NativeTrainer(b, lr=0.12)
+        int_x, cat_x, y = (t.cuda() for t in orc.synth_batch(300 + si, nd, ne, seed=70 + si))
+        _pin(a, ch)
+        _pin(b, ch)
+        la, lossa = ta.step(int_x, cat_x, y)
+        lb, lossb = tb.step(int_x, cat_x, y)
+        assert tb.net is not None and ta.net is not None
+        assert _lib.query("nasrec_wgrad_pending") == 0
+        assert torch.equal(la, lb) and torch.equal(lossa, lossb)
+        assert abs(float(ta.last_total_norm) - float(tb.last_total_norm)) <= 1e-6 * max(1.0, float(ta.last_total_norm))
+        sa, sb = a.state_dict(), b.state_dict()
+        for k in sa:
+            assert float((sa[k] - sb[k]).abs().max()) <= 2e-6 * max(1e-2, float(sa[k].abs().max())), (si, k)
