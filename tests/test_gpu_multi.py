@@ -28,6 +28,11 @@ def test_data_parallel_two_ranks_consistent(kind):
     assert line, out.stdout[-2000:]
     r = json.loads(line[-1][len("DPCHECK "):])
     assert r["replicas_identical"] is True
-    assert r["max_rel_weight_diff"] < 1e-5, r
+    # 2 x 256 equals 1 x 512 to fp32 summation order: every tensor within 1e-4 in relative L2 and all but a handful of
+    # elements within 1e-5 -- the handful being a unit whose near-zero ReLU input fell on the other side in one of the four
+    # steps (tools/dp_check.py; a rank-1 outlier of at most lr, measured 1.7e-4)
+    assert r["max_rel_l2_diff"] < 1e-4, r
+    assert r["frac_elements_off"] < 1e-4, r
+    assert r["max_rel_weight_diff"] < 5e-3, r
     if kind == "native":
         assert r["native"] is True

@@ -45,13 +45,22 @@ if rank == 0:
         cat = [np.concatenate([pools[r][i][k] for r in range(world)]) for k in range(3)]
         t1.step(*[torch.from_numpy(a).to(dev) for a in cat])
     torch.cuda.synchronize()
-    worst = 0.0
-    for (n, p), q in zip(m.named_parameters(), m1.parameters()):
-        d = float((p - q).abs().max() / (q.abs().max() + 1e-12))
-        worst = max(worst, d)
+    # Elementwise max AND robust measures: over four Adagrad steps a near-zero ReLU input can land on different sides in the
+    # two runs (different GEMM shapes -> different fp32 summation order), which moves one unit's row of one weight by up to
+    # lr -- a rank-1 outlier, not a data-parallel error (tests/test_gpu_baseline_sizes.py pins this effect to the oracle).
+    worst, worst_l2, off, total = 0.0, 0.0, 0, 0
+    with torch.no_grad():
+        for (n, p), q in zip(m.named_parameters(), m1.parameters()):
+            diff = (p - q).abs()
+            scale = float(q.abs().max()) + 1e-12
+            worst = max(worst, float(diff.max()) / scale)
+            worst_l2 = max(worst_l2, float(diff.double().norm() / (q.double().norm() + 1e-12)))
+            off += int((diff > 1e-5 * scale).sum())
+            total += diff.numel()
     import json
     print("DPCHECK " + json.dumps({"kind": kind, "native": getattr(getattr(tr, "_nt", None), "net", None) is not None,
-                                   "replicas_identical": bool(same), "max_rel_weight_diff": worst, "world": world, "B": B}), flush=True)
+                                   "replicas_identical": bool(same), "max_rel_weight_diff": worst, "max_rel_l2_diff": worst_l2,
+                                   "frac_elements_off": off / max(total, 1), "world": world, "B": B}), flush=True)
     print(kind, "| native path used:", getattr(getattr(tr, "_nt", None), "net", None) is not None,
           "| replicas bit-identical:", same, "| dp(2x%d) vs single(%d) max rel weight diff after 4 steps: %.2e" % (B, world * B, worst), flush=True)
 dist.destroy_process_group()
