@@ -138,6 +138,152 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
     }
 }
 
+// ------------------------------------------------------------------ wide rows: four warps per row
+// With one warp per row a [512, 1024] LayerNorm is 512 warps of ~1500 dependent instructions each -- 4 resident warps
+// per SM, ~6 clk per instruction, ~10 us (ncu, warm caches: warps active 6 %, issue active 14 %, profiles/r02_notes.md).
+// For N > 256 a row is split over LNW_WPR = 4 warps (contiguous column quarters, 8 values per lane) and a CTA of 8 warps
+// works on two rows at a time; row sums cross the warps through shared memory and are added in a fixed order.
+constexpr int LNW_WPR = 4;                       // warps per row
+constexpr int LNW_RPC = 8 / LNW_WPR;             // rows per CTA and iteration
+constexpr int LNW_VPT = LN_VPT / LNW_WPR;        // values per lane
+
+__device__ __forceinline__ float lnw_row_sum(float v, float (*red)[LNW_WPR], int g, int q, int lane) {
+    v = warp_sum(v);
+    __syncthreads();                             // the previous use of `red` is over
+    if (lane == 0) red[g][q] = v;
+    __syncthreads();
+    return (red[g][0] + red[g][1]) + (red[g][2] + red[g][3]);
+}
+
+__global__ void __launch_bounds__(256) ln_fwd_wide_kernel(const float* __restrict__ x, long long ldx, int M, int N,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, int relu,
+                                                          int d_out, float* __restrict__ y, long long ldy,
+                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                          int accumulate) {
+    pdl_enter();
+    __shared__ float red[LNW_RPC][LNW_WPR];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = warp / LNW_WPR, q = warp % LNW_WPR;
+    const int row = blockIdx.x * LNW_RPC + g;
+    const bool live = row < M;
+    const float* xr = x + (long long)(live ? row : 0) * ldx;
+    float* yr = y + (long long)(live ? row : 0) * ldy;
+    const int j0 = q * (32 * LNW_VPT) + lane;
+    float v[LNW_VPT], gm[LNW_VPT], bt[LNW_VPT], yo[LNW_VPT];
+#pragma unroll
+    for (int k = 0; k < LNW_VPT; ++k) {
+        const int j = j0 + 32 * k;
+        v[k] = ldg_nc_pred(xr + j, live && j < N);
+        gm[k] = ldg_nc_pred(gamma + j, j < d_out);
+        bt[k] = ldg_nc_pred(beta + j, j < d_out);
+        yo[k] = ld_pred(yr + j, live && accumulate && j < d_out);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LNW_VPT; ++k) s += v[k];
+    const float mean = lnw_row_sum(s, red, g, q, lane) / (float)N;
+    float qq = 0.f;
+#pragma unroll
+    for (int k = 0; k < LNW_VPT; ++k) {
+        const int j = j0 + 32 * k;
+        const float d = j < N ? v[k] - mean : 0.f;
+        qq += d * d;
+    }
+    const float rstd = 1.0f / sqrtf(lnw_row_sum(qq, red, g, q, lane) / (float)N + eps);
+    if (!live) return;
+    if (lane == 0 && q == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < LNW_VPT; ++k) {
+        const int j = j0 + 32 * k;
+        float o = (v[k] - mean) * rstd * gm[k] + bt[k];
+        if (relu) o = fmaxf(o, 0.f);
+        if (j < d_out) yr[j] = accumulate ? yo[k] + o : o;
+    }
+}
+
+// dx for every row; with `part`, this CTA's partial column sums of dgamma / dbeta (part[cta][0|1][j]) for the second stage
+__global__ void __launch_bounds__(256) ln_bwd_wide_kernel(const float* __restrict__ dy, long long lddy, int d_out,
+                                                          const float* __restrict__ x, long long ldx, int M, int N,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const float* __restrict__ mean_in,
+                                                          const float* __restrict__ rstd_in, int relu,
+                                                          float* __restrict__ dx, long long lddx,
+                                                          float* __restrict__ part) {
+    pdl_enter();
+    extern __shared__ float sred[];          // [2][LNW_RPC][N] when part != null
+    __shared__ float red[LNW_RPC][LNW_WPR];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = warp / LNW_WPR, q = warp % LNW_WPR;
+    const int j0 = q * (32 * LNW_VPT) + lane;
+    float accg[LNW_VPT], accb[LNW_VPT], gm[LNW_VPT], bt[LNW_VPT];
+#pragma unroll
+    for (int k = 0; k < LNW_VPT; ++k) {
+        accg[k] = 0.f;
+        accb[k] = 0.f;
+        gm[k] = ldg_nc_pred(gamma + j0 + 32 * k, j0 + 32 * k < d_out);
+        bt[k] = ldg_nc_pred(beta + j0 + 32 * k, j0 + 32 * k < d_out);
+    }
+    for (int r0 = blockIdx.x * LNW_RPC; r0 < M; r0 += gridDim.x * LNW_RPC) {       // uniform trip count per CTA
+        const int row = r0 + g;
+        const bool live = row < M;
+        const float* xr = x + (long long)(live ? row : 0) * ldx;
+        const float* dyr = dy + (long long)(live ? row : 0) * lddy;
+        const float mean = live ? mean_in[row] : 0.f, rstd = live ? rstd_in[row] : 0.f;
+        float xh[LNW_VPT], a[LNW_VPT];
+#pragma unroll
+        for (int k = 0; k < LNW_VPT; ++k) {
+            const int j = j0 + 32 * k;
+            xh[k] = ldg_nc_pred(xr + j, live && j < N);
+            a[k] = ldg_nc_pred(dyr + j, live && j < d_out);
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LNW_VPT; ++k) {
+            const int j = j0 + 32 * k;
+            xh[k] = (live && j < N) ? (xh[k] - mean) * rstd : 0.f;
+            float d = a[k];                                      // 0 beyond d_out
+            if (relu && (xh[k] * gm[k] + bt[k]) <= 0.f) d = 0.f;
+            a[k] = d * gm[k];
+            accg[k] = fmaf(d, xh[k], accg[k]);
+            accb[k] += d;
+            s1 += a[k];
+            s2 += a[k] * xh[k];
+        }
+        const float c1 = lnw_row_sum(s1, red, g, q, lane) / (float)N;
+        const float c2 = lnw_row_sum(s2, red, g, q, lane) / (float)N;
+        if (dx && live) {
+            float* dxr = dx + (long long)row * lddx;
+#pragma unroll
+            for (int k = 0; k < LNW_VPT; ++k) {
+                const int j = j0 + 32 * k;
+                if (j < N) dxr[j] = rstd * (a[k] - c1 - xh[k] * c2);
+            }
+        }
+    }
+    if (!part) return;
+    float* sg = sred;
+    float* sb = sred + LNW_RPC * N;
+#pragma unroll
+    for (int k = 0; k < LNW_VPT; ++k) {
+        const int j = j0 + 32 * k;
+        if (j < N) {
+            sg[g * N + j] = accg[k];
+            sb[g * N + j] = accb[k];
+        }
+    }
+    __syncthreads();
+    float* o = part + (long long)blockIdx.x * 2 * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        o[j] = sg[j] + sg[N + j];
+        o[N + j] = sb[j] + sb[N + j];
+    }
+}
+
 // Second stage of the dgamma/dbeta reduction: part[k][0|1][j], k < nblk.  One CTA per 32 columns; warp r
 // sums partial rows r, r+8, ... (coalesced 128-byte reads, 4 independent loads in flight), then the 8
 // warp totals are added in a fixed order -- deterministic for a given nblk.
@@ -352,6 +498,149 @@ __global__ void __launch_bounds__(128) ln3_bwd_kernel(const float* __restrict__ 
     }
 }
 
+// ---- four warps per sample (same reasoning as the wide row kernels above: one warp per sample leaves 4 resident warps
+// per SM walking ~2000 dependent instructions each).  Warp (g, qw) of a CTA handles sample blockIdx * 2 + g and the rows
+// p = 8 k + 2 qw + ph, k < 8; the two row sums of every (sample, e) cross the four warps through shared memory.
+constexpr int LN3W_V = LN3_V / 4;
+__device__ __forceinline__ float ln3w_sum(float v, float (*red)[4][16], int g, int qw, int e, int ph) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    __syncthreads();
+    if (ph == 0) red[g][qw][e] = v;
+    __syncthreads();
+    return (red[g][0][e] + red[g][1][e]) + (red[g][2][e] + red[g][3][e]);
+}
+
+__global__ void __launch_bounds__(256) ln3_fwd_wide_kernel(const float* __restrict__ z, long long zbs, int B, int P,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, int relu,
+                                                           int p_out, float* __restrict__ y, long long ybs,
+                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                           int accumulate) {
+    pdl_enter();
+    __shared__ float red[2][4][16];
+    const int lane = threadIdx.x & 31, e = lane & 15, ph = lane >> 4, warp = threadIdx.x >> 5;
+    const int g = warp >> 2, qw = warp & 3;
+    const int b = blockIdx.x * 2 + g;
+    const bool live = b < B;
+    const float* zp = z + (long long)(live ? b : 0) * zbs + e;
+    float* yp = y + (long long)(live ? b : 0) * ybs + e;
+    float v[LN3W_V], gm[LN3W_V], bt[LN3W_V], yo[LN3W_V];
+#pragma unroll
+    for (int k = 0; k < LN3W_V; ++k) {
+        const int p = 8 * k + 2 * qw + ph;
+        v[k] = ldg_nc_pred(zp + p * 16, live && p < P);
+        gm[k] = ldg_nc_pred(gamma + p, p < p_out);
+        bt[k] = ldg_nc_pred(beta + p, p < p_out);
+        yo[k] = ld_pred(yp + p * 16, live && accumulate && p < p_out);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN3W_V; ++k) s += v[k];
+    const float mean = ln3w_sum(s, red, g, qw, e, ph) / (float)P;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN3W_V; ++k) {
+        const int p = 8 * k + 2 * qw + ph;
+        const float d = p < P ? v[k] - mean : 0.f;
+        q += d * d;
+    }
+    const float rstd = 1.0f / sqrtf(ln3w_sum(q, red, g, qw, e, ph) / (float)P + eps);
+    if (!live) return;
+    if (ph == 0 && qw == 0) {
+        mean_out[b * 16 + e] = mean;
+        rstd_out[b * 16 + e] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < LN3W_V; ++k) {
+        const int p = 8 * k + 2 * qw + ph;
+        float o = (v[k] - mean) * rstd * gm[k] + bt[k];
+        if (relu) o = fmaxf(o, 0.f);
+        if (p < p_out) yp[p * 16] = accumulate ? yo[k] + o : o;
+    }
+}
+
+__global__ void __launch_bounds__(256) ln3_bwd_wide_kernel(const float* __restrict__ dy, long long dybs, int p_out,
+                                                           const float* __restrict__ z, long long zbs, int B, int P,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           const float* __restrict__ mean_in,
+                                                           const float* __restrict__ rstd_in, int relu,
+                                                           float* __restrict__ dz, long long dzbs,
+                                                           float* __restrict__ part) {
+    pdl_enter();
+    __shared__ float sg[2][LN3_MAXP], sb[2][LN3_MAXP];
+    __shared__ float red[2][4][16];
+    const int lane = threadIdx.x & 31, e = lane & 15, ph = lane >> 4, warp = threadIdx.x >> 5;
+    const int g = warp >> 2, qw = warp & 3;
+    float accg[LN3W_V], accb[LN3W_V], gm[LN3W_V], bt[LN3W_V];
+#pragma unroll
+    for (int k = 0; k < LN3W_V; ++k) {
+        const int p = 8 * k + 2 * qw + ph;
+        accg[k] = 0.f;
+        accb[k] = 0.f;
+        gm[k] = ldg_nc_pred(gamma + p, p < p_out);
+        bt[k] = ldg_nc_pred(beta + p, p < p_out);
+    }
+    for (int b0 = blockIdx.x * 2; b0 < B; b0 += gridDim.x * 2) {              // uniform trip count per CTA
+        const int b = b0 + g;
+        const bool live = b < B;
+        const float* zp = z + (long long)(live ? b : 0) * zbs + e;
+        const float* dp = dy + (long long)(live ? b : 0) * dybs + e;
+        const float mean = live ? mean_in[b * 16 + e] : 0.f, rstd = live ? rstd_in[b * 16 + e] : 0.f;
+        float xh[LN3W_V], a[LN3W_V];
+#pragma unroll
+        for (int k = 0; k < LN3W_V; ++k) {
+            const int p = 8 * k + 2 * qw + ph;
+            xh[k] = ldg_nc_pred(zp + p * 16, live && p < P);
+            a[k] = ldg_nc_pred(dp + p * 16, live && p < p_out);
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN3W_V; ++k) {
+            const int p = 8 * k + 2 * qw + ph;
+            xh[k] = (live && p < P) ? (xh[k] - mean) * rstd : 0.f;
+            float d = a[k];                                      // 0 beyond p_out
+            if (relu && (xh[k] * gm[k] + bt[k]) <= 0.f) d = 0.f;
+            a[k] = d * gm[k];
+            accg[k] = fmaf(d, xh[k], accg[k]);
+            accb[k] += d;
+            s1 += a[k];
+            s2 = fmaf(a[k], xh[k], s2);
+        }
+        const float c1 = ln3w_sum(s1, red, g, qw, e, ph) / (float)P;
+        const float c2 = ln3w_sum(s2, red, g, qw, e, ph) / (float)P;
+        if (dz && live) {
+            float* op = dz + (long long)b * dzbs + e;
+#pragma unroll
+            for (int k = 0; k < LN3W_V; ++k) {
+                const int p = 8 * k + 2 * qw + ph;
+                if (p < P) op[p * 16] = rstd * (a[k] - c1 - xh[k] * c2);
+            }
+        }
+    }
+    if (!part) return;
+    // sum over the 16 embedding columns (lanes with equal ph), then over the CTA's two sample groups
+#pragma unroll
+    for (int k = 0; k < LN3W_V; ++k) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            accg[k] += __shfl_xor_sync(0xffffffffu, accg[k], o);
+            accb[k] += __shfl_xor_sync(0xffffffffu, accb[k], o);
+        }
+        if (e == 0) {
+            sg[g][8 * k + 2 * qw + ph] = accg[k];
+            sb[g][8 * k + 2 * qw + ph] = accb[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < LN3_MAXP) {
+        const int p = threadIdx.x;
+        float* o = part + (long long)blockIdx.x * 2 * LN3_MAXP;
+        o[p] = sg[0][p] + sg[1][p];
+        o[LN3_MAXP + p] = sb[0][p] + sb[1][p];
+    }
+}
+
 // part[k][0|1][p], k < nblk: warp r sums partial rows r, r+8, ...; fixed-order add of the 8 warp totals.
 __global__ void __launch_bounds__(256) ln3_param_final_kernel(const float* __restrict__ part, int nblk, int P,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -486,8 +775,12 @@ int nasrec_ln_fwd(const float* x, int64_t ldx, int M, int N, const float* gamma,
                   void* stream) {
     CHECK_ARG(x && gamma && beta && y && mean && rstd && M > 0 && N > 0 && d_out >= 0 && d_out <= N);
     if (N > LN_MAXN) return NASREC_ETOOBIG;
-    nasrec_launch(ln_fwd_kernel, cdiv(M, 4), 128, 0, as_stream(stream), x, ldx, M, N, gamma, beta, eps, relu, d_out, y, ldy,
-                                                             mean, rstd, accumulate);
+    if (N > 256)
+        nasrec_launch(ln_fwd_wide_kernel, cdiv(M, LNW_RPC), 256, 0, as_stream(stream), x, ldx, M, N, gamma, beta, eps, relu, d_out, y,
+                      ldy, mean, rstd, accumulate);
+    else
+        nasrec_launch(ln_fwd_kernel, cdiv(M, 4), 128, 0, as_stream(stream), x, ldx, M, N, gamma, beta, eps, relu, d_out, y, ldy,
+                                                                 mean, rstd, accumulate);
     return nasrec_launch_status();
 }
 
@@ -506,9 +799,15 @@ int nasrec_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* x, int6
     if (grid > 296) grid = 296;                    // persistent warps: fixed row -> warp assignment
     const bool fused = want && ws && nws >= (long long)grid * 2 * N;
     if (dx || fused) {
-        const size_t smem = fused ? (size_t)8 * N * sizeof(float) : 0;
-        nasrec_launch(ln_bwd_kernel, grid, 128, smem, st, dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx, lddx,
-                                               fused ? ws : nullptr);
+        if (N > 256) {
+            const size_t smem = fused ? (size_t)2 * LNW_RPC * N * sizeof(float) : 0;
+            nasrec_launch(ln_bwd_wide_kernel, grid, 256, smem, st, dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx,
+                          lddx, fused ? ws : nullptr);
+        } else {
+            const size_t smem = fused ? (size_t)8 * N * sizeof(float) : 0;
+            nasrec_launch(ln_bwd_kernel, grid, 128, smem, st, dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx, lddx,
+                                                   fused ? ws : nullptr);
+        }
         int rc = nasrec_launch_status();
         if (rc) return rc;
     }
@@ -529,8 +828,12 @@ int nasrec_ln3_fwd(const float* z, int64_t z_bstride, int B, int P, const float*
                    int accumulate, void* stream) {
     CHECK_ARG(z && gamma && beta && y && mean && rstd && B > 0 && P > 0 && p_out >= 0 && p_out <= P);
     if (P > LN3_MAXP) return NASREC_ETOOBIG;
-    nasrec_launch(ln3_fwd_kernel, cdiv(B, 4), 128, 0, as_stream(stream), z, z_bstride, B, P, gamma, beta, eps, relu, p_out, y,
-                                                             y_bstride, mean, rstd, accumulate);
+    if (P > 16)
+        nasrec_launch(ln3_fwd_wide_kernel, cdiv(B, 2), 256, 0, as_stream(stream), z, z_bstride, B, P, gamma, beta, eps, relu, p_out, y,
+                      y_bstride, mean, rstd, accumulate);
+    else
+        nasrec_launch(ln3_fwd_kernel, cdiv(B, 4), 128, 0, as_stream(stream), z, z_bstride, B, P, gamma, beta, eps, relu, p_out, y,
+                                                                 y_bstride, mean, rstd, accumulate);
     return nasrec_launch_status();
 }
 
@@ -550,8 +853,12 @@ int nasrec_ln3_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* 
     if (grid > 148) grid = 148;                    // persistent warps: fixed sample -> warp assignment
     const bool fused = want && ws && nws >= (long long)grid * 2 * LN3_MAXP;
     if (dz || fused) {
-        nasrec_launch(ln3_bwd_kernel, grid, 128, 0, st, dy, dy_bstride, p_out, z, z_bstride, B, P, gamma, beta, mean, rstd, relu,
-                                             dz, dz_bstride, fused ? ws : nullptr);
+        if (P > 16)
+            nasrec_launch(ln3_bwd_wide_kernel, grid, 256, 0, st, dy, dy_bstride, p_out, z, z_bstride, B, P, gamma, beta, mean, rstd,
+                          relu, dz, dz_bstride, fused ? ws : nullptr);
+        else
+            nasrec_launch(ln3_bwd_kernel, grid, 128, 0, st, dy, dy_bstride, p_out, z, z_bstride, B, P, gamma, beta, mean, rstd, relu,
+                                                 dz, dz_bstride, fused ? ws : nullptr);
         int rc = nasrec_launch_status();
         if (rc) return rc;
     }

@@ -1,3 +1,3 @@
 #!/bin/bash
-python -m pytest tests -x -q -m gpu > gpurun_out/r2l_gputests.log 2>&1; tail -3 gpurun_out/r2l_gputests.log; grep "^E  " gpurun_out/r2l_gputests.log | head -4
-python bench.py --no-cpu --no-extras > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err; cut -c1-300 gpurun_out/r2l_bench.json
+python -m pytest tests -x -q -m gpu > gpurun_out/r2o_gputests.log 2>&1; tail -3 gpurun_out/r2o_gputests.log; grep "^E  " gpurun_out/r2o_gputests.log | head -4
+python bench.py --no-cpu --no-extras > gpurun_out/r2o_bench.json 2> gpurun_out/r2o_bench.err; cut -c1-300 gpurun_out/r2o_bench.json
