@@ -297,13 +297,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
     // nprod: 1 = plain tf32 single pass, 2 = bf16-rounded operands single pass, 3/4 = tf32 hi/lo split products
     const bool conv_b = nprod > 1 && tb.lb.convert;
 
-    if (tid == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, TM_CONV_WARPS / 2);
-            mbar_init(bar_empty + 8 * s, 1);
-        }
-        mbar_init(bar_done, 1);
+    if (tid < 32) {          // one barrier per lane: the 25 initialisations go out together instead of one after the other
+        if (tid < Cfg::STAGES) mbar_init(bar_full + 8 * tid, 1);
+        else if (tid < 2 * Cfg::STAGES) mbar_init(bar_conv + 8 * (tid - Cfg::STAGES), TM_CONV_WARPS / 2);
+        else if (tid < 3 * Cfg::STAGES) mbar_init(bar_empty + 8 * (tid - 2 * Cfg::STAGES), 1);
+        else if (tid == 3 * Cfg::STAGES) mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -578,13 +576,41 @@ __global__ void __launch_bounds__(TM_THREADS, 1) gemm_tma_kernel(const __grid_co
                     __syncwarp();
                     const int n = n0 + c0 + lane;
                     const float bias = (pr.bias && n < pr.N) ? __ldg(pr.bias + n) : 0.f;
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int mm = m0 + warp * 32 + rr;
-                        if (mm >= pr.M || n >= pr.N) continue;
-                        const long long o = (long long)(mm >> pr.c_sh_i) * pr.c_hi_i + (long long)(mm & cmask) * pr.c_lo_i + n;
-                        float v = scratch[rr * 33 + lane] + bias;
-                        if (pr.addend) v += pr.addend[o];
-                        pr.c[o + (long long)split * pr.split_stride] = v;
+                    if (pr.c_sh_i == 0 && n < pr.N) {
+                        // plain row-major output (every linear): one running offset, rows unrolled by 8 so that the addend
+                        // loads and the stores of several rows are in flight together (this loop is ~1 us of every launch)
+                        const int mbase = m0 + warp * 32;
+                        const int rows = min(32, pr.M - mbase);
+                        const long long so = (long long)split * pr.split_stride;
+                        long long o = (long long)mbase * pr.c_hi_i + n;
+                        int rr = 0;
+                        for (; rr + 8 <= rows; rr += 8) {
+                            float v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) v[u] = scratch[(rr + u) * 33 + lane] + bias;
+                            if (pr.addend) {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) v[u] += pr.addend[o + (long long)u * pr.c_hi_i];
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) pr.c[o + (long long)u * pr.c_hi_i + so] = v[u];
+                            o += 8 * pr.c_hi_i;
+                        }
+                        for (; rr < rows; ++rr) {
+                            float v = scratch[rr * 33 + lane] + bias;
+                            if (pr.addend) v += pr.addend[o];
+                            pr.c[o + so] = v;
+                            o += pr.c_hi_i;
+                        }
+                    } else {
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const int mm = m0 + warp * 32 + rr;
+                            if (mm >= pr.M || n >= pr.N) continue;
+                            const long long o = (long long)(mm >> pr.c_sh_i) * pr.c_hi_i + (long long)(mm & cmask) * pr.c_lo_i + n;
+                            float v = scratch[rr * 33 + lane] + bias;
+                            if (pr.addend) v += pr.addend[o];
+                            pr.c[o + (long long)split * pr.split_stride] = v;
+                        }
                     }
                     __syncwarp();
                 } else if (row < pr.M) {

@@ -179,30 +179,65 @@ __global__ void __launch_bounds__(256) adagrad_kernel(const __grid_constant__ Ad
         const float4* g4 = reinterpret_cast<const float4*>(g + beg);
         float4* s4 = reinterpret_cast<float4*>(s + beg);
         float4* w4 = reinterpret_cast<float4*>(w + beg);
-        for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
-            const float4 gv = __ldg(g4 + i);
-            float4 sv = s4[i], wv = w4[i];
-            upd(gv.x, sv.x, wv.x);
-            upd(gv.y, sv.y, wv.y);
-            upd(gv.z, sv.z, wv.z);
-            upd(gv.w, sv.w, wv.w);
-            s4[i] = sv;
-            w4[i] = wv;
-            if (ph) {
-                const long long e = beg + (i << 2);
-                if (ldp == (long long)cols && shift == 0) {      // planes have w's own layout: 16-byte stores
-                    float4 h4, l4;
-                    plane_split(wv.x, h4.x, l4.x, pk.bf16);
-                    plane_split(wv.y, h4.y, l4.y, pk.bf16);
-                    plane_split(wv.z, h4.z, l4.z, pk.bf16);
-                    plane_split(wv.w, h4.w, l4.w, pk.bf16);
-                    *reinterpret_cast<float4*>(ph + e) = h4;
-                    *reinterpret_cast<float4*>(pl + e) = l4;
-                } else {
-                    plane(e, wv.x);
-                    plane(e + 1, wv.y);
-                    plane(e + 2, wv.z);
-                    plane(e + 3, wv.w);
+        // Four 16-byte groups per thread and pass, every load issued before the first use; the (row, column) of a group in the
+        // padded planes advances incrementally (one division per thread instead of one per element: the reference layout's
+        // row length, e.g. 1037, is not a power of two).  20 B/parameter + 8 B for the planes: ~220 MB per step.
+        constexpr int AU = 4;
+        unsigned pr0 = 0, pc0 = 0;                         // (row, column in w) of this thread's first element of the pass
+        if (ph) {
+            const unsigned e0 = (unsigned)(beg + ((long long)threadIdx.x << 2));
+            pr0 = e0 / cols;
+            pc0 = e0 - pr0 * cols;
+        }
+        const unsigned step_r = (unsigned)(blockDim.x * 4) / cols, step_c = (unsigned)(blockDim.x * 4) - step_r * cols;
+        const bool same_layout = ldp == (long long)cols && shift == 0;
+        for (long long i0 = threadIdx.x; i0 < n4; i0 += (long long)blockDim.x * AU) {
+            float4 gv[AU], sv[AU], wv[AU];
+#pragma unroll
+            for (int u = 0; u < AU; ++u) {
+                const long long i = i0 + (long long)u * blockDim.x;
+                if (i < n4) {
+                    gv[u] = __ldg(g4 + i);
+                    sv[u] = s4[i];
+                    wv[u] = w4[i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < AU; ++u) {
+                const long long i = i0 + (long long)u * blockDim.x;
+                if (i >= n4) break;
+                upd(gv[u].x, sv[u].x, wv[u].x);
+                upd(gv[u].y, sv[u].y, wv[u].y);
+                upd(gv[u].z, sv[u].z, wv[u].z);
+                upd(gv[u].w, sv[u].w, wv[u].w);
+                s4[i] = sv[u];
+                w4[i] = wv[u];
+                if (ph) {
+                    if (same_layout) {      // planes have w's own layout: 16-byte stores
+                        const long long e = beg + (i << 2);
+                        float4 h4, l4;
+                        plane_split(wv[u].x, h4.x, l4.x, pk.bf16);
+                        plane_split(wv[u].y, h4.y, l4.y, pk.bf16);
+                        plane_split(wv[u].z, h4.z, l4.z, pk.bf16);
+                        plane_split(wv[u].w, h4.w, l4.w, pk.bf16);
+                        *reinterpret_cast<float4*>(ph + e) = h4;
+                        *reinterpret_cast<float4*>(pl + e) = l4;
+                    } else {
+                        const float vals[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+                        unsigned r = pr0, c = pc0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float h, l;
+                            plane_split(vals[q], h, l, pk.bf16);
+                            const long long o = (long long)r * ldp + c + (c >= first ? shift : 0u);
+                            ph[o] = h;
+                            pl[o] = l;
+                            if (++c == cols) { c = 0; ++r; }
+                        }
+                    }
+                    pr0 += step_r;
+                    pc0 += step_c;
+                    if (pc0 >= cols) { pc0 -= cols; ++pr0; }
                 }
             }
         }
