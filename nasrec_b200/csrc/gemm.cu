@@ -725,6 +725,13 @@ int run_tma(Job& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
         if (!get_map(&tb.maps[i], job.spec[i])) return NASREC_EINVAL;
     }
     dim3 grid((maxN + bn - 1) / bn, (maxM + nasrec_gemm::TC_BM - 1) / nasrec_gemm::TC_BM, totz);
+    if (tb.nprob > 1 && !tb.flat) {
+        // several problems of different sizes (gradient targets of a dgrad, segments of a wgrad): enumerate the real tiles
+        // instead of launching the bounding box of the largest problem for each of them
+        bool plain = true;
+        for (int i = 0; i < tb.nprob; ++i) plain = plain && tb.prob[i].nsplit == 1;
+        if (plain) tb.flat = 1;
+    }
     if (tb.flat) {
         // one CTA (or cluster) per REAL output tile: running tile totals per problem; flat launches carry no pre-split problems
         int tot = 0;

@@ -556,7 +556,10 @@ inline TilePlan tc_plan(const Prob* prob, int nprob, int maxN, KTiles ktiles_of,
     static const int widths[4] = {16, 32, 64, 128};
     // measured us per k-tile of one CTA (gemm_prof2.py, B200, 3xTF32), by operand kind and tile width
     static const double t_tile[3][4] = {{0.40, 0.42, 0.52, 0.78}, {0.40, 0.42, 0.60, 0.97}, {0.42, 0.42, 0.73, 1.20}};
-    static const int capacity[4] = {148, 148, 144, 128};      // SMs a grid of clusters of 1 / 2 / 4 / 8 one-CTA-per-SM CTAs can fill
+    // SMs a grid of clusters of 1 / 2 / 4 / 8 one-CTA-per-SM CTAs fills in one wave.  A cluster lives inside one GPC (16-20
+    // SMs, not all multiples of the cluster size); measured: 144 CTAs in clusters of 4 take two waves (dgrad M = 512,
+    // N = 13 + 1024, K = 1024: 23.9 us at (128, 4) against 15.1 us at (64, 2), profiles/r02_gemm.md)
+    static const int capacity[4] = {148, 144, 128, 112};
     const double* tt = t_tile[kind < 0 || kind > 2 ? 2 : kind];
     for (int w = 0; w < 4; ++w) {
         const int bn = widths[w];
