@@ -172,6 +172,11 @@ void nasrec_internal_workspace(float** ws, long long* nfloats);
 // `accumulate`; cleared by that call): lets the op-level backward entry points serve fresh and accumulated gradient
 // targets with one launch
 void nasrec_internal_set_dgrad_flags(const int* flags);
+// deferred LayerNorm parameter gradients (ln.cu): scratch for first-stage partials (null detaches and drops the queue),
+// number of recorded reductions, and the batched launch that finishes them
+void nasrec_internal_ln_defer_scratch(float* base, long long nfloats);
+long long nasrec_internal_ln_pending();
+int nasrec_internal_ln_flush(cudaStream_t st);
 // fork: returns the side stream ordered after everything issued to `main` so far (or `main` itself when none is attached);
 // the work must be joined with nasrec_side_join
 cudaStream_t nasrec_internal_fork_side(cudaStream_t main);

@@ -1408,11 +1408,12 @@ int nasrec_wgrad_defer(int on) {
 }
 
 int nasrec_wgrad_flush(void* stream) {
-    if (g_wq.empty()) return 0;
+    int rc = nasrec_internal_ln_flush(as_stream(stream));      // the other deferred parameter gradients (ln.cu)
+    if (rc || g_wq.empty()) return rc;
     return wgrad_flush(as_stream(stream));
 }
 
-int64_t nasrec_wgrad_pending(void) { return (int64_t)g_wq.size(); }
+int64_t nasrec_wgrad_pending(void) { return (int64_t)g_wq.size() + nasrec_internal_ln_pending(); }
 
 int nasrec_set_small_k(int k) {
     const int old = g_small_k;

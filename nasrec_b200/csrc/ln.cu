@@ -7,6 +7,7 @@
 // The statistics always span the full width N (masked columns included, as in
 // the reference: LayerNorm runs before the mask); only the d_out live columns
 // are stored.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -766,7 +767,92 @@ int ew_grid(long long total) {
     return (int)g;
 }
 
+
+// ---- deferred parameter gradients ---------------------------------------------------------------------------------------
+// dgamma / dbeta are read only by the optimizer, but their second reduction stage used to be a launch of its own right
+// behind every LayerNorm backward -- ~23 launches on the dY -> dX chain of a step.  While a scratch region is attached
+// (nasrec_internal_ln_defer_scratch: the step executor hands over a piece of its arena for the duration of a backward
+// pass), every LayerNorm backward keeps its first-stage partials in a slot of its own and only records what is left to
+// do; nasrec_internal_ln_flush (called by nasrec_wgrad_flush, i.e. once per block, on the side stream when there is one)
+// finishes all recorded reductions in ONE launch.  Same fixed-order sums as the per-operator kernels' contract:
+// deterministic, independent of scheduling.
+struct LnFinalRec {
+    const float* part;
+    float* dgamma;
+    float* dbeta;
+    int nblk, N, S, accumulate;          // S: column stride between the two halves of a partial row (N, or LN3_MAXP)
+};
+constexpr int LNF_MAX = 32;
+struct LnFinalBatch {
+    int n;
+    int pad_;
+    LnFinalRec r[LNF_MAX];
+};
+
+__global__ void __launch_bounds__(256) ln_param_final_batched_kernel(const __grid_constant__ LnFinalBatch bt) {
+    pdl_enter();
+    const LnFinalRec& rec = bt.r[blockIdx.y];
+    if ((int)blockIdx.x * 32 >= rec.N) return;
+    __shared__ float sg[8][33], sb[8][33];
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + c;
+    float g = 0.f, b = 0.f;
+    if (j < rec.N) {
+        const float* p0 = rec.part + j;
+        const long long row = 2LL * rec.S;
+        int k = r;
+        for (; k + 8 < rec.nblk; k += 16) {           // two independent loads per half and pass
+            const float g0 = p0[k * row], b0 = p0[k * row + rec.S];
+            const float g1 = p0[(k + 8) * row], b1 = p0[(k + 8) * row + rec.S];
+            g += g0 + g1;
+            b += b0 + b1;
+        }
+        for (; k < rec.nblk; k += 8) {
+            g += p0[k * row];
+            b += p0[k * row + rec.S];
+        }
+    }
+    sg[r][c] = g;
+    sb[r][c] = b;
+    __syncthreads();
+    if (r == 0 && j < rec.N) {
+        const float gt = ((sg[0][c] + sg[1][c]) + (sg[2][c] + sg[3][c])) + ((sg[4][c] + sg[5][c]) + (sg[6][c] + sg[7][c]));
+        const float bt2 = ((sb[0][c] + sb[1][c]) + (sb[2][c] + sb[3][c])) + ((sb[4][c] + sb[5][c]) + (sb[6][c] + sb[7][c]));
+        rec.dgamma[j] = rec.accumulate ? rec.dgamma[j] + gt : gt;
+        rec.dbeta[j] = rec.accumulate ? rec.dbeta[j] + bt2 : bt2;
+    }
+}
+
+float* g_lnd_base = nullptr;
+long long g_lnd_cap = 0, g_lnd_off = 0;
+LnFinalBatch g_lnd_q{};
+
+// slot for `need` floats of partials, or null (no scratch attached / full / queue full: the caller finishes at once)
+float* lnd_slot(long long need) {
+    if (!g_lnd_base || g_lnd_q.n >= LNF_MAX || g_lnd_off + need > g_lnd_cap) return nullptr;
+    float* p = g_lnd_base + g_lnd_off;
+    g_lnd_off += (need + 63) & ~63LL;
+    return p;
+}
 }  // namespace
+
+void nasrec_internal_ln_defer_scratch(float* base, long long nfloats) {
+    static const bool off = getenv("NASREC_LN_DEFER") && atoi(getenv("NASREC_LN_DEFER")) == 0;      // experiment knob
+    if (off) base = nullptr;
+    g_lnd_base = base;
+    g_lnd_cap = base ? nfloats : 0;
+    g_lnd_off = 0;
+    if (!base) g_lnd_q.n = 0;
+}
+long long nasrec_internal_ln_pending() { return g_lnd_q.n; }
+int nasrec_internal_ln_flush(cudaStream_t st) {
+    if (g_lnd_q.n == 0) return 0;
+    int maxN = 0;
+    for (int i = 0; i < g_lnd_q.n; ++i) maxN = g_lnd_q.r[i].N > maxN ? g_lnd_q.r[i].N : maxN;
+    nasrec_launch(ln_param_final_batched_kernel, dim3(cdiv(maxN, 32), g_lnd_q.n), 256, 0, st, g_lnd_q);
+    g_lnd_q.n = 0;                      // slots are NOT recycled before the scratch is re-attached: the launch may still read them
+    return nasrec_launch_status();
+}
 
 extern "C" {
 
@@ -797,6 +883,21 @@ int nasrec_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* x, int6
     nasrec_internal_workspace(&ws, &nws);
     int grid = cdiv(M, 4);
     if (grid > 296) grid = 296;                    // persistent warps: fixed row -> warp assignment
+    // deferred second stage: partials go to a slot of the attached scratch and the final sums join the batched launch
+    // (an in-place accumulate may depend on a queued record for the same parameters: finish the queue first)
+    float* slot = nullptr;
+    if (want && g_lnd_base) {
+        if (accumulate_params) {
+            const int rc = nasrec_internal_ln_flush(st);
+            if (rc) return rc;
+        } else {
+            slot = lnd_slot((long long)grid * 2 * N);
+        }
+    }
+    if (slot) {
+        ws = slot;
+        nws = (long long)grid * 2 * N;
+    }
     const bool fused = want && ws && nws >= (long long)grid * 2 * N;
     if (dx || fused) {
         if (N > 256) {
@@ -810,6 +911,10 @@ int nasrec_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* x, int6
         }
         int rc = nasrec_launch_status();
         if (rc) return rc;
+    }
+    if (fused && slot) {
+        g_lnd_q.r[g_lnd_q.n++] = LnFinalRec{slot, dgamma, dbeta, grid, N, N, 0};
+        return 0;
     }
     if (fused) {
         nasrec_launch(ln_param_final_kernel, cdiv(N, 32), 256, 0, st, ws, grid, N, dgamma, dbeta, accumulate_params);
@@ -851,6 +956,19 @@ int nasrec_ln3_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* 
     nasrec_internal_workspace(&ws, &nws);
     int grid = cdiv(B, 4);
     if (grid > 148) grid = 148;                    // persistent warps: fixed sample -> warp assignment
+    float* slot = nullptr;                         // deferred second stage, as in nasrec_ln_bwd
+    if (want && g_lnd_base) {
+        if (accumulate_params) {
+            const int rc = nasrec_internal_ln_flush(st);
+            if (rc) return rc;
+        } else {
+            slot = lnd_slot((long long)grid * 2 * LN3_MAXP);
+        }
+    }
+    if (slot) {
+        ws = slot;
+        nws = (long long)grid * 2 * LN3_MAXP;
+    }
     const bool fused = want && ws && nws >= (long long)grid * 2 * LN3_MAXP;
     if (dz || fused) {
         if (P > 16)
@@ -861,6 +979,10 @@ int nasrec_ln3_bwd(const float* dy, int64_t dy_bstride, int p_out, const float* 
                                                  dz, dz_bstride, fused ? ws : nullptr);
         int rc = nasrec_launch_status();
         if (rc) return rc;
+    }
+    if (fused && slot) {
+        g_lnd_q.r[g_lnd_q.n++] = LnFinalRec{slot, dgamma, dbeta, grid, P, LN3_MAXP, 0};
+        return 0;
     }
     if (fused) {
         nasrec_launch(ln3_param_final_kernel, cdiv(P, 32), 256, 0, st, ws, grid, P, dgamma, dbeta, accumulate_params);

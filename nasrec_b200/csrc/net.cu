@@ -1117,6 +1117,12 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
         size_t sealed = 0;
         int mark = (int)n->block_mark.size() - 1;
         nasrec_wgrad_defer(n->defer_wgrad ? 1 : 0);
+        if (n->defer_wgrad) {
+            // first-stage partials of every LayerNorm backward of this pass (<= 32 recorded per flush, <= 296 x 2 x 1024
+            // floats each) stay in the arena until the batched final reduction of their block has been launched
+            const long long lnd = (long long)std::min(296, (B + 3) / 4) * 2 * 1024 * 32;
+            nasrec_internal_ln_defer_scratch(n->act.alloc(lnd), lnd);
+        }
         // queued weight gradients run as one batched launch per block, on the side stream when one is attached: the batch
         // then overlaps the dY -> dX chain of the next block instead of extending the step by its ~90 us
         auto flush_wgrads = [&]() {
@@ -1138,6 +1144,7 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
         n->tape.clear();
         flush_wgrads();
         nasrec_wgrad_defer(0);
+        nasrec_internal_ln_defer_scratch(nullptr, 0);
         if (n->overlap) ck(nasrec_side_join(st), 0);
         if (n->seal_cb && n->pg.off > sealed) n->seal_cb((int64_t)sealed, (int64_t)(n->pg.off - sealed));
         n->pg_dirty = n->pg.off;
@@ -1146,6 +1153,7 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
     if (rc) {
         n->pg_dirty = n->pg.cap;       // a failed step may have scribbled anywhere in the bucket: clear all of it next time
         nasrec_wgrad_defer(0);         // ... and nothing of it may stay queued (turning deferral off drops the queue)
+        nasrec_internal_ln_defer_scratch(nullptr, 0);
     }
     return rc;
 }
