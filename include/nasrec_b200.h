@@ -369,7 +369,7 @@ int nasrec_net_set_planes(void* net, float* const* hi, float* const* lo, const i
  * the step's own B).  forward_backward reserves the reduction's and the clip's scratch for that many rows up front, so the
  * two later calls never run out of arena after the step's gradients exist. */
 int nasrec_net_set_reserve(void* net, int rows);
-int nasrec_net_set_overlap(void* net, int on);      /* join the side stream (nasrec_set_side_stream) after backward */
+int nasrec_net_set_overlap(void* net, int on);      /* 1: join the side stream (nasrec_set_side_stream) after backward; 2: join it in nasrec_net_apply instead (the caller reads no gradient in between), so that nasrec_net_sparse_reduce overlaps the last batch of parameter gradients */
 int nasrec_net_set_defer_wgrad(void* net, int on); /* queue dense weight gradients during backward, one batched launch at its end (default on) */
 /* Data-parallel overlap: during nasrec_net_forward_backward, cb(offset_bytes, nbytes) is called on the host each
  * time a block's parameter gradients are final -- the byte range of the gradient bucket sealed since the last call,

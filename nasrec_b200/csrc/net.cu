@@ -94,6 +94,9 @@ struct Net {
     int64_t* uniq = nullptr; int* nuniq = nullptr; float* row_grad = nullptr; float* sumsq = nullptr; int sB = 0;
     bool have_sparse = false;
     bool overlap = false;
+    bool late_join = false;    // see nasrec_net_set_overlap
+    cudaEvent_t join_ev = nullptr;
+    bool join_pending = false; // side-stream work of the last backward not yet joined (done by nasrec_net_apply / _grad_bucket)
     bool defer_wgrad = true;   // dense weight gradients queue up during backward and run as one batched launch (nasrec_wgrad_flush)
     // scratch of nasrec_net_sparse_reduce / nasrec_net_apply, reserved by forward_backward so that those two calls cannot
     // overflow an arena after the step's gradients exist (growing the arenas then would leave them pointing at freed memory)
@@ -993,7 +996,11 @@ void* nasrec_net_create(const int* desc_i, int desc_len, int n_params, float* co
     return n;
 }
 
-void nasrec_net_destroy(void* net) { delete (Net*)net; }
+void nasrec_net_destroy(void* net) {
+    Net* n = (Net*)net;
+    if (n && n->join_ev) cudaEventDestroy(n->join_ev);
+    delete n;
+}
 
 int nasrec_net_set_arenas(void* net, void* act, int64_t act_bytes, void* pgrad, int64_t pgrad_bytes) {
     Net* n = (Net*)net;
@@ -1034,7 +1041,11 @@ int nasrec_net_set_planes(void* net, float* const* hi, float* const* lo, const i
     return 0;
 }
 
-int nasrec_net_set_overlap(void* net, int on) { ((Net*)net)->overlap = on != 0; return 0; }
+int nasrec_net_set_overlap(void* net, int on) {
+    ((Net*)net)->overlap = on != 0;
+    ((Net*)net)->late_join = on == 2;       // 2: the caller always runs nasrec_net_apply next and reads no gradient before it
+    return 0;
+}
 int nasrec_net_set_defer_wgrad(void* net, int on) { ((Net*)net)->defer_wgrad = on != 0; return 0; }
 
 int nasrec_net_set_reserve(void* net, int rows) {
@@ -1107,6 +1118,10 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
             n->res_partial = n->act.alloc(chunks);
             n->res_partial_n = chunks;
         }
+        if (n->join_pending) {              // a step that never reached nasrec_net_apply: its side-stream work ends before this one starts
+            n->join_pending = false;
+            ck((int)cudaStreamWaitEvent(st, n->join_ev, 0), 0);
+        }
         if (n->pg_dirty) ck((int)cudaMemsetAsync(n->pg.base, 0, n->pg_dirty, st));
         Var* out = forward(*n, choice, int_x, cat_x, nullptr, B, true);
         out->g = n->act.alloc(B);
@@ -1145,7 +1160,18 @@ int nasrec_net_forward_backward(void* net, const int* choice, const float* int_x
         flush_wgrads();
         nasrec_wgrad_defer(0);
         nasrec_internal_ln_defer_scratch(nullptr, 0);
-        if (n->overlap) ck(nasrec_side_join(st), 0);
+        // The last batch of parameter gradients (side stream) is needed by the optimizer only: without a seal callback the
+        // join moves to nasrec_net_apply, so that the sorted-row reduction of the embedding gradient (nasrec_net_sparse_reduce,
+        // 26 CTAs on the main stream) overlaps it (only when the caller asked for it: nasrec_net_set_overlap(net, 2)).
+        n->join_pending = false;
+        if (n->overlap && n->late_join && !n->seal_cb) {
+            if (cudaStream_t side = nasrec_internal_side_stream()) {     // still attached here; the caller detaches it on return
+                if (!n->join_ev) ck((int)cudaEventCreateWithFlags(&n->join_ev, cudaEventDisableTiming), 0);
+                ck((int)cudaEventRecord(n->join_ev, side), 0);
+                n->join_pending = true;
+            }
+        }
+        if (n->overlap && !n->join_pending) ck(nasrec_side_join(st), 0);
         if (n->seal_cb && n->pg.off > sealed) n->seal_cb((int64_t)sealed, (int64_t)(n->pg.off - sealed));
         n->pg_dirty = n->pg.off;
         n->step_valid = true;
@@ -1222,6 +1248,10 @@ int nasrec_net_apply(void* net, float lr, float eps, float max_norm, float* norm
     return guarded([&] {
         cudaStream_t st = as_stream(stream);
         if (!n->step_valid) throw CallFailed(NASREC_EINVAL);
+        if (n->join_pending) {
+            n->join_pending = false;
+            ck((int)cudaStreamWaitEvent(st, n->join_ev, 0), 0);
+        }
         std::vector<int> dense;
         for (int pi : n->ref_order) {
             bool is_emb = false;

@@ -416,6 +416,7 @@ class NativeTrainer(FusedTrainer):
         self.fallback_reason: Optional[str] = None
         # weight-gradient GEMMs on a second stream, off the dY -> dX critical path (joined before the optimizer)
         self.overlap_wgrad = overlap_wgrad
+        self.late_join = True
         self._side: Optional[torch.cuda.Stream] = None
 
     def _fork_on(self, net: "NativeNet"):
@@ -423,7 +424,9 @@ class NativeTrainer(FusedTrainer):
             return
         if self._side is None:
             self._side = torch.cuda.Stream()
-            _check(_fn("nasrec_net_set_overlap")(net.handle, 1), "nasrec_net_set_overlap")
+            # 2 = the final join moves into nasrec_net_apply (step() below always calls it next); a data-parallel owner
+            # reads the gradient bucket in between and sets late_join = False
+            _check(_fn("nasrec_net_set_overlap")(net.handle, 2 if self.late_join else 1), "nasrec_net_set_overlap")
         _fn("nasrec_set_side_stream")(self._side.cuda_stream)
 
     def _fork_off(self):

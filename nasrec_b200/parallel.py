@@ -135,6 +135,7 @@ class NativeDataParallelTrainer(DataParallelTrainer):
         super().__init__(model, lr, eps, clip, group)
         from .native import NativeTrainer
         self._nt = NativeTrainer(model, lr, eps, clip)
+        self._nt.late_join = False                        # the gradient bucket is all-reduced between backward and apply
         self._nt.state = self.state                       # one set of Adagrad accumulators for both paths
         self.overlap_comm = True
         self._cb_net = None

@@ -1,6 +1,3 @@
 #!/bin/bash
-for n in 1 2; do
-NASREC_LN_DEFER=0 python tools/step_dump.py /tmp/a$n.npz $n > /dev/null 2>&1
-NASREC_LN_DEFER=1 python tools/step_dump.py /tmp/b$n.npz $n > /dev/null 2>&1
-echo "== after $n step(s): defer off vs on"; python tools/step_cmp.py /tmp/a$n.npz /tmp/b$n.npz 2>/dev/null | head -8
-done
+python -m pytest tests -x -q -m gpu > gpurun_out/r2q_gputests.log 2>&1; tail -3 gpurun_out/r2q_gputests.log; grep "^E  " gpurun_out/r2q_gputests.log | head -4 | cut -c1-600
+python bench.py --no-cpu --no-extras > gpurun_out/r2q_bench.json 2> gpurun_out/r2q_bench.err; cut -c1-300 gpurun_out/r2q_bench.json
