@@ -7,6 +7,7 @@
 //
 // HBM-bound byte work: rows are 64 B (16 fp32); 4 lanes move one row as float4,
 // so one warp instruction moves 8 rows; indices are read coalesced along F.
+#include <cub/block/block_radix_sort.cuh>
 #include "common.cuh"
 
 namespace {
@@ -56,6 +57,11 @@ __global__ void __launch_bounds__(256) emb_gather_kernel(const float* const* __r
 // One CTA per table: bitonic sort of (row << 32 | sample) keys in shared memory,
 // head flags + block scan -> unique rows, then 16 lanes per unique row sum the
 // duplicates in ascending sample order.
+// ITEMS == 0: bitonic sort of the keys in shared memory (any power-of-two Bpad, Bpad threads up to 1024).
+// ITEMS >= 1: 1024 threads x ITEMS keys in registers, stable LSD radix sort on the row bits only (cub::BlockRadixSort; keys
+//             enter in sample order, so equal rows stay in ascending sample order): O(n) per pass instead of the bitonic
+//             network's O(n log^2 n) -- what the data-parallel global batch (N x 512 ids per table) needs.
+template <int ITEMS>
 __global__ void __launch_bounds__(1024) emb_sort_reduce_kernel(const int64_t* __restrict__ idx,
                                                                const int64_t* __restrict__ num_rows, int* err_flag,
                                                                const float* __restrict__ gout, int Bin, int Bpad,
@@ -89,6 +95,21 @@ __global__ void __launch_bounds__(1024) emb_sort_reduce_kernel(const int64_t* __
     __syncthreads();
     const int B = s_valid;                    // valid keys; the scratch / output strides stay Bin
     if (tid == 0 && B != Bin && err_flag) atomicOr(err_flag, 1);
+    if constexpr (ITEMS > 0) {
+        using Sort = cub::BlockRadixSort<unsigned long long, 1024, ITEMS>;
+        unsigned long long mine[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) mine[j] = keys[tid * ITEMS + j];
+        __syncthreads();                      // the key array doubles as cub's scratch from here on
+        // row bits only: 2^bits > nrows, so the all-ones key of a dropped / padding entry sorts behind every valid row
+        int bits = 1;
+        while (bits < 31 && (1ull << bits) <= nrows) ++bits;
+        Sort(*reinterpret_cast<typename Sort::TempStorage*>(keys)).Sort(mine, 32, 32 + bits);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) keys[tid * ITEMS + j] = mine[j];
+        __syncthreads();
+    } else
     for (int k = 2; k <= Bpad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < Bpad; i += nt) {
@@ -232,6 +253,28 @@ __global__ void __launch_bounds__(256) emb_adagrad_kernel(const int64_t* __restr
     }
 }
 
+template <int ITEMS>
+int launch_sort_reduce(const int64_t* idx, const int64_t* num_rows, int* err_flag, const float* gout, int B, int Bpad, int F,
+                       int64_t* uniq, int* nuniq, float* row_grad, float* sumsq, int* seg_scratch, void* stream) {
+    size_t smem = (size_t)Bpad * sizeof(unsigned long long);
+    if (ITEMS > 0) {
+        const size_t tmp = sizeof(typename cub::BlockRadixSort<unsigned long long, 1024, (ITEMS > 0 ? ITEMS : 1)>::TempStorage);
+        if (tmp > smem) smem = tmp;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        size_t cap = 16384 * 8;
+        if (smem > cap) cap = smem;
+        cudaError_t e = cudaFuncSetAttribute(emb_sort_reduce_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int threads = Bpad >= 1024 ? 1024 : (Bpad < 64 ? 64 : Bpad);
+    nasrec_launch(emb_sort_reduce_kernel<ITEMS>, F, threads, smem, as_stream(stream), idx, num_rows, err_flag, gout, B, Bpad, F, uniq,
+                  nuniq, row_grad, sumsq, seg_scratch);
+    return nasrec_launch_status();
+}
+
 }  // namespace
 
 extern "C" {
@@ -262,18 +305,16 @@ int nasrec_emb_grad_sort_reduce_checked(const int64_t* idx, const int64_t* num_r
     if (B > 16384) return NASREC_ETOOBIG;
     int Bpad = 32;
     while (Bpad < B) Bpad <<= 1;
-    const size_t smem = (size_t)Bpad * sizeof(unsigned long long);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(emb_sort_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             16384 * 8);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+    if (Bpad >= 1024 && Bpad <= 8192) {
+        // radix variant: 1024 threads x (Bpad / 1024) keys
+        switch (Bpad / 1024) {
+            case 1: return launch_sort_reduce<1>(idx, num_rows, err_flag, gout, B, Bpad, F, uniq, nuniq, row_grad, sumsq, seg_scratch, stream);
+            case 2: return launch_sort_reduce<2>(idx, num_rows, err_flag, gout, B, Bpad, F, uniq, nuniq, row_grad, sumsq, seg_scratch, stream);
+            case 4: return launch_sort_reduce<4>(idx, num_rows, err_flag, gout, B, Bpad, F, uniq, nuniq, row_grad, sumsq, seg_scratch, stream);
+            default: return launch_sort_reduce<8>(idx, num_rows, err_flag, gout, B, Bpad, F, uniq, nuniq, row_grad, sumsq, seg_scratch, stream);
+        }
     }
-    const int threads = Bpad >= 1024 ? 1024 : (Bpad < 64 ? 64 : Bpad);
-    nasrec_launch(emb_sort_reduce_kernel, F, threads, smem, as_stream(stream), idx, num_rows, err_flag, gout, B, Bpad, F, uniq,
-                  nuniq, row_grad, sumsq, seg_scratch);
-    return nasrec_launch_status();
+    return launch_sort_reduce<0>(idx, num_rows, err_flag, gout, B, Bpad, F, uniq, nuniq, row_grad, sumsq, seg_scratch, stream);
 }
 
 int nasrec_emb_grad_to_dense(const int64_t* uniq, const int* nuniq, const float* row_grad,

@@ -646,7 +646,7 @@ def reduce_sparse(cat_x: torch.Tensor, gout: torch.Tensor, tables: Optional["Emb
     sg.row_grad = torch.empty(F, B, E, dtype=torch.float32, device=dev)
     sg.sumsq = torch.empty(F, dtype=torch.float32, device=dev)
     scratch = torch.empty(F, B + 1, dtype=torch.int32, device=dev)
-    if B > 1024 and F <= 31:
+    if B > 2048 and F <= 31:
         # large batches (data-parallel global batch, KDD): multi-CTA radix-sort reduction (csrc/emb_big.cu)
         from ._lib import query
         nb = query("nasrec_emb_grad_sort_reduce_big_ws_bytes", B, F)
