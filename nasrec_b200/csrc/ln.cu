@@ -16,6 +16,9 @@ constexpr int LN_MAXN = 1024;
 constexpr int LN_VPT = LN_MAXN / 32;   // values per lane
 
 // ------------------------------------------------------------------ row LN
+// VPT = values per lane: 32 lanes x VPT >= N.  The narrow instances (N <= 64 / 128 / 256) exist because a fixed VPT of 32 makes an
+// N = 64 row pay for 32 predicated-off loop bodies per lane where 2 do the work.
+template <int VPT>
 __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x, long long ldx, int M, int N,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float eps, int relu,
@@ -29,9 +32,9 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
     const float* xr = x + (long long)row * ldx;
     float* yr = y + (long long)row * ldy;
     // phase 1: every load of the row is issued before anything waits (see ldg_nc_pred)
-    float v[LN_VPT], gm[LN_VPT], bt[LN_VPT], yo[LN_VPT];
+    float v[VPT], gm[VPT], bt[VPT], yo[VPT];
 #pragma unroll
-    for (int k = 0; k < LN_VPT; ++k) {
+    for (int k = 0; k < VPT; ++k) {
         const int j = lane + 32 * k;
         v[k] = ldg_nc_pred(xr + j, j < N);
         gm[k] = ldg_nc_pred(gamma + j, j < d_out);
@@ -40,11 +43,11 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
     }
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_VPT; ++k) s += v[k];
+    for (int k = 0; k < VPT; ++k) s += v[k];
     const float mean = warp_sum(s) / (float)N;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_VPT; ++k) {
+    for (int k = 0; k < VPT; ++k) {
         const int j = lane + 32 * k;
         const float d = j < N ? v[k] - mean : 0.f;
         q += d * d;
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
         rstd_out[row] = rstd;
     }
 #pragma unroll
-    for (int k = 0; k < LN_VPT; ++k) {
+    for (int k = 0; k < VPT; ++k) {
         const int j = lane + 32 * k;
         float o = (v[k] - mean) * rstd * gm[k] + bt[k];
         if (relu) o = fmaxf(o, 0.f);
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const float* __restrict__ x
 
 // dx for every row (persistent warps, fixed row -> warp assignment); when `part` is given, also this
 // CTA's partial column sums of dgamma/dbeta (part[cta][0][j], part[cta][1][j]) for the second stage.
+template <int VPT>
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ dy, long long lddy, int d_out,
                                                      const float* __restrict__ x, long long ldx, int M, int N,
                                                      const float* __restrict__ gamma,
@@ -76,9 +80,9 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
     pdl_enter();
     extern __shared__ float sred[];          // [2][4][N] when part != null
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float accg[LN_VPT], accb[LN_VPT];
+    float accg[VPT], accb[VPT];
 #pragma unroll
-    for (int k = 0; k < LN_VPT; ++k) {
+    for (int k = 0; k < VPT; ++k) {
         accg[k] = 0.f;
         accb[k] = 0.f;
     }
@@ -87,9 +91,9 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
         const float* dyr = dy + (long long)row * lddy;
         // phase 1: all loads in flight together
         const float mean = mean_in[row], rstd = rstd_in[row];
-        float xh[LN_VPT], a[LN_VPT], gm[LN_VPT], bt[LN_VPT];
+        float xh[VPT], a[VPT], gm[VPT], bt[VPT];
 #pragma unroll
-        for (int k = 0; k < LN_VPT; ++k) {
+        for (int k = 0; k < VPT; ++k) {
             const int j = lane + 32 * k;
             xh[k] = ldg_nc_pred(xr + j, j < N);
             a[k] = ldg_nc_pred(dyr + j, j < d_out);
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
         }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < LN_VPT; ++k) {
+        for (int k = 0; k < VPT; ++k) {
             const int j = lane + 32 * k;
             xh[k] = j < N ? (xh[k] - mean) * rstd : 0.f;
             float d = a[k];                                      // 0 beyond d_out
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
         if (dx) {
             float* dxr = dx + (long long)row * lddx;
 #pragma unroll
-            for (int k = 0; k < LN_VPT; ++k) {
+            for (int k = 0; k < VPT; ++k) {
                 const int j = lane + 32 * k;
                 if (j < N) dxr[j] = rstd * (a[k] - c1 - xh[k] * c2);
             }
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const float* __restrict__ d
     float* sg = sred;
     float* sb = sred + 4 * N;
 #pragma unroll
-    for (int k = 0; k < LN_VPT; ++k) {
+    for (int k = 0; k < VPT; ++k) {
         const int j = lane + 32 * k;
         if (j < N) {
             sg[w * N + j] = accg[k];
@@ -864,9 +868,15 @@ int nasrec_ln_fwd(const float* x, int64_t ldx, int M, int N, const float* gamma,
     if (N > 256)
         nasrec_launch(ln_fwd_wide_kernel, cdiv(M, LNW_RPC), 256, 0, as_stream(stream), x, ldx, M, N, gamma, beta, eps, relu, d_out, y,
                       ldy, mean, rstd, accumulate);
+    else if (N <= 64)
+        nasrec_launch(ln_fwd_kernel<2>, cdiv(M, 4), 128, 0, as_stream(stream), x, ldx, M, N, gamma, beta, eps, relu, d_out, y, ldy,
+                      mean, rstd, accumulate);
+    else if (N <= 128)
+        nasrec_launch(ln_fwd_kernel<4>, cdiv(M, 4), 128, 0, as_stream(stream), x, ldx, M, N, gamma, beta, eps, relu, d_out, y, ldy,
+                      mean, rstd, accumulate);
     else
-        nasrec_launch(ln_fwd_kernel, cdiv(M, 4), 128, 0, as_stream(stream), x, ldx, M, N, gamma, beta, eps, relu, d_out, y, ldy,
-                                                                 mean, rstd, accumulate);
+        nasrec_launch(ln_fwd_kernel<8>, cdiv(M, 4), 128, 0, as_stream(stream), x, ldx, M, N, gamma, beta, eps, relu, d_out, y, ldy,
+                      mean, rstd, accumulate);
     return nasrec_launch_status();
 }
 
@@ -906,8 +916,15 @@ int nasrec_ln_bwd(const float* dy, int64_t lddy, int d_out, const float* x, int6
                           lddx, fused ? ws : nullptr);
         } else {
             const size_t smem = fused ? (size_t)8 * N * sizeof(float) : 0;
-            nasrec_launch(ln_bwd_kernel, grid, 128, smem, st, dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx, lddx,
-                                                   fused ? ws : nullptr);
+            if (N <= 64)
+                nasrec_launch(ln_bwd_kernel<2>, grid, 128, smem, st, dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx,
+                              lddx, fused ? ws : nullptr);
+            else if (N <= 128)
+                nasrec_launch(ln_bwd_kernel<4>, grid, 128, smem, st, dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx,
+                              lddx, fused ? ws : nullptr);
+            else
+                nasrec_launch(ln_bwd_kernel<8>, grid, 128, smem, st, dy, lddy, d_out, x, ldx, M, N, gamma, beta, mean, rstd, relu, dx,
+                              lddx, fused ? ws : nullptr);
         }
         int rc = nasrec_launch_status();
         if (rc) return rc;
