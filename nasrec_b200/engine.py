@@ -181,6 +181,25 @@ def _dgrad_groups(seg_list: Sequence[Seg]):
     return out
 
 
+# Weight planes for the TMA-fed GEMM (nasrec_b200/planes.py).  The trainers that keep planes in step with the weights
+# (FusedTrainer and its subclasses) publish their PlaneCache here for the duration of a forward / backward; every linear
+# then announces its weight's planes to the library right before its call (a one-entry hint, ignored when it does not
+# match the W pointer of the call).  None -> LDG-producer kernel, as with plain autograd.
+PLANES = None
+
+
+def _hint(W: "PVar"):
+    c = PLANES
+    if c is None:
+        return
+    pl = c.planes(W.p)
+    if pl is None:
+        return
+    hi, lo, ldp, first = pl
+    from ._lib import LIB
+    LIB.set_weight_planes(W.t.data_ptr(), hi.data_ptr(), lo.data_ptr(), ldp, W.t.shape[0], W.t.shape[1], first)
+
+
 # --------------------------------------------------------------------------- 2-D linear (+LN/act)
 def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[PVar],
               ln: Optional[Tuple[PVar, PVar]], relu: bool, d_out: int, n_off: int = 0, n_full: Optional[int] = None,
@@ -206,9 +225,11 @@ def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[
         mean = rstd = None
         gam = bet = pm = pr = None
     if FUSED_CALLS:
+        _hint(W)
         call("nasrec_linear_ln_fwd", sp, ns, _p(W.t), ldw, n_off, N, _p(b.t) if b is not None else None, gam, bet,
              LN_EPS, int(relu), d_out, _p(z), _p(out.t, out_off), ldy, pm, pr, accumulate, M)
     else:
+        _hint(W)
         call("nasrec_seg_linear_fwd", sp, ns, _p(W.t), ldw, n_off, N, _p(b.t) if b is not None else None, _p(z), N, M)
         if ln is not None:
             call("nasrec_ln_fwd", _p(z), N, M, N, gam, bet, LN_EPS, int(relu), d_out, _p(out.t, out_off), ldy, pm, pr,
@@ -232,6 +253,7 @@ def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[
         targets = _grad_targets(seg_list) if (FUSED_CALLS and _distinct_woffs(seg_list)) else None
         if targets is not None:
             dsp, flags = targets
+            _hint(W)
             call("nasrec_linear_ln_bwd", _p(out.g, out_off), ldy, d_out, _p(z), M, N, gam, bet, pm, pr, int(relu), sp,
                  dsp, flags, ns, _p(W.t), ldw, n_off, _p(gw) if gw is not None else None,
                  _p(gb) if gb is not None else None, _p(ln[0].grad(True)) if want_ln else None,
@@ -253,6 +275,7 @@ def linear_ln(tape: Tape, seg_list: Sequence[Seg], M: int, W: PVar, b: Optional[
             call("nasrec_colsum", _p(dz), N, M, N, _p(gb, n_off), 0)
         for grp, acc in _dgrad_groups(seg_list):
             spk, nsk = _pack(grp, grad=True)
+            _hint(W)
             call("nasrec_seg_linear_dgrad", _p(dz), N, N, _p(W.t), ldw, n_off, spk, nsk, M, acc)
 
     tape.record(bwd)
@@ -282,9 +305,11 @@ def sproj_ln(tape: Tape, seg_list: Sequence[Seg], B: int, W: PVar, b: Optional[P
         mean = rstd = None
         gam = bet = pm = pr = None
     if FUSED_CALLS:
+        _hint(W)
         call("nasrec_sproj_ln_fwd", sp, ns, _p(W.t), ldw, P, _p(b.t) if b is not None else None, gam, bet, LN_EPS,
              int(relu), p_out, _p(z), _p(out.t, out_off), out_bstride, pm, pr, accumulate, B)
     else:
+        _hint(W)
         call("nasrec_sproj_fwd", sp, ns, _p(W.t), ldw, P, _p(b.t) if b is not None else None, _p(z), P * E, B)
         if ln is not None:
             call("nasrec_ln3_fwd", _p(z), P * E, B, P, gam, bet, LN_EPS, int(relu), p_out, _p(out.t, out_off),
@@ -311,6 +336,7 @@ def sproj_ln(tape: Tape, seg_list: Sequence[Seg], B: int, W: PVar, b: Optional[P
             ws = None
             if gw is not None:
                 ws = _new(query("nasrec_sproj_wgrad_ws_floats", P, sum(s.width for s in seg_list), B), like=ref)
+            _hint(W)
             call("nasrec_sproj_ln_bwd", _p(out.g, out_off), out_bstride, p_out, _p(z), B, P, gam, bet, pm, pr, int(relu),
                  sp, dsp, flags, ns, _p(W.t), ldw, _p(gw) if gw is not None else None,
                  _p(gb) if gb is not None else None, _p(ln[0].grad(True)) if want_ln else None,
@@ -334,6 +360,7 @@ def sproj_ln(tape: Tape, seg_list: Sequence[Seg], B: int, W: PVar, b: Optional[P
             call("nasrec_sproj_bias_grad", _p(dz), P * E, P, B, _p(gb), 0)
         for grp, acc in _dgrad_groups(seg_list):
             spk, nsk = _pack(grp, grad=True)
+            _hint(W)
             call("nasrec_sproj_dgrad", _p(dz), P * E, P, _p(W.t), ldw, spk, nsk, B, acc)
 
     tape.record(bwd)

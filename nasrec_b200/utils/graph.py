@@ -41,6 +41,9 @@ class GraphedFusedTrainer:
             self._static[0].copy_(int_x, non_blocking=True)
             self._static[1].copy_(cat_x, non_blocking=True)
             self._static[2].copy_(y, non_blocking=True)
+            # the captured step keeps the weight planes in step by itself; a weight changed from outside since the last
+            # replay (load_state_dict, an in-place edit) is noticed here and its planes are rebuilt before the replay
+            self.trainer._planes()
         self.graph.replay()
         from .. import _lib
         _lib.LIB.launches += self.kernels_per_replay

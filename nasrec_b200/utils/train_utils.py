@@ -219,6 +219,10 @@ class FusedTrainer:
         self.defer_sparse = False
         # set by GraphedFusedTrainer during capture: weight-gradient GEMMs fork onto this stream
         self.side_stream: Optional[torch.cuda.Stream] = None
+        # pre-split weight planes (nasrec_b200/planes.py): forward / dgrad GEMMs take the TMA-fed kernel, the Adagrad
+        # kernel keeps the planes in step.  Costs 2x the dense weights in HBM; False = LDG-producer kernel everywhere.
+        self.use_planes = True
+        self._plane_params = None
 
     def _state_of(self, p: torch.Tensor) -> torch.Tensor:
         s = self.state.get(id(p))
@@ -248,6 +252,26 @@ class FusedTrainer:
         sink.defer = self.defer_sparse
         run = Run(tape, sparse_sink=sink)
         cat = cat_x if cat_x.dtype == torch.int64 else cat_x.long()
+        eng.PLANES = self._planes()            # forward and dgrad GEMMs fetch pre-split weight planes by TMA
+        try:
+            return self._forward_backward(model, run, tape, sink, int_x, cat, y, macro, micro, grad_scale)
+        finally:
+            eng.PLANES = None
+
+    def _planes(self):
+        """The model's PlaneCache with every dense 2-D weight's planes in step (apply() keeps them so; anything else that
+        touched a weight is noticed through Tensor._version / data_ptr / the library's epoch and rebuilt here)."""
+        if not self.use_planes:
+            return None
+        from ..planes import PlaneCache
+        cache = PlaneCache.of(self.model)
+        if self._plane_params is None:
+            emb = {id(m.weight) for m in self.model._embedding}
+            self._plane_params = [p for p in self.model.parameters() if id(p) not in emb and PlaneCache.wanted(p)]
+        cache.sync(self._plane_params)
+        return cache
+
+    def _forward_backward(self, model, run, tape, sink, int_x, cat, y, macro, micro, grad_scale):
         logits = model._run_network(run, Var(int_x.contiguous()), cat.contiguous(), macro, micro)
         loss, dl = eng.bce_with_logits(logits.t, y, grad_scale=grad_scale)
         logits.g = dl
@@ -289,10 +313,27 @@ class FusedTrainer:
         else:
             coef = None
         if dense:
-            _lib.call("nasrec_adagrad_multi", _lib.ptr_array([h.t.data_ptr() for h in dense]),
-                      _lib.ptr_array([h.g.data_ptr() for h in dense]),
-                      _lib.ptr_array([self._state_of(h.p).data_ptr() for h in dense]), _lib.i64_array(sizes),
-                      len(dense), float(lr), float(self.eps), coef)
+            cache = None
+            if self.use_planes:
+                from ..planes import PlaneCache
+                cache = self.model.__dict__.get(PlaneCache.ATTR)
+            pls = [cache.planes(h.p) if cache is not None else None for h in dense]
+            if any(pl is not None for pl in pls):
+                # same update, and the hi / lo planes of every tensor that has them are rewritten in the same pass
+                _lib.call("nasrec_adagrad_multi_planes", _lib.ptr_array([h.t.data_ptr() for h in dense]),
+                          _lib.ptr_array([h.g.data_ptr() for h in dense]),
+                          _lib.ptr_array([self._state_of(h.p).data_ptr() for h in dense]), _lib.i64_array(sizes),
+                          len(dense), float(lr), float(self.eps), coef,
+                          _lib.ptr_array([pl[0].data_ptr() if pl else 0 for pl in pls]),
+                          _lib.ptr_array([pl[1].data_ptr() if pl else 0 for pl in pls]),
+                          _lib.i32_array([h.t.shape[1] if (pl and h.t.dim() == 2) else 0 for h, pl in zip(dense, pls)]),
+                          _lib.i32_array([pl[3] if pl else 0 for pl in pls]),
+                          _lib.i64_array([pl[2] if pl else 0 for pl in pls]))
+            else:
+                _lib.call("nasrec_adagrad_multi", _lib.ptr_array([h.t.data_ptr() for h in dense]),
+                          _lib.ptr_array([h.g.data_ptr() for h in dense]),
+                          _lib.ptr_array([self._state_of(h.p).data_ptr() for h in dense]), _lib.i64_array(sizes),
+                          len(dense), float(lr), float(self.eps), coef)
         if sparse is not None:
             tp, sp = self._emb_tables()
             _lib.call("nasrec_emb_rowwise_adagrad", sparse.uniq.data_ptr(), sparse.nuniq.data_ptr(),
