@@ -368,25 +368,12 @@ nasrec_gemm::TilePlan plan_launch(const Prob* prob, int nprob, KTiles ktiles_of,
     }
     static const int kinds = getenv("NASREC_SPLIT_KINDS") ? atoi(getenv("NASREC_SPLIT_KINDS")) : 7;      // experiment knob
     if (!((kinds >> g_plan_kind) & 1)) eligible = false;
-    static const int lo = getenv("NASREC_SPLIT_LO") ? atoi(getenv("NASREC_SPLIT_LO")) : -1;
-    static const int hi = getenv("NASREC_SPLIT_HI") ? atoi(getenv("NASREC_SPLIT_HI")) : 1 << 30;
-    static int counter = 0;
-    if (lo >= 0 && eligible) {
-        const int id = counter++;
-        if (id < lo || id >= hi) eligible = false;
-        else if (getenv("NASREC_SPLIT_VERBOSE"))
-            fprintf(stderr, "split launch %d kind %d nprob %d M %d N %d maxN %d\n", id, g_plan_kind, nprob, prob[0].M, prob[0].N, maxN);
-    }
     // SM budget of backward launches (experiment knob; measured: planning the two backward streams for half of the SMs
     // each changes nothing on the B = 512 step, 1.566 vs 1.574 ms).  Must not depend on whether a side stream is attached:
     // the Python engine and the executor have to plan -- and round -- alike.
     static const int bwd_sms = getenv("NASREC_BWD_SMS") ? atoi(getenv("NASREC_BWD_SMS")) : nasrec_gemm::TC_SM_COUNT;
     const int budget = g_plan_kind != 0 ? bwd_sms : nasrec_gemm::TC_SM_COUNT;
-    const nasrec_gemm::TilePlan pl = nasrec_gemm::tc_plan(prob, nprob, maxN, ktiles_of, eligible, g_plan_kind, budget);
-    if (lo >= 0 && eligible && getenv("NASREC_SPLIT_VERBOSE"))
-        fprintf(stderr, "   plan bn %d ns %d ktiles %d nterm %d c %p ldc %lld bias %p addend %p\n", pl.bn, pl.ns, ktiles_of(0), prob[0].nterm,
-                (void*)prob[0].c, (long long)prob[0].c_hi_i, (const void*)prob[0].bias, (const void*)prob[0].addend);
-    return pl;
+    return nasrec_gemm::tc_plan(prob, nprob, maxN, ktiles_of, eligible, g_plan_kind, budget);
 }
 
 // LDG-producer kernel: the split CTAs write partial tiles to the library workspace and a fixed-order reduction launch
@@ -712,7 +699,6 @@ int run_tma(Job& job, cudaStream_t st, RedBatch* extra_rb = nullptr) {
         for (int t = 0; t < tb.prob[0].nterm; ++t) k += tb.term[tb.prob[0].term0 + t].K;
         g_prof.desc[prof.slot] = GemmProf::Desc{tb.prob[0].M, maxN, k, tb.nprob, g_plan_kind, pl.bn, pl.ns, 1};
     }
-    if (getenv("NASREC_WGRAD_VERBOSE") && tb.flat) fprintf(stderr, "   plan bn %d ns %d\n", pl.bn, pl.ns);
     tb.cluster_ns = pl.ns;             // split-K inside thread-block clusters (DSMEM reduction in the kernel)
     if (pl.ns > 1) totz *= pl.ns;      // eligible launches have nsplit == 1 everywhere: z = problem * ns + split
     tb.nprod = g_gemm_mode;
@@ -877,12 +863,6 @@ int wgrad_flush(cudaStream_t st) {
         }
         tb.nprob = np;
         tb.flat = 1;
-        if (getenv("NASREC_WGRAD_VERBOSE")) {
-            fprintf(stderr, "wgrad batch: %d problems, %d maps\n", np, job.nmap);
-            for (int q = 0; q < np; ++q)
-                fprintf(stderr, "   M %d N %d K %d c %p ldc %lld a %d b %d\n", tb.prob[q].M, tb.prob[q].N, tb.term[q].K, (void*)tb.prob[q].c,
-                        (long long)tb.prob[q].c_hi_i, tb.term[q].a_hi, tb.term[q].b_hi);
-        }
         rc = np ? run_tma(job, st) : NASREC_EINVAL;
     }
     g_wq.clear();
