@@ -113,7 +113,10 @@ int nasrec_planes_refresh(const float* W, int64_t ldw, int rows, int cols, int f
  * stops, synchronises on the events and writes {total ms, launches, flops} to out3 (host doubles). */
 int nasrec_gemm_prof(int what, double* out3);
 /* Host-side launch accounting: what = 1 starts (and clears), 0 stops, 2 returns the nanoseconds spent inside
- * cudaLaunchKernelEx since the start, 3 the number of launches. */
+ * cudaLaunchKernelEx since the start, 3 the number of launches; what = 4 returns the number of kernels the library has
+ * launched since it was loaded (always counted: bench.py's gpu_launches); what = 10 starts the per-kernel device trace
+ * (a CUDA-event pair around every launch), 11 stops it, appends `name launches total_us` lines to $NASREC_TRACE_FILE and
+ * returns the number of traced launches. */
 int64_t nasrec_host_prof(int what);
 /* which = 0: tensor-map cache hits, 1: tensor maps encoded, 2: GEMM launches that took the TMA path */
 int64_t nasrec_tensor_map_stats(int which);

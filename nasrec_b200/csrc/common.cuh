@@ -86,6 +86,7 @@ __device__ __forceinline__ void pdl_enter() {
 
 // host-side launch accounting (nasrec_host_prof): nanoseconds spent inside cudaLaunchKernelEx and the number of launches
 extern long long g_nasrec_launch_ns, g_nasrec_launch_count;
+extern long long g_nasrec_launch_total;      // every kernel launch of the library since load (nasrec_host_prof(4))
 extern int g_nasrec_host_prof;
 // device-side trace (nasrec_host_prof(10 / 11)): CUDA events around EVERY kernel launch of the library on its own stream,
 // aggregated by kernel name -- per-kernel time inside the real step (warm L2, both streams), which ncu's serialised
@@ -121,6 +122,7 @@ static inline cudaError_t nasrec_launch_cluster(void (*kernel)(KArgs...), dim3 g
         attr[1].val.clusterDim.z = (unsigned)cluster_z;
         cfg.numAttrs = 2;
     }
+    ++g_nasrec_launch_total;
     if (g_nasrec_trace) {
         nasrec_trace_begin(reinterpret_cast<const void*>(kernel), st);
         const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
@@ -150,6 +152,7 @@ static inline cudaError_t nasrec_launch(void (*kernel)(KArgs...), dim3 grid, dim
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    ++g_nasrec_launch_total;
     if (g_nasrec_trace) {
         nasrec_trace_begin(reinterpret_cast<const void*>(kernel), st);
         const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

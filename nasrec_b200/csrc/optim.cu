@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-long long g_nasrec_launch_ns = 0, g_nasrec_launch_count = 0;
+long long g_nasrec_launch_ns = 0, g_nasrec_launch_count = 0, g_nasrec_launch_total = 0;
 int g_nasrec_host_prof = 0;
 int g_nasrec_trace = 0;
 
@@ -280,6 +280,7 @@ int64_t nasrec_host_prof(int what) {
         case 0: g_nasrec_host_prof = 0; return 0;
         case 1: g_nasrec_host_prof = 1; g_nasrec_launch_ns = 0; g_nasrec_launch_count = 0; return 0;
         case 2: return g_nasrec_launch_ns;
+        case 4: return g_nasrec_launch_total;      // kernels launched by the library since it was loaded (always counted)
         case 10: g_nasrec_trace = 1; g_trace_used = 0; return 0;
         case 11: {            // stop; synchronise; append "name launches total_us" lines to $NASREC_TRACE_FILE; returns launches
             g_nasrec_trace = 0;
