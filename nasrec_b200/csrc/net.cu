@@ -16,6 +16,7 @@
 #include <new>
 #include <stdexcept>
 #include <vector>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -23,7 +24,7 @@ namespace {
 constexpr int E = NASREC_EMB_DIM;
 constexpr int GROUPS = 8;            // DS_INTERACT_NUM_SPLITS (supernet.py:49)
 constexpr float LN_EPS = 1e-5f;
-constexpr int BIG_REDUCE_ROWS = 2048;   // above this many ids per table the multi-CTA sorted-row reduction takes over (measured crossover, tools/sort_reduce_prof.py: 121 vs 134 us at 2048, 235 vs 164 us at 4096; up to it one CTA per table, radix sort from 1024)
+const int BIG_REDUCE_ROWS = getenv("NASREC_BIG_REDUCE_ROWS") ? atoi(getenv("NASREC_BIG_REDUCE_ROWS")) : 2048;   // above this many ids per table the multi-CTA sorted-row reduction takes over (measured crossover, tools/sort_reduce_prof.py: 121 vs 134 us at 2048, 235 vs 164 us at 4096; up to it one CTA per table, radix sort from 1024)
 
 struct OutOfArena : std::runtime_error { OutOfArena() : std::runtime_error("arena") {} };
 struct CallFailed : std::runtime_error { int rc; explicit CallFailed(int r) : std::runtime_error("call"), rc(r) {} };
