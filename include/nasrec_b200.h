@@ -89,6 +89,10 @@ int nasrec_set_gemm_tma(int on);
  * drops the queue (flush first).  nasrec_wgrad_defer returns the previous setting; nasrec_wgrad_pending the queue length.
  * The step executor (nasrec_net_forward_backward) does this by itself unless nasrec_net_set_defer_wgrad(net, 0). */
 int nasrec_wgrad_defer(int on);
+/* Host-only diagnostic: the tile width (16 / 32 / 64 / 128 output columns per CTA) and the split-K factor (1 / 2 / 4 / 8 CTAs
+ * of a thread-block cluster per output tile) the planner picks for `nprob` row-major problems [M x N x K] of one launch;
+ * kind: 0 forward, 1 dgrad, 2 wgrad operand layouts.  Needs no GPU. */
+int nasrec_gemm_plan(int kind, int M, int N, int K, int nprob, int* bn, int* ns);
 int nasrec_wgrad_flush(void* stream);
 int64_t nasrec_wgrad_pending(void);
 /* Contractions of at most `k` elements (one or two k-tiles: 13 dense features, 16-wide FM / DotProduct projections, 26..64

@@ -80,7 +80,7 @@ _SIGS_I64["nasrec_tensor_map_stats"] = [_i]
 _SIGS_I64["nasrec_host_prof"] = [_i]
 _SIGS_I64["nasrec_wgrad_pending"] = []
 EXPORTS = ["nasrec_version", "nasrec_set_gemm_mode", "nasrec_get_gemm_mode", "nasrec_set_workspace",
-           "nasrec_set_side_stream", "nasrec_side_join", "nasrec_set_gemm_tma", "nasrec_set_small_k", "nasrec_wgrad_defer",
+           "nasrec_set_side_stream", "nasrec_side_join", "nasrec_set_gemm_tma", "nasrec_set_small_k", "nasrec_wgrad_defer", "nasrec_gemm_plan",
            "nasrec_set_weight_planes", "nasrec_gemm_prof"] + list(_SIGS) + list(_SIGS_I64)
 
 
@@ -120,6 +120,8 @@ class _Lib:
         self.cdll.nasrec_get_gemm_mode.restype = C.c_int
         self.cdll.nasrec_set_gemm_tma.argtypes = [C.c_int]
         self.cdll.nasrec_set_gemm_tma.restype = C.c_int
+        self.cdll.nasrec_gemm_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self.cdll.nasrec_gemm_plan.restype = C.c_int
         self.cdll.nasrec_wgrad_defer.argtypes = [C.c_int]
         self.cdll.nasrec_wgrad_defer.restype = C.c_int
         self.cdll.nasrec_set_small_k.argtypes = [C.c_int]
@@ -151,6 +153,14 @@ class _Lib:
         """TMA-fed operand path of the tensor-core GEMM on/off (both paths agree bit for bit)."""
         self.load()
         self.cdll.nasrec_set_gemm_tma(1 if on else 0)
+
+    def gemm_plan(self, kind: int, M: int, N: int, K: int, nprob: int = 1) -> Tuple[int, int]:
+        """(tile width, split-K factor) the planner picks for a launch of `nprob` [M x N x K] problems (host only)."""
+        self.load()
+        bn, ns = C.c_int(0), C.c_int(0)
+        if self.cdll.nasrec_gemm_plan(kind, M, N, K, nprob, C.byref(bn), C.byref(ns)) != 0:
+            raise ValueError("nasrec_gemm_plan rejected its arguments")
+        return bn.value, ns.value
 
     def set_small_k(self, k: int) -> int:
         """Largest contraction length served by the CUDA-core kernel instead of the tensor-core pipeline (0 = never)."""

@@ -1380,6 +1380,25 @@ int nasrec_gemm_prof(int what, double* out3) {
     return 0;
 }
 
+int nasrec_gemm_plan(int kind, int M, int N, int K, int nprob, int* bn, int* ns) {
+    // host-only: the (tile width, split-K) the planner picks for `nprob` plain row-major problems of this shape
+    if (kind < 0 || kind > 2 || M <= 0 || N <= 0 || K <= 0 || nprob <= 0 || nprob > MAXP || !bn || !ns) return NASREC_EINVAL;
+    Prob prob[MAXP] = {};
+    for (int p = 0; p < nprob; ++p) {
+        prob[p].M = M;
+        prob[p].N = N;
+        prob[p].nsplit = 1;
+        prob[p].c_hi_j = 1;
+    }
+    const int saved = g_plan_kind;
+    g_plan_kind = kind;
+    const nasrec_gemm::TilePlan pl = plan_launch(prob, nprob, [&](int) { return (K + 31) / 32; }, N);
+    g_plan_kind = saved;
+    *bn = pl.bn;
+    *ns = pl.ns;
+    return 0;
+}
+
 int nasrec_wgrad_defer(int on) {
     const int old = g_wdefer ? 1 : 0;
     g_wdefer = on != 0;

@@ -274,3 +274,33 @@ def test_public_header_is_plain_c():
     assert r.returncode == 0, r.stderr
     code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)          # declarations only, comments stripped
     assert "torch" not in code.lower() and "at::" not in code and "std::" not in code and "Tensor" not in code
+
+
+def test_gemm_planner_invariants_and_pinned_choices():
+    """Host-only: the tile-width / split-K planner of the tensor-core GEMMs (csrc/gemm_tc.cuh tc_plan, through the
+    nasrec_gemm_plan diagnostic).  Invariants that numerics and the kernels rely on, and the measured choices for the
+    headline shapes (profiles/r02_gemm.md) so that an accidental change of the cost tables shows up without a GPU."""
+    from nasrec_b200 import _lib
+    L = _lib.LIB
+    for kind in (0, 1, 2):
+        for M in (1, 64, 512, 1000, 8192):
+            for N in (1, 13, 16, 45, 64, 128, 1024, 1037):
+                for K in (13, 64, 416, 1037, 4109, 8192):
+                    for nprob in (1, 3):
+                        bn, ns = L.gemm_plan(kind, M, N, K, nprob)
+                        kt = (K + 31) // 32
+                        assert bn in (16, 32, 64, 128) and ns in (1, 2, 4, 8)
+                        assert (bn == 16) == (N <= 16)                      # 16-wide tiles exactly for N <= 16
+                        assert bn < 2 * max(N, 17)                          # never a tile more than twice as wide as the output
+                        if ns > 1:
+                            assert kt >= 2 * ns                             # every CTA of a cluster walks at least two k-tiles
+                        if bn == 128:
+                            assert -(-kt // ns) <= 16                       # two accumulators: bounded MMA chain (fp32 truncation)
+    # measured best plans (us per launch in profiles/r02_gemm.md): skinny forward splits K four ways over 128-wide tiles,
+    # a large-M forward does not split, a tiny-K launch has nothing to split
+    assert L.gemm_plan(0, 512, 1024, 1037) == (128, 4)
+    assert L.gemm_plan(0, 8192, 1024, 1037) == (64, 1)
+    assert L.gemm_plan(0, 512, 1024, 16) == (32, 1)
+    assert L.gemm_plan(2, 1024, 1037, 512, 2)[1] == 1
+    with pytest.raises(ValueError):
+        L.gemm_plan(3, 512, 1024, 1037)
