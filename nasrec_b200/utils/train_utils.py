@@ -144,6 +144,15 @@ def train_and_test_one_epoch(model, epoch: int, optimizer, lr_scheduler, train_l
     logs = {k: [] for k in ("train_loss", "train_AUROC", "train_Accuracy", "test_loss", "test_AUROC", "test_Accuracy",
                             "epoch", "iters")}
     fused = isinstance(optimizer, FusedTrainer)
+    if fused and l2_loss_fn is not None:
+        # The fused step has no L2 term (train_utils.py:283 adds get_l2_loss to the loss; main_train.py:317 defaults
+        # --wd to 1e-8).  Training on without it would silently differ from the reference: refuse instead.
+        with torch.no_grad():
+            l2_now = float(l2_loss_fn(model))
+        if l2_now != 0.0:
+            raise ValueError("the fused step (FusedTrainer / NativeTrainer) has no weight-decay term but l2_loss_fn(model) = %g; "
+                             "pass wd = 0 (l2_loss_fn=None) or a torch optimizer, which runs the reference's own step "
+                             "body including the L2 loss" % l2_now)
     model.train()
     for batch_num, (int_x, cat_x, y) in enumerate(train_loader):
         int_x, cat_x, y = (t.to(gpu, non_blocking=True) for t in (int_x, cat_x, y))

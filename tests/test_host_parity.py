@@ -304,3 +304,19 @@ def test_gemm_planner_invariants_and_pinned_choices():
     assert L.gemm_plan(2, 1024, 1037, 512, 2)[1] == 1
     with pytest.raises(ValueError):
         L.gemm_plan(3, 512, 1024, 1037)
+
+
+def test_fused_trainer_refuses_nonzero_weight_decay():
+    """train_utils.py:283 / main_train.py:317: the reference adds get_l2_loss (default wd 1e-8) to the loss.  The fused
+    step has no such term, so the mirrored loop must refuse a nonzero L2 loss rather than train without it."""
+    import torch
+    from nasrec_b200.utils import train_utils as tu
+    model = torch.nn.Linear(4, 3)
+    fused = object.__new__(tu.FusedTrainer)                      # no CUDA needed: the check precedes any device work
+    with pytest.raises(ValueError, match="weight-decay"):
+        tu.train_and_test_one_epoch(model, 0, fused, None, [], [], torch.nn.BCEWithLogitsLoss(),
+                                    lambda m: tu.get_l2_loss(m, 1e-8, None, gpu="cpu"), 8, "cpu")
+    # wd = 0 passes the check (and, with no batches, the loop is empty)
+    logs = tu.train_and_test_one_epoch(model, 0, fused, None, [], [], torch.nn.BCEWithLogitsLoss(),
+                                       lambda m: tu.get_l2_loss(m, 0, None, gpu="cpu"), 8, "cpu")
+    assert logs["train_loss"] == []
