@@ -11,6 +11,7 @@
 // exp(score) to every softmax denominator, exactly as in the reference, which
 // passes no key-padding mask (modules.py:653-664).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -38,7 +39,11 @@ __device__ __forceinline__ float score(float q0, float q1, float k0, float k1) {
 }
 
 // y = W x + b for a 16x16 row-major W in shared memory
+// The compiler barrier in front of each 16x16 product matters: without it the 256 shared-memory loads of every product
+// of a thread's chain are hoisted above the first shared-memory store of the chain (they may alias it) and ~770 values
+// are spilled to local memory and read back one per FMA (ptxas: 5 KB of spill traffic per thread, profiles/r02_sass.md).
 __device__ __forceinline__ void matvec16(const float* W, const float* b, const float* x, float* y) {
+    asm volatile("" ::: "memory");
 #pragma unroll
     for (int c = 0; c < E; ++c) {
         float acc = b[c];
@@ -50,6 +55,7 @@ __device__ __forceinline__ void matvec16(const float* W, const float* b, const f
 
 // y = W^T x
 __device__ __forceinline__ void matvec16_t(const float* W, const float* x, float* y) {
+    asm volatile("" ::: "memory");
 #pragma unroll
     for (int e = 0; e < E; ++e) y[e] = 0.f;
 #pragma unroll
@@ -112,6 +118,23 @@ __device__ __forceinline__ void token_qkv(const float* P, const float* x, float*
     }
 }
 
+// everything behind the attention output f.o for one live token: out_proj, residual + LN, FC-ReLU-FC, residual + LN
+__device__ __forceinline__ void token_tail(const float* P, Fwd& f) {
+    float a[E], r[E];
+    matvec16(P + OUT_W, P + OUT_B, f.o, a);
+#pragma unroll
+    for (int e = 0; e < E; ++e) r[e] = a[e] + f.x[e];
+    ln16(r, P + LN1_W, P + LN1_B, f.xh1, f.rstd1, f.h1);
+    float pre[E], f2[E];
+    matvec16(P + FC1_W, P + FC1_B, f.h1, pre);
+#pragma unroll
+    for (int e = 0; e < E; ++e) f.f1[e] = fmaxf(pre[e], 0.f);
+    matvec16(P + FC2_W, P + FC2_B, f.f1, f2);
+#pragma unroll
+    for (int e = 0; e < E; ++e) r[e] = f.h1[e] + f2[e];
+    ln16(r, P + LN2_W, P + LN2_B, f.xh2, f.rstd2, f.y);
+}
+
 // attention + the two residual/LN stages for one live token (needs Ks/Vs complete)
 __device__ __forceinline__ void token_rest(const float* P, const float* Ks, const float* Vs, int L, Fwd& f) {
 #pragma unroll
@@ -131,19 +154,7 @@ __device__ __forceinline__ void token_rest(const float* P, const float* Ks, cons
         f.o[2 * h] = o0 / sum;
         f.o[2 * h + 1] = o1 / sum;
     }
-    float a[E], r[E];
-    matvec16(P + OUT_W, P + OUT_B, f.o, a);
-#pragma unroll
-    for (int e = 0; e < E; ++e) r[e] = a[e] + f.x[e];
-    ln16(r, P + LN1_W, P + LN1_B, f.xh1, f.rstd1, f.h1);
-    float pre[E], f2[E];
-    matvec16(P + FC1_W, P + FC1_B, f.h1, pre);
-#pragma unroll
-    for (int e = 0; e < E; ++e) f.f1[e] = fmaxf(pre[e], 0.f);
-    matvec16(P + FC2_W, P + FC2_B, f.f1, f2);
-#pragma unroll
-    for (int e = 0; e < E; ++e) r[e] = f.h1[e] + f2[e];
-    ln16(r, P + LN2_W, P + LN2_B, f.xh2, f.rstd2, f.y);
+    token_tail(P, f);
 }
 
 __device__ __forceinline__ void load_row16(const float* p, float* v) {
@@ -422,6 +433,307 @@ __global__ void __launch_bounds__(LMAX) attn_bwd_kernel(const float* __restrict_
     for (int i = t; i < NPARAM; i += LMAX) ws[(long long)blockIdx.x * NPARAM + i] = PG[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Four threads per token (round 2).  One thread per token leaves a sample with two warps walking ~25 000 dependent
+// instructions each (backward: 168 registers + 5 KB of spills, 124 us per launch at B = 256).  Three quarters of that
+// are the per-head loops over the keys, and heads are independent: thread (t, hq) of a 256-thread CTA owns heads 2*hq
+// and 2*hq + 1 of token t in every pass over keys / queries, a quarter of the in-projection outputs and a quarter of
+// the dX columns; only the 16-wide tail (out_proj, LayerNorms, FFN and their backward) stays with thread (t, 0).
+// Every sum keeps the order of the one-thread-per-token kernels above, which stay selectable (NASREC_ATTN_OLD=1).
+constexpr int NT4 = 4 * LMAX;
+
+// in-projection outputs 12*hq .. 12*hq + 11 of token t (q | k | v rows of in_proj_weight)
+__device__ __forceinline__ void qkv_quarter(const float* P, const float* x, float* Qs, float* Ks, float* Vs, int t,
+                                            int hq) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const int c = 12 * hq + i;
+        float acc = P[IN_B + c];
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc = fmaf(P[IN_W + c * E + e], x[e], acc);
+        float* dst = c < E ? Qs : (c < 2 * E ? Ks : Vs);
+        dst[t * ST + (c & (E - 1))] = acc;
+    }
+}
+
+// softmax(q k^T / sqrt 2) v for heads 2*hq, 2*hq + 1 of query token t; q4 / o4: [head][2], m2 / l2: row max / sum
+__device__ __forceinline__ void heads_fwd(const float* Qs, const float* Ks, const float* Vs, int L, int t, int hq,
+                                          float* q4, float* o4, float* m2, float* l2) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int h = 2 * hq + hh;
+        const float q0 = Qs[t * ST + 2 * h], q1 = Qs[t * ST + 2 * h + 1];
+        float mx = -INFINITY;
+        for (int j = 0; j < L; ++j) mx = fmaxf(mx, score(q0, q1, Ks[j * ST + 2 * h], Ks[j * ST + 2 * h + 1]));
+        float sum = 0.f, o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float p = expf(score(q0, q1, Ks[j * ST + 2 * h], Ks[j * ST + 2 * h + 1]) - mx);
+            sum += p;
+            o0 = fmaf(p, Vs[j * ST + 2 * h], o0);
+            o1 = fmaf(p, Vs[j * ST + 2 * h + 1], o1);
+        }
+        q4[2 * hh] = q0;
+        q4[2 * hh + 1] = q1;
+        m2[hh] = mx;
+        l2[hh] = sum;
+        o4[2 * hh] = o0 / sum;
+        o4[2 * hh + 1] = o1 / sum;
+    }
+}
+
+__global__ void __launch_bounds__(NT4) attn_fwd4_kernel(const float* __restrict__ x, long long xbs, int L, int s_live,
+                                                        const __grid_constant__ AttnPtrs ap, float* __restrict__ y,
+                                                        long long ybs, int B) {
+    pdl_enter();
+    __shared__ float P[NPARAM];
+    __shared__ float Ks[LMAX * ST], Vs[LMAX * ST], Qs[LMAX * ST], Os[LMAX * ST];
+    const int tid = threadIdx.x, t = tid & (LMAX - 1), hq = tid >> 6;
+    load_params(P, ap, tid, NT4);
+    __syncthreads();
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const bool active = t < L, live = t < s_live;
+        Fwd f;
+        if (live) load_row16(x + (long long)b * xbs + t * E, f.x);
+        else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) f.x[e] = 0.f;
+        }
+        if (active) qkv_quarter(P, f.x, Qs, Ks, Vs, t, hq);
+        __syncthreads();
+        if (live) {
+            float q4[4], o4[4], m2[2], l2[2];
+            heads_fwd(Qs, Ks, Vs, L, t, hq, q4, o4, m2, l2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) Os[t * ST + 4 * hq + k] = o4[k];
+        }
+        __syncthreads();
+        // the tail reads Os, P and registers only; the next sample's first phase writes Qs / Ks / Vs, and Os is not
+        // written again before the barrier behind that phase, so no third barrier is needed
+        if (live && hq == 0) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) f.o[e] = Os[t * ST + e];
+            token_tail(P, f);
+            store_row16(y + (long long)b * ybs + t * E, f.y);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NT4, 2) attn_bwd4_kernel(const float* __restrict__ dy, long long dybs,
+                                                        const float* __restrict__ x, long long xbs, int L, int s_live,
+                                                        const __grid_constant__ AttnPtrs ap, float* __restrict__ dx,
+                                                        long long dxbs, float* __restrict__ ws, int B) {
+    pdl_enter();
+    extern __shared__ float sm[];
+    float* P = sm + S_P;
+    float *Ks = sm + S_KS, *Vs = sm + S_VS, *Qs = sm + S_QS, *DOs = sm + S_DOS;
+    float *Ms = sm + S_MS, *Ls = sm + S_LS, *Ds = sm + S_DS;
+    float* PG = sm + S_PG;
+    float* DQKV = sm + S_DQKV;
+    const int tid = threadIdx.x, t = tid & (LMAX - 1), hq = tid >> 6;
+    load_params(P, ap, tid, NT4);
+    for (int i = tid; i < NPARAM; i += NT4) PG[i] = 0.f;
+    __syncthreads();
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const bool active = t < L, live = t < s_live;
+        Fwd f;                                        // thread (t, 0) uses all of it, the others only f.x
+        if (live) load_row16(x + (long long)b * xbs + t * E, f.x);
+        else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) f.x[e] = 0.f;
+        }
+        if (active) qkv_quarter(P, f.x, Qs, Ks, Vs, t, hq);
+        if (live && hq == 0) put16(sm + S_X, t, f.x);
+        __syncthreads();
+        // ---- forward attention of my two heads; my token's k / v of those heads for pass B
+        float q4[4], o4[4], m2[2], l2[2], k4[4], v4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            k4[k] = active ? Ks[t * ST + 4 * hq + k] : 0.f;
+            v4[k] = active ? Vs[t * ST + 4 * hq + k] : 0.f;
+            q4[k] = 0.f;
+            o4[k] = 0.f;
+        }
+        m2[0] = m2[1] = 0.f;
+        l2[0] = l2[1] = 1.f;
+        if (live) {
+            heads_fwd(Qs, Ks, Vs, L, t, hq, q4, o4, m2, l2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sm[S_O + t * ST + 4 * hq + k] = o4[k];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                Ms[t * 9 + 2 * hq + hh] = m2[hh];
+                Ls[t * 9 + 2 * hq + hh] = l2[hh];
+            }
+        }
+        __syncthreads();
+        // ---- the 16-wide tail and its backward, one thread per token
+        if (live && hq == 0) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) f.o[e] = sm[S_O + t * ST + e];
+            token_tail(P, f);
+            float g[E], dr2[E], df1[E], dh1[E], tmp[E], da[E], dout[E];
+            load_row16(dy + (long long)b * dybs + t * E, g);
+            // LN2
+            ln16_bwd(g, f.xh2, f.rstd2, P + LN2_W, dr2);
+#pragma unroll
+            for (int e = 0; e < E; ++e) tmp[e] = g[e] * f.xh2[e];
+            put16(sm + S_GX2, t, tmp);
+            put16(sm + S_DY, t, g);
+            // fc2 / relu / fc1
+            matvec16_t(P + FC2_W, dr2, df1);
+#pragma unroll
+            for (int e = 0; e < E; ++e) df1[e] = f.f1[e] > 0.f ? df1[e] : 0.f;
+            matvec16_t(P + FC1_W, df1, dh1);
+#pragma unroll
+            for (int e = 0; e < E; ++e) dh1[e] += dr2[e];
+            put16(sm + S_DF2, t, dr2);
+            put16(sm + S_F1, t, f.f1);
+            put16(sm + S_DF1, t, df1);
+            put16(sm + S_H1, t, f.h1);
+            // LN1
+            ln16_bwd(dh1, f.xh1, f.rstd1, P + LN1_W, da);
+#pragma unroll
+            for (int e = 0; e < E; ++e) tmp[e] = dh1[e] * f.xh1[e];
+            put16(sm + S_GX1, t, tmp);
+            put16(sm + S_DH1, t, dh1);
+            put16(sm + S_DA, t, da);                  // also the residual part of dX
+            // out_proj
+            matvec16_t(P + OUT_W, da, dout);
+#pragma unroll
+            for (int h = 0; h < H; ++h) Ds[t * 9 + h] = dout[2 * h] * f.o[2 * h] + dout[2 * h + 1] * f.o[2 * h + 1];
+            put16(DOs, t, dout);
+        }
+        __syncthreads();
+        // ---- pass A: dq_i = scale * sum_j dS_ij k_j for my two heads
+        float dq4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dq4[k] = 0.f;
+        if (live) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int h = 2 * hq + hh;
+                const float q0 = q4[2 * hh], q1 = q4[2 * hh + 1];
+                const float d0 = DOs[t * ST + 2 * h], d1 = DOs[t * ST + 2 * h + 1];
+                const float Dh = Ds[t * 9 + h];
+                const float inv_l = 1.f / l2[hh];
+                float a0 = 0.f, a1 = 0.f;
+                for (int j = 0; j < L; ++j) {
+                    const float k0 = Ks[j * ST + 2 * h], k1 = Ks[j * ST + 2 * h + 1];
+                    const float p = expf(score(q0, q1, k0, k1) - m2[hh]) * inv_l;
+                    const float dp = d0 * Vs[j * ST + 2 * h] + d1 * Vs[j * ST + 2 * h + 1];
+                    const float ds = p * (dp - Dh);
+                    a0 = fmaf(ds, k0, a0);
+                    a1 = fmaf(ds, k1, a1);
+                }
+                dq4[2 * hh] = a0 * SCALE;
+                dq4[2 * hh + 1] = a1 * SCALE;
+            }
+        }
+        // ---- pass B: as key / value token t, gather from every live query i (my two heads)
+        if (active) {
+            float dk4[4], dv4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                dk4[k] = 0.f;
+                dv4[k] = 0.f;
+            }
+            for (int i = 0; i < s_live; ++i) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int h = 2 * hq + hh;
+                    const float q0 = Qs[i * ST + 2 * h], q1 = Qs[i * ST + 2 * h + 1];
+                    const float d0 = DOs[i * ST + 2 * h], d1 = DOs[i * ST + 2 * h + 1];
+                    const float p = expf(score(q0, q1, k4[2 * hh], k4[2 * hh + 1]) - Ms[i * 9 + h]) / Ls[i * 9 + h];
+                    const float dp = d0 * v4[2 * hh] + d1 * v4[2 * hh + 1];
+                    const float ds = p * (dp - Ds[i * 9 + h]) * SCALE;
+                    dk4[2 * hh] = fmaf(ds, q0, dk4[2 * hh]);
+                    dk4[2 * hh + 1] = fmaf(ds, q1, dk4[2 * hh + 1]);
+                    dv4[2 * hh] = fmaf(p, d0, dv4[2 * hh]);
+                    dv4[2 * hh + 1] = fmaf(p, d1, dv4[2 * hh + 1]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                DQKV[t * 49 + 4 * hq + k] = dq4[k];
+                DQKV[t * 49 + E + 4 * hq + k] = dk4[k];
+                DQKV[t * 49 + 2 * E + 4 * hq + k] = dv4[k];
+            }
+        }
+        __syncthreads();
+        // ---- dX columns 4*hq .. 4*hq + 3 of my token: residual + in_proj^T (dq | dk | dv)
+        if (live && dx) {
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = sm[S_DA + t * ST + 4 * hq + k];
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                const float dqc = DQKV[t * 49 + c], dkc = DQKV[t * 49 + E + c], dvc = DQKV[t * 49 + 2 * E + c];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int e = 4 * hq + k;
+                    o[k] = fmaf(P[IN_W + c * E + e], dqc, o[k]);
+                    o[k] = fmaf(P[IN_W + (E + c) * E + e], dkc, o[k]);
+                    o[k] = fmaf(P[IN_W + (2 * E + c) * E + e], dvc, o[k]);
+                }
+            }
+            *reinterpret_cast<float4*>(dx + (long long)b * dxbs + t * E + 4 * hq) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        // ---- parameter gradients: every PG element is owned by exactly one thread (three groups of threads)
+        if (tid < 48) {                               // one row of in_proj_weight + its bias element
+            float acc[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = 0.f;
+            float bsum = 0.f;
+            const float* X = sm + S_X;
+            for (int i = 0; i < L; ++i) {
+                const float d = DQKV[i * 49 + tid];
+                bsum += d;
+                if (i < s_live) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[e] = fmaf(d, X[i * ST + e], acc[e]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) PG[IN_W + tid * E + e] += acc[e];
+            PG[IN_B + tid] += bsum;
+        } else if (tid >= 64 && tid < 112) {          // one row of out_proj / fc1 / fc2 + its bias element
+            const int u = tid - 64, grp = u >> 4, c = u & 15;
+            const float* G = sm + (grp == 0 ? S_DA : (grp == 1 ? S_DF1 : S_DF2));
+            const float* A = sm + (grp == 0 ? S_O : (grp == 1 ? S_H1 : S_F1));
+            const int wofs = grp == 0 ? OUT_W : (grp == 1 ? FC1_W : FC2_W);
+            const int bofs = grp == 0 ? OUT_B : (grp == 1 ? FC1_B : FC2_B);
+            float acc[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = 0.f;
+            float bsum = 0.f;
+            for (int i = 0; i < s_live; ++i) {
+                const float d = G[i * ST + c];
+                bsum += d;
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[e] = fmaf(d, A[i * ST + e], acc[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) PG[wofs + c * E + e] += acc[e];
+            PG[bofs + c] += bsum;
+        } else if (tid >= 128 && tid < 144) {         // the two LayerNorms' gamma / beta
+            const int c = tid - 128;
+            float g1 = 0.f, b1 = 0.f, g2 = 0.f, b2 = 0.f;
+            for (int i = 0; i < s_live; ++i) {
+                g1 += sm[S_GX1 + i * ST + c];
+                b1 += sm[S_DH1 + i * ST + c];
+                g2 += sm[S_GX2 + i * ST + c];
+                b2 += sm[S_DY + i * ST + c];
+            }
+            PG[LN1_W + c] += g1;
+            PG[LN1_B + c] += b1;
+            PG[LN2_W + c] += g2;
+            PG[LN2_B + c] += b2;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < NPARAM; i += NT4) ws[(long long)blockIdx.x * NPARAM + i] = PG[i];
+}
+
 __global__ void attn_param_reduce_kernel(const float* __restrict__ ws, int nblk, float* __restrict__ dparams,
                                          int accumulate) {
     pdl_enter();
@@ -435,6 +747,15 @@ __global__ void attn_param_reduce_kernel(const float* __restrict__ ws, int nblk,
 int attn_grid(int B) {
     const int cap = 148 * 4;
     return B < cap ? B : cap;
+}
+
+// NASREC_ATTN_OLD=1: the one-thread-per-token kernels (A/B timing, tests of the two against each other)
+bool attn_old() {
+    static const bool v = [] {
+        const char* e = getenv("NASREC_ATTN_OLD");
+        return e && atoi(e) != 0;
+    }();
+    return v;
 }
 
 }  // namespace
@@ -455,8 +776,19 @@ int nasrec_attn_fwd(const float* x, int64_t x_bstride, int L, int s_live, const 
     CHECK_ARG(x && y && B > 0 && L > 0 && L <= LMAX && s_live > 0 && s_live <= L);
     AttnPtrs ap;
     if (fill_ptrs(ap, params)) return NASREC_EINVAL;
-    const int grid = B < 148 * 16 ? B : 148 * 16;
-    nasrec_launch(attn_fwd_kernel, grid, LMAX, 0, as_stream(stream), x, x_bstride, L, s_live, ap, y, y_bstride, B);
+    // forward: four threads per token while the batch cannot fill the SMs with 64-thread CTAs (latency regime); above
+    // that the one-thread-per-token kernel keeps more tokens in flight per SM (NASREC_ATTN_FWD4_MAXB, default 1024)
+    static const int fwd4_maxb = [] {
+        const char* e = getenv("NASREC_ATTN_FWD4_MAXB");
+        return e ? atoi(e) : 1024;
+    }();
+    if (attn_old() || B > fwd4_maxb) {
+        const int grid = B < 148 * 16 ? B : 148 * 16;
+        nasrec_launch(attn_fwd_kernel, grid, LMAX, 0, as_stream(stream), x, x_bstride, L, s_live, ap, y, y_bstride, B);
+    } else {
+        const int grid = B < 148 * 8 ? B : 148 * 8;
+        nasrec_launch(attn_fwd4_kernel, grid, NT4, 0, as_stream(stream), x, x_bstride, L, s_live, ap, y, y_bstride, B);
+    }
     return nasrec_launch_status();
 }
 
@@ -472,12 +804,17 @@ int nasrec_attn_bwd(const float* dy, int64_t dy_bstride, const float* x, int64_t
     const size_t smem = (size_t)S_TOTAL * sizeof(float);
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     const int grid = attn_grid(B);
     cudaStream_t st = as_stream(stream);
-    nasrec_launch(attn_bwd_kernel, grid, LMAX, smem, st, dy, dy_bstride, x, x_bstride, L, s_live, ap, dx, dx_bstride, ws, B);
+    if (attn_old())
+        nasrec_launch(attn_bwd_kernel, grid, LMAX, smem, st, dy, dy_bstride, x, x_bstride, L, s_live, ap, dx, dx_bstride, ws, B);
+    else
+        nasrec_launch(attn_bwd4_kernel, grid, NT4, smem, st, dy, dy_bstride, x, x_bstride, L, s_live, ap, dx, dx_bstride, ws, B);
     int rc = nasrec_launch_status();
     if (rc) return rc;
     if (dparams) {
