@@ -5,6 +5,7 @@
 // the FM reductions (:736-738), sigmoid/multiply (:580-582) and
 // _pad_2Dtensors_if_needed + torch.cat (:403-430).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -108,6 +109,41 @@ __global__ void __launch_bounds__(256) fm_bwd_kernel(const float* __restrict__ d
     for (int r = 0; r < rows; ++r) {
         const float v = g2 * (s - xp[r * 16]);
         op[r * 16] = ip ? ip[r * 16] + v : v;
+    }
+}
+
+// Same arithmetic with one CTA per sample: at B = 512 the kernel above is 32 CTAs whose threads each walk `rows`
+// strided loads twice, a few loads in flight at a time (14 us, ncu).  Here the CTA stages the sample's rows in shared
+// memory with one round of coalesced loads, 16 threads form the column sums in the same row order (so the result is
+// bit-identical) and all 256 threads write the rows.  dx_in may be dx (in-place accumulate): an element is read and
+// written by the same thread.
+constexpr int FM_ROWS_SMEM = 128;
+__global__ void __launch_bounds__(256) fm_bwd_rows_kernel(const float* __restrict__ dix, const float* __restrict__ x,
+                                                          long long xbs, int rows, const float* dx_in,
+                                                          long long dxin_bs, float* dx, long long dxbs, int B) {
+    pdl_enter();
+    __shared__ float X[FM_ROWS_SMEM * 16];
+    __shared__ float S[16];
+    const int e = threadIdx.x & 15, rg = threadIdx.x >> 4;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* xb = x + (long long)b * xbs;
+        for (int i = threadIdx.x; i < rows * 16; i += 256) X[i] = xb[i];
+        __syncthreads();
+        if (rg == 0) {
+            float s = 0.f;
+            for (int r = 0; r < rows; ++r) s += X[r * 16 + e];
+            S[e] = s;
+        }
+        __syncthreads();
+        const float s = S[e];
+        const float g2 = 2.f * dix[b * 16 + e];
+        float* op = dx + (long long)b * dxbs + e;
+        const float* ip = dx_in ? dx_in + (long long)b * dxin_bs + e : nullptr;
+        for (int r = rg; r < rows; r += 16) {
+            const float v = g2 * (s - X[r * 16 + e]);
+            op[r * 16] = ip ? ip[r * 16] + v : v;
+        }
+        __syncthreads();
     }
 }
 
@@ -230,7 +266,15 @@ int nasrec_fm_fwd(const float* x, int64_t x_bstride, int rows, float* ix, int B,
 int nasrec_fm_bwd(const float* dix, const float* x, int64_t x_bstride, int rows, const float* dx_in,
                   int64_t dxin_bstride, float* dx, int64_t dx_bstride, int B, void* stream) {
     CHECK_ARG(dix && x && dx && B > 0 && rows > 0);
-    nasrec_launch(fm_bwd_kernel, cdiv((long long)B * 16, 256), 256, 0, as_stream(stream), dix, x, x_bstride, rows, dx_in,
+    static const int rows_maxb = [] {                 // NASREC_FM_ROWS_MAXB=0: always the thread-per-column kernel
+        const char* e = getenv("NASREC_FM_ROWS_MAXB");
+        return e ? atoi(e) : 2048;
+    }();
+    if (B <= rows_maxb && rows <= FM_ROWS_SMEM)
+        nasrec_launch(fm_bwd_rows_kernel, B < 148 * 8 ? B : 148 * 8, 256, 0, as_stream(stream), dix, x, x_bstride, rows,
+                      dx_in, dxin_bstride, dx, dx_bstride, B);
+    else
+        nasrec_launch(fm_bwd_kernel, cdiv((long long)B * 16, 256), 256, 0, as_stream(stream), dix, x, x_bstride, rows, dx_in,
                                                                               dxin_bstride, dx, dx_bstride, B);
     return nasrec_launch_status();
 }

@@ -22,11 +22,21 @@ def _device_code():
     return body
 
 
-def _build(tmp_path):
-    (tmp_path / "attn_device_code.inc").write_text(_device_code())
-    exe = tmp_path / "attn_emul"
+def _fm_device_code():
+    src = open(os.path.join(ROOT, "nasrec_b200", "csrc", "interact.cu")).read()
+    a = src.index("namespace {")
+    b = src.index("// ------------------------------------------------------------------ gating / concat")
+    body = src[a:b]
+    assert "__shfl" not in body and "atomic" not in body
+    return body
+
+
+def _build(tmp_path, name="attn", code=None):
+    (tmp_path / ("%s_device_code.inc" % ("attn" if name == "attn" else "interact"))).write_text(code or _device_code())
+    exe = tmp_path / (name + "_emul")
     cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-pthread", "-I", str(tmp_path),
-           os.path.join(ROOT, "tests", "host_emul", "attn_emul.cpp"), "-o", str(exe)]
+           "-I", os.path.join(ROOT, "tests", "host_emul"),
+           os.path.join(ROOT, "tests", "host_emul", name + "_emul.cpp"), "-o", str(exe)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return exe
@@ -80,3 +90,12 @@ def test_four_threads_per_token_kernels_match_one_thread_per_token_kernels_and_t
     assert float((out.detach() - y).abs().max()) < 2e-5
     assert float((xr.grad - dx).abs().max()) < 1e-4 * max(1.0, float(xr.grad.abs().max()))
     assert float((ref - dpar).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_fm_backward_one_cta_per_sample_matches_thread_per_column_kernel(tmp_path):
+    """interact.cu: fm_bwd_rows_kernel (used up to B = 2048) against fm_bwd_kernel, bit for bit, incl. in-place accumulate."""
+    exe = _build(tmp_path, "fm", _fm_device_code())
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-1000:]
+    assert len(re.findall(r" 0 differ", r.stdout)) == 7
