@@ -99,3 +99,18 @@ def test_fm_backward_one_cta_per_sample_matches_thread_per_column_kernel(tmp_pat
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-1000:]
     assert len(re.findall(r" 0 differ", r.stdout)) == 7
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_dot_product_triangle_and_fm_kernels_match_the_reference_formulas(tmp_path):
+    """interact.cu on the host: DotProduct's strict lower triangle (tril_indices row-major order, modules.py:366-383) and
+    the FM reductions (modules.py:736-738), forward and backward, against direct double-precision evaluation."""
+    (tmp_path / "interact_device_code.inc").write_text(_fm_device_code())
+    exe = tmp_path / "interact_emul"
+    cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-pthread", "-I", str(tmp_path),
+           "-I", os.path.join(ROOT, "tests", "host_emul"),
+           os.path.join(ROOT, "tests", "host_emul", "interact_emul.cpp"), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-1000:]
